@@ -1,0 +1,88 @@
+/* B200-native batch extension of the A*PA2 C-ABI.
+ *
+ * The reference's C-ABI (astarpa-c/astarpa.h:15-65, one pair per call) cannot feed a GPU, so the single-pair
+ * symbols in include/astarpa.h are served by a batch engine whose entry points are declared here. Plain C:
+ * pointers and sizes only, no torch / CUDA types in any signature.
+ */
+#ifndef ASTARPA_B200_H
+#define ASTARPA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- synthetic input (stands in for pa-generate) */
+/* Error models: 0 Uniform, 1 NoisyInsert, 2 NoisyDelete, 3 SymmetricRepeat (pa-test/src/lib.rs:42-47). */
+int64_t apa_generate_pair(uint64_t n, double e, int model, uint64_t seed, uint8_t* a_out, uint8_t* b_out, uint64_t b_cap);
+int apa_generate_batch(uint64_t n_pairs, uint64_t n, double e, int model, uint64_t seed0, uint8_t* a_all, uint8_t* b_all,
+                       uint64_t b_stride, int64_t* b_len, int n_threads);
+
+/* ---------------------------------------------------------------- engine */
+#define APA_PRESET_SIMPLE 0 /* AstarPa2Params::simple(), astarpa2/src/params.rs:70-96  */
+#define APA_PRESET_FULL 1   /* AstarPa2Params::full(),   astarpa2/src/params.rs:98-128 */
+
+/* Error codes (negative return values). The reference has no error convention (a Rust panic aborts the
+ * process, astarpa-c/src/lib.rs:17-23); we return codes instead and never a wrong cost. */
+#define APA_OK 0
+#define APA_ERR_NO_DEVICE -1    /* CUDA runtime/driver/device unavailable: there is NO CPU fallback */
+#define APA_ERR_CUDA -2         /* a CUDA call failed; see apa_last_error() */
+#define APA_ERR_BAD_INPUT -3    /* byte outside ACGT (BitProfile::build panics, pa-bitpacking/src/profile.rs:113) */
+#define APA_ERR_INTERNAL -4     /* device-side assertion (a reference panic path) */
+#define APA_ERR_TOO_LARGE -5    /* sequence length >= 2^31 (I = i32) or memory budget exceeded */
+
+typedef struct apa_engine apa_engine; /* one per GPU; owns stream, scratch arenas, result pools */
+typedef struct apa_batch apa_batch;   /* a batch of pairs resident in HBM */
+
+typedef struct apa_batch_stats {
+    double h2d_ms, kernel_ms, d2h_ms; /* CUDA-event timings of the last run of this batch */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t computed_cells; /* 64 * lanes * cols evaluated by the block-DP kernel (reference: BlockStats.computed_lanes,
+                                astarpa2/src/blocks.rs:705-712, times i_range.len()) */
+    uint64_t dp_word_steps;  /* 32-row word x column steps issued by the block-DP kernel */
+    uint64_t passes;         /* sum over pairs of f_max tries (AstarPa2Stats.f_max_tries, domain.rs:36) */
+    uint64_t kernel_launches;
+    uint64_t retries;        /* pairs re-run with a larger scratch arena */
+    uint64_t fill_blocks, dt_blocks; /* traceback: blocks re-filled / solved by DT-trace (TraceStats, trace.rs:3-14) */
+} apa_batch_stats;
+
+const char* apa_last_error(void);
+int apa_device_count(void);
+
+int apa_engine_create(int device, apa_engine** out);
+void apa_engine_destroy(apa_engine* e);
+
+/* Host -> HBM: copies the concatenated sequences (a_off/b_off have n_pairs+1 entries) and validates ACGT. */
+int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all,
+                     const int64_t* b_off, apa_batch** out);
+/* Run the hot path on a resident batch; results stay in HBM. trace != 0 also produces CIGARs
+ * (Aligner::align with trace = true, astarpa2/src/lib.rs:210-215; trace = false is AstarPa2::cost, lib.rs:177-179). */
+int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace);
+/* HBM -> host: costs[n_pairs]; if cigar_off != NULL also the CIGAR text pool: *cigar_pool is malloc'd (free with
+ * apa_free), pair p's NUL-terminated text starts at cigar_off[p], strlen = cigar_off[p+1]-cigar_off[p]-1. */
+int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off);
+int apa_batch_get_stats(apa_batch* b, apa_batch_stats* out);
+void apa_batch_free(apa_engine* e, apa_batch* b);
+void apa_free(void* p);
+
+/* Convenience: upload + run + download. */
+int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off,
+                    const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool, int64_t* cigar_off,
+                    apa_batch_stats* stats);
+
+/* Debug/test introspection: per-pass band log of one pair in the oracle's layout
+ * (passes, then per pass: f_max, nblocks, nblocks x (j_s, j_e, fixed_s, fixed_e)). Returns int32 count or <0. */
+int64_t apa_debug_band_log(apa_engine* e, int preset, int trace, const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m,
+                           int32_t* out, uint64_t cap);
+
+/* Block-DP kernel on its own (pa_bitpacking::simd::compute semantics, pa-bitpacking/src/simd.rs:98-226):
+ * rectangle a[na] x b[mb]; h one byte per column (bit0 = +1, bit1 = -1), in/out; v interleaved (p,m) u64 pairs
+ * per 64-row word, in/out. Returns the sum of the bottom-row deltas via *bottom_sum. */
+int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, const uint8_t* b, uint64_t mb, uint8_t* h, uint64_t* v,
+                      int64_t* bottom_sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
