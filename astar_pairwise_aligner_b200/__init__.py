@@ -1,0 +1,295 @@
+"""B200-native A*PA2 hot path behind the reference's interface.
+
+Host-side mirror (Python, ctypes over the C-ABI shared library ``libastarpa_c.so``) of the Rust entry points
+of the reference for this path:
+
+* ``astarpa2_simple(a, b)`` / ``astarpa2_full(a, b)``  -> ``(cost, cigar)``   (astarpa2/src/lib.rs:44-53)
+* ``AstarPa2(preset, trace).align(a, b)`` / ``.cost(a, b)``                    (astarpa2/src/lib.rs:177-215,
+  the ``pa_types::Aligner`` trait: ``align(&mut self, a, b) -> (Cost, Option<Cigar>)``)
+* ``AstarPa2.align_batch(pairs)`` — the batch extension a GPU needs (include/astarpa_b200.h).
+
+All compute happens in hand-written sm_100a CUDA kernels inside the shared library. There is no CPU fallback:
+if the library is missing or no B200-class device is usable, calls raise ``AstarPaError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["AstarPa2", "AstarPaError", "Engine", "astarpa2_simple", "astarpa2_full", "generate_pair", "generate_batch",
+           "PRESET_SIMPLE", "PRESET_FULL", "lib_path", "load_library"]
+
+PRESET_SIMPLE, PRESET_FULL = 0, 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class AstarPaError(RuntimeError):
+    pass
+
+
+class BatchStats(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("computed_cells", C.c_uint64),
+                ("dp_word_steps", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("retries", C.c_uint64), ("fill_blocks", C.c_uint64), ("dt_blocks", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def lib_path():
+    return os.path.join(_HERE, "libastarpa_c.so")
+
+
+def load_library():
+    """Load libastarpa_c.so (built in-tree by __graft_entry__.build()). Fails loudly when absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise AstarPaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.apa_last_error.restype = C.c_char_p
+    L.apa_device_count.restype = C.c_int
+    L.apa_engine_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.apa_engine_destroy.argtypes = [C.c_void_p]
+    L.apa_batch_upload.argtypes = [C.c_void_p, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_void_p)]
+    L.apa_batch_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.apa_batch_download.argtypes = [C.c_void_p, C.c_void_p, vp, C.POINTER(C.c_void_p), vp, vp]
+    L.apa_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
+    L.apa_batch_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.apa_free.argtypes = [C.c_void_p]
+    L.apa_generate_pair.restype = C.c_int64
+    L.apa_generate_pair.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64]
+    L.apa_generate_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64, vp, C.c_int]
+    L.apa_block_compute.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.POINTER(C.c_int64)]
+    for name in ("astarpa2_simple", "astarpa2_full", "astarpa"):
+        f = getattr(L, name)
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.astarpa_gcsh.restype = C.c_uint64
+    L.astarpa_gcsh.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_bool,
+                               C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.astarpa_free_cigar.argtypes = [C.c_void_p]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise AstarPaError(f"libastarpa_c error {rc}: {load_library().apa_last_error().decode()}")
+
+
+# ----------------------------------------------------------------------------------------------- generator
+def generate_pair(n, e, model=0, seed=31415):
+    """Synthetic pair (stands in for pa_generate::generate_model, pa-test/src/lib.rs:60)."""
+    L = load_library()
+    a = np.empty(max(n, 1), dtype=np.uint8)
+    cap = 3 * n + 64
+    b = np.empty(cap, dtype=np.uint8)
+    bl = L.apa_generate_pair(n, float(e), model, seed, a.ctypes.data, b.ctypes.data, cap)
+    if bl < 0:
+        raise AstarPaError("generator buffer too small")
+    return a[:n].tobytes(), b[:bl].tobytes()
+
+
+def generate_batch(n_pairs, n, e, model=0, seed0=31415, threads=None):
+    """Returns (a_all, a_off, b_all, b_off) numpy arrays; pair p uses seed seed0 + p."""
+    L = load_library()
+    threads = threads or (os.cpu_count() or 1)
+    stride = int(n * (1 + e) + n * e + 64)
+    a_all = np.empty(max(n_pairs * n, 1), dtype=np.uint8)
+    b_buf = np.empty(max(n_pairs * stride, 1), dtype=np.uint8)
+    b_len = np.zeros(max(n_pairs, 1), dtype=np.int64)
+    rc = L.apa_generate_batch(n_pairs, n, float(e), model, seed0, a_all.ctypes.data, b_buf.ctypes.data, stride,
+                              b_len.ctypes.data, threads)
+    if rc != 0:
+        raise AstarPaError("generator stride too small")
+    a_off = np.arange(n_pairs + 1, dtype=np.int64) * n
+    b_off = np.zeros(n_pairs + 1, dtype=np.int64)
+    np.cumsum(b_len[:n_pairs], out=b_off[1:])
+    b_all = np.empty(max(int(b_off[-1]), 1), dtype=np.uint8)
+    for p in range(n_pairs):
+        b_all[b_off[p]:b_off[p + 1]] = b_buf[p * stride:p * stride + b_len[p]]
+    return a_all[:n_pairs * n], a_off, b_all[:int(b_off[-1])], b_off
+
+
+# ----------------------------------------------------------------------------------------------- engine
+class Engine:
+    """One per GPU: owns the stream, the scratch arenas and the device work queue."""
+
+    def __init__(self, device=0):
+        L = load_library()
+        self._L = L
+        self._h = None
+        h = C.c_void_p()
+        _check(L.apa_engine_create(device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._L.apa_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, a_all, a_off, b_all, b_off):
+        return Batch(self, a_all, a_off, b_all, b_off)
+
+    def block_compute(self, a: bytes, b: bytes, v=None):
+        """pa_bitpacking::simd::compute on the GPU with +1 top deltas. Returns (bottom_sum, h_out, v_out)."""
+        na, mb = len(a), len(b)
+        nwords = (mb + 63) // 64
+        h = np.ones(max(na, 1), dtype=np.uint8)
+        vv = np.zeros(2 * max(nwords, 1), dtype=np.uint64)
+        if v is None:
+            vv[0::2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        else:
+            vv[:2 * nwords] = v
+        s = C.c_int64()
+        ab = np.frombuffer(a, dtype=np.uint8) if na else np.zeros(1, np.uint8)
+        bb = np.frombuffer(b, dtype=np.uint8) if mb else np.zeros(1, np.uint8)
+        _check(self._L.apa_block_compute(self._h, ab.ctypes.data, na, bb.ctypes.data, mb, h.ctypes.data, vv.ctypes.data,
+                                         C.byref(s)))
+        return s.value, h[:na], vv[:2 * nwords]
+
+
+class Batch:
+    """A batch of pairs resident in HBM (apa_batch)."""
+
+    def __init__(self, eng, a_all, a_off, b_all, b_off):
+        self._eng = eng
+        self._L = eng._L
+        self._h = None
+        a_all = np.ascontiguousarray(a_all, dtype=np.uint8)
+        b_all = np.ascontiguousarray(b_all, dtype=np.uint8)
+        a_off = np.ascontiguousarray(a_off, dtype=np.int64)
+        b_off = np.ascontiguousarray(b_off, dtype=np.int64)
+        self.n_pairs = len(a_off) - 1
+        h = C.c_void_p()
+        ap = a_all.ctypes.data if a_all.size else None
+        bp = b_all.ctypes.data if b_all.size else None
+        _check(self._L.apa_batch_upload(eng._h, self.n_pairs, ap, a_off.ctypes.data, bp, b_off.ctypes.data, C.byref(h)))
+        self._h = h
+
+    def run(self, preset=PRESET_FULL, trace=True):
+        _check(self._L.apa_batch_run(self._eng._h, self._h, preset, int(trace)))
+        return self
+
+    def download(self, cigars=True):
+        n = self.n_pairs
+        costs = np.zeros(max(n, 1), dtype=np.int64)
+        if not cigars:
+            _check(self._L.apa_batch_download(self._eng._h, self._h, costs.ctypes.data, None, None, None))
+            return costs[:n], None
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        ln = np.zeros(max(n, 1), dtype=np.int64)
+        pool = C.c_void_p()
+        _check(self._L.apa_batch_download(self._eng._h, self._h, costs.ctypes.data, C.byref(pool), off.ctypes.data,
+                                          ln.ctypes.data))
+        out = None
+        if pool.value:
+            out = [C.string_at(pool.value + int(off[p]), int(ln[p])).decode() for p in range(n)]
+            self._L.apa_free(pool)
+        return costs[:n], out
+
+    def download_raw(self):
+        """As download(), without building Python strings: (costs, pool pointer, off, len); free pool with free_pool."""
+        n = self.n_pairs
+        costs = np.zeros(max(n, 1), dtype=np.int64)
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        ln = np.zeros(max(n, 1), dtype=np.int64)
+        pool = C.c_void_p()
+        _check(self._L.apa_batch_download(self._eng._h, self._h, costs.ctypes.data, C.byref(pool), off.ctypes.data,
+                                          ln.ctypes.data))
+        return costs[:n], pool, off[:n], ln[:n]
+
+    def free_pool(self, pool):
+        if pool and pool.value:
+            self._L.apa_free(pool)
+
+    def stats(self):
+        st = BatchStats()
+        _check(self._L.apa_batch_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def free(self):
+        if self._h:
+            self._L.apa_batch_free(self._eng._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _concat(pairs):
+    a_off = np.zeros(len(pairs) + 1, dtype=np.int64)
+    b_off = np.zeros(len(pairs) + 1, dtype=np.int64)
+    for p, (a, b) in enumerate(pairs):
+        a_off[p + 1] = a_off[p] + len(a)
+        b_off[p + 1] = b_off[p] + len(b)
+    a_all = np.frombuffer(b"".join(a for a, _ in pairs), dtype=np.uint8)
+    b_all = np.frombuffer(b"".join(b for _, b in pairs), dtype=np.uint8)
+    return a_all, a_off, b_all, b_off
+
+
+_DEFAULT_ENGINES = {}
+
+
+def _engine(device=0):
+    if device not in _DEFAULT_ENGINES:
+        _DEFAULT_ENGINES[device] = Engine(device)
+    return _DEFAULT_ENGINES[device]
+
+
+class AstarPa2:
+    """Mirror of ``AstarPa2Params::{simple,full}().make_aligner(trace)`` (astarpa2/src/params.rs:70-132)."""
+
+    def __init__(self, preset="full", trace=True, device=0):
+        self.preset = {"simple": PRESET_SIMPLE, "full": PRESET_FULL, 0: 0, 1: 1}[preset]
+        self.trace = trace
+        self.device = device
+
+    def align_batch(self, pairs):
+        """pairs: list of (a, b) byte strings over ACGT. Returns (costs ndarray, list of CIGAR strings or None)."""
+        eng = _engine(self.device)
+        batch = eng.upload(*_concat(pairs))
+        try:
+            batch.run(self.preset, self.trace)
+            return batch.download(cigars=self.trace)
+        finally:
+            batch.free()
+
+    def align(self, a: bytes, b: bytes):
+        """Aligner::align (astarpa2/src/lib.rs:210-215): (cost, cigar or None)."""
+        costs, cigs = self.align_batch([(a, b)])
+        return int(costs[0]), (cigs[0] if cigs is not None else None)
+
+    def cost(self, a: bytes, b: bytes):
+        """AstarPa2::cost (astarpa2/src/lib.rs:177-179)."""
+        saved, self.trace = self.trace, False
+        try:
+            return self.align(a, b)[0]
+        finally:
+            self.trace = saved
+
+
+def astarpa2_simple(a: bytes, b: bytes):
+    """astarpa2::astarpa2_simple (astarpa2/src/lib.rs:44-47)."""
+    return AstarPa2("simple", True).align(a, b)
+
+
+def astarpa2_full(a: bytes, b: bytes):
+    """astarpa2::astarpa2_full (astarpa2/src/lib.rs:50-53)."""
+    return AstarPa2("full", True).align(a, b)

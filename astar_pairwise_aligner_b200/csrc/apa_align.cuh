@@ -1,0 +1,319 @@
+// Device-side A*PA2 driver for one pair (one warp): band selection, band doubling, block store.
+// Replaces, per pair and entirely on the GPU:
+//   AstarPa2Instance::{j_range, fixed_j_range, align_for_bounded_dist}   astarpa2/src/domain.rs:77-541
+//   Blocks::{init, compute_next_block, set_last_block_fixed_j_range}     astarpa2/src/blocks.rs:146-569
+//   band::exponential_search + AstarPa2::cost_or_align                   astarpa2/src/band.rs:100-141, lib.rs:122-175
+// Blocks are always recomputed (no reuse_next_block / incremental doubling): the reference itself asserts that
+// both give the same V column (blocks.rs:471-543), and the oracle's differential check confirms it. The
+// reuse *decision* is still tracked because it keeps the old original_j_range (domain.rs:451-455, blocks.rs:190-197).
+#pragma once
+#include "apa_blockdp.cuh"
+
+namespace apa {
+
+// Everything one warp needs to know about its pair.
+struct PairCtx {
+    I n, m;
+    const uint8_t* a;
+    const uint8_t* b;
+    const uint2* bprof;  // negated bit planes of b per 32 rows (profile.rs:124-131), zero padded to a multiple of 64 rows
+    uint8_t* arena;      // per-pair scratch
+    uint32_t arena_size;
+    BlkMeta* meta;       // nblk + 1 entries (entry 0 = column 0)
+    int nblk;            // number of 256-column blocks
+    int nblk_alloc;      // blocks.len() of the reference: entries [0, nblk_alloc) hold ranges of an earlier pass
+    uint32_t v_base;     // start of the V region in the arena (bytes)
+    uint32_t v_top;      // bump pointer
+    uint32_t hi_bot;     // lowest byte used by the downward-growing region at the arena end (CIGAR elements)
+    int status;          // ST_PENDING while healthy
+    // stats
+    unsigned long long word_steps, computed_cells;
+    int passes;
+    int fill_blocks, dt_blocks;
+    // optional band log (apa_debug_band_log): records of 7 ints {pass, f_max, block, j_s, j_e, fixed_s, fixed_e}
+    int32_t* dbg;
+    uint32_t dbg_cap, dbg_n;
+};
+
+__device__ __forceinline__ void dbg_log(PairCtx& cx, Cost f_max, int t, JRange jr, JRange fx) {
+    if (!cx.dbg) return;
+    if (cx.dbg_n + 7 <= cx.dbg_cap && (threadIdx.x & 31) == 0) {
+        int32_t* r = cx.dbg + cx.dbg_n;
+        r[0] = cx.passes;
+        r[1] = f_max;
+        r[2] = t;
+        r[3] = jr.s;
+        r[4] = jr.e;
+        r[5] = fx.s;
+        r[6] = fx.e;
+    }
+    cx.dbg_n += 7;
+}
+
+__device__ __forceinline__ uint32_t arena_alloc(PairCtx& cx, uint32_t bytes) {
+    bytes = (bytes + 15u) & ~15u;
+    if (cx.v_top + bytes > cx.hi_bot) {
+        cx.status = ST_OVERFLOW;
+        return 0xffffffffu;
+    }
+    uint32_t off = cx.v_top;
+    cx.v_top += bytes;
+    return off;
+}
+
+__device__ __forceinline__ BlkView view_of(const PairCtx& cx, const BlkMeta& mt) {
+    BlkView v;
+    v.js = mt.js;
+    v.je = mt.je;
+    v.top_val = mt.top_val;
+    v.bot_val = mt.bot_val;
+    v.ones = mt.ones;
+    v.v = (const uint2*)(cx.arena + mt.v_off);
+    int nhw = (mt.je - mt.js) >> 5;
+    v.cum = (const int32_t*)(cx.arena + mt.v_off + (size_t)nhw * 8);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------- heuristics
+// GapCost (pa-heuristic/src/heuristic/distances.rs:130-169): the whole heuristic of astarpa2_simple.
+struct GapH {
+    I n, m;
+    static constexpr bool PRUNE = false;
+    __device__ __forceinline__ Cost h(I i, I j) const {
+        I d = (n - i) - (m - j);
+        return d < 0 ? -d : d;
+    }
+    __device__ __forceinline__ void prune_block(I, I, I, I) {}
+    __device__ __forceinline__ void update_contours() {}
+};
+
+// ---------------------------------------------------------------------------------------------- band selection
+// AstarPa2Instance::j_range for Domain::Astar with sparse_h (domain.rs:77-246). prev_fixed is the fixed range of
+// the previous column, gu the value at its end (0 for the virtual column -1).
+template <class Hh>
+__device__ JRange dev_j_range(const PairCtx& cx, Hh& hh, I is, I ie, Cost f_max, JRange prev_fixed, const BlkView* prev,
+                              bool has_old, JRange old_range) {
+    I fixed_start = prev_fixed.s, fixed_end = prev_fixed.e;
+    I ui = is, uj = fixed_end;
+    Cost gu = is < 0 ? 0 : blk_index(*prev, fixed_end);
+    I vi = ui + 1, vj = uj + 1;
+    vj += BLOCK_W;
+    vj = min(vj, cx.m);
+    for (;;) {
+        if (vj < vi - ui + uj) {
+            vj = vi - ui + uj;
+            break;
+        }
+        I dd = (vi - ui) - (vj - uj);
+        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj);
+        if (fv <= f_max) {
+            if (vj == cx.m) break;
+            vj += 8;
+            if (vj >= cx.m) vj = cx.m;
+        } else {
+            vi += div_ceil_pos(fv - f_max, 2);
+            if (vi > ie) {
+                vi = ie;
+                break;
+            }
+        }
+    }
+    vi = ie;
+    for (;;) {
+        if (vj < vi - ui + uj) {
+            vj = vi - ui + uj;
+            break;
+        }
+        I dd = (vi - ui) - (vj - uj);
+        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj);
+        if (fv <= f_max) break;
+        vj -= div_ceil_pos(fv - f_max, 2);
+    }
+    JRange range{fixed_start, vj};
+    if (has_old) range = jr_union(range, old_range);
+    return jr_inter(range, JRange{0, cx.m});
+}
+
+// AstarPa2Instance::fixed_j_range with sparse_h (domain.rs:251-350).
+template <class Hh>
+__device__ JRange dev_fixed_j_range(const PairCtx& cx, Hh& hh, I i, Cost f_max, JRange prev_fixed, const BlkView& blk, I orig_e,
+                                    bool has_old_fixed, JRange old_fixed) {
+    I start = prev_fixed.s;
+    I end = min(orig_e, cx.m);
+    while (start <= end) {
+        Cost f = blk_index(blk, start) + hh.h(i, start);
+        if (f <= f_max) break;
+        start += div_ceil_pos(f - f_max, 2);
+    }
+    while (end >= start) {
+        Cost f = blk_index(blk, end) + hh.h(i, end);
+        if (f <= f_max) break;
+        end -= div_ceil_pos(f - f_max, 2);
+    }
+    JRange fixed{start, end};
+    if (has_old_fixed) {
+        if (jr_empty(fixed))
+            fixed = old_fixed;
+        else
+            fixed = jr_union(fixed, old_fixed);
+    }
+    return fixed;
+}
+
+constexpr Cost PASS_NONE = -1;
+
+// One pass for a given f_max: AstarPa2Instance::align_for_bounded_dist (domain.rs:356-541), without the trace.
+// Returns the distance found in the last column, or PASS_NONE.
+template <class Hh>
+__device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
+    const int lane = threadIdx.x & 31;
+    cx.passes++;
+    if (Hh::PRUNE) hh.update_contours();
+    cx.v_top = cx.v_base;  // blocks are recomputed in every pass
+
+    // Column 0 (domain.rs:395-413, blocks.rs:146-179).
+    BlkMeta* meta = cx.meta;
+    BlkMeta m0 = meta[0];
+    bool had0 = cx.nblk_alloc > 0;
+    JRange jr0 = dev_j_range(cx, hh, -1, 0, f_max, JRange{-1, -1}, nullptr, had0, JRange{m0.js, m0.je});
+    if (jr_empty(jr0) || jr0.s > 0) return PASS_NONE;
+    {
+        JRange init = jr0;
+        if (had0) init = jr_union(init, JRange{m0.js, m0.je});
+        JRange rounded = jr_round_out(init);
+        BlkMeta nm;
+        nm.orig_s = jr0.s;
+        nm.orig_e = jr0.e;
+        nm.js = rounded.s;
+        nm.je = rounded.e;
+        nm.fs = jr0.s;
+        nm.fe = jr0.e;
+        nm.has_fixed = 1;
+        nm.ones = 1;
+        nm.top_val = 0;
+        nm.bot_val = rounded.e;
+        nm.v_off = 0;
+        nm.col_s = -1;
+        nm.col_e = 0;
+        __syncwarp();
+        if (lane == 0) meta[0] = nm;
+        __syncwarp();
+        if (cx.nblk_alloc < 1) cx.nblk_alloc = 1;
+        dbg_log(cx, f_max, 0, jr0, jr0);
+    }
+    bool all_reused = true;
+    for (int t = 1; t <= cx.nblk; t++) {
+        const I is = (t - 1) * BLOCK_W;
+        const I ie = min(is + BLOCK_W, cx.n);
+        const BlkMeta pm = meta[t - 1];
+        const BlkView prev = view_of(cx, pm);
+        const bool existed = t < cx.nblk_alloc;
+        const BlkMeta old = existed ? meta[t] : BlkMeta{};
+        const JRange prev_fixed{pm.fs, pm.fe};
+        JRange jr = dev_j_range(cx, hh, is, ie, f_max, prev_fixed, &prev, existed, JRange{old.js, old.je});
+        if (jr_empty(jr)) return PASS_NONE;
+        bool reuse = existed && old.js == jr.s && old.je == jr.e && all_reused;
+        all_reused = all_reused && reuse;
+
+        // Blocks::compute_next_block (blocks.rs:205-545), always from scratch.
+        JRange rounded = jr_round_out(jr);
+        int nhw = (rounded.e - rounded.s) >> 5;
+        uint32_t off = arena_alloc(cx, (uint32_t)nhw * 8u + (uint32_t)(nhw + 1) * 4u);
+        if (cx.status != ST_PENDING) return PASS_NONE;
+        Cost top_val = blk_index(prev, rounded.s) + (ie - is);
+        stage_amask(sm, cx.a, is, ie - is, lane);
+        uint2* vout = (uint2*)(cx.arena + off);
+        int32_t* cumout = (int32_t*)(cx.arena + off + (size_t)nhw * 8);
+        Cost bot_val = block_dp<false>(sm, cx.bprof, prev, ie - is, rounded.s, rounded.e, vout, cumout, top_val, nullptr,
+                                       cx.word_steps);
+        cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
+
+        BlkMeta nm;
+        nm.orig_s = reuse ? old.orig_s : jr.s;
+        nm.orig_e = reuse ? old.orig_e : jr.e;
+        nm.js = rounded.s;
+        nm.je = rounded.e;
+        nm.top_val = top_val;
+        nm.bot_val = bot_val;
+        nm.v_off = off;
+        nm.ones = 0;
+        nm.col_s = is;
+        nm.col_e = ie;
+        BlkView cur;
+        cur.js = rounded.s;
+        cur.je = rounded.e;
+        cur.top_val = top_val;
+        cur.bot_val = bot_val;
+        cur.v = vout;
+        cur.cum = cumout;
+        cur.ones = 0;
+
+        const bool has_old_fixed = existed && old.has_fixed;
+        JRange next_fixed = dev_fixed_j_range(cx, hh, ie, f_max, prev_fixed, cur, nm.orig_e, has_old_fixed, JRange{old.fs, old.fe});
+        // The block is stored (with its previous fixed range) even when the pass aborts right after it.
+        JRange stored = next_fixed;
+        bool store_fixed = true;
+        if (jr_empty(next_fixed)) {
+            stored = JRange{old.fs, old.fe};
+            store_fixed = has_old_fixed;
+        } else if (has_old_fixed) {
+            stored = jr_union(JRange{old.fs, old.fe}, next_fixed);  // set_last_block_fixed_j_range, blocks.rs:556-563
+        }
+        nm.fs = stored.s;
+        nm.fe = stored.e;
+        nm.has_fixed = store_fixed ? 1 : 0;
+        __syncwarp();
+        if (lane == 0) meta[t] = nm;
+        __syncwarp();
+        if (cx.nblk_alloc < t + 1) cx.nblk_alloc = t + 1;
+        if (jr_empty(next_fixed)) return PASS_NONE;
+        dbg_log(cx, f_max, t, jr, stored);
+
+        if (Hh::PRUNE) {
+            JRange inter = jr_inter(prev_fixed, next_fixed);
+            if (!jr_empty(inter)) hh.prune_block(is, ie, inter.s, inter.e);
+        }
+    }
+    // dist = last_block.get(|b|) (domain.rs:520-522)
+    const BlkMeta lm = meta[cx.nblk];
+    if (cx.m < lm.js || cx.m > lm.je) return PASS_NONE;
+    const BlkView last = view_of(cx, lm);
+    return blk_index(last, cx.m);
+}
+
+// band::exponential_search driven by cost_or_align (band.rs:100-141, lib.rs:140-159): offset = h0,
+// s0 = max(1, block_width) = 256, factor 2.0. Returns the cost; the blocks of the final pass stay in the arena.
+template <class Hh>
+__device__ Cost dev_band_doubling(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost h0) {
+    Cost offset = h0;
+    Cost last_s = -1;
+    Cost s = offset + BLOCK_W;
+    Cost maxs = INT32_MAX;
+    for (;;) {
+        Cost cost = dev_pass(cx, sm, hh, s);
+        if (cx.status != ST_PENDING) return -1;
+        if (cost != PASS_NONE) {
+            if (cost > maxs) {
+                cx.status = ST_ASSERT;
+                return -1;
+            }
+            if (cost <= s) {
+                if (cost <= last_s) {
+                    cx.status = ST_ASSERT;
+                    return -1;
+                }
+                return cost;
+            }
+            maxs = min(maxs, cost);
+        } else if (maxs != INT32_MAX) {
+            cx.status = ST_ASSERT;
+            return -1;
+        }
+        last_s = s;
+        float grown = ceilf(2.0f * (float)(s - offset));
+        s = max((Cost)grown, 1) + offset;
+        s = min(s, maxs);
+    }
+}
+
+}  // namespace apa

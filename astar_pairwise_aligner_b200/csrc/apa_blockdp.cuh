@@ -1,0 +1,124 @@
+// K1 / K3: the Myers bit-vector block-DP wavefront (replaces pa_bitpacking::simd::{compute,fill},
+// pa-bitpacking/src/simd.rs:98-226,326-437, and myers::compute_block, myers.rs:27-55).
+//
+// Mapping: one warp computes a (cols <= 256) x (rows = 32 * nhw) rectangle. Lane r owns the 32-row
+// half-word r of the current 32-lane chunk and sweeps the columns left to right, one anti-diagonal per
+// step: at step t lane r evaluates column t - r. The horizontal delta words (hp, hm) of the lane above
+// arrive by __shfl_up_sync; bit 31 of them is the delta entering this lane's top row, which a funnel shift
+// folds into (hp << 1) | hp0 without extracting it. Bands taller than 32 half-words are processed chunk by
+// chunk; the bottom delta row of a chunk (2 bits per column) is handed to the next chunk through shared
+// memory. The recurrence is bit-for-bit the reference's, evaluated in a different topological order, so the
+// resulting V column is identical.
+#pragma once
+#include "apa_common.cuh"
+
+namespace apa {
+
+struct WarpSmem {
+    uint2 amask[BLOCK_W];   // per column of the current block: (0 - rank bit0, 0 - rank bit1) of a[i]  (profile.rs:117-121)
+    uint8_t hrow[BLOCK_W];  // bottom horizontal deltas of the previous chunk: bit0 = +1, bit1 = -1
+};
+
+// One 32-row x 1-column Myers step (myers.rs:27-55 on a 32-bit word).
+// hp_in/hm_in: delta words of the lane above (bit 31 = delta entering at the top). Outputs the un-shifted
+// hp/hm words of this lane (bit 31 = delta leaving at the bottom).
+__device__ __forceinline__ void myers_step(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t& vp, uint32_t& vm,
+                                           uint32_t hp_in, uint32_t hm_in, uint32_t& hp_out, uint32_t& hm_out) {
+    uint32_t eq = (a0 ^ b0) & (a1 ^ b1);  // BitProfile::eq, profile.rs:141-144 (b planes are stored negated)
+    uint32_t vx = eq | vm;
+    uint32_t eq2 = eq | (hm_in >> 31);    // `eq |= h0.m`: the input delta may be -1 (myers.rs:31-32)
+    uint32_t hx = (((eq2 & vp) + vp) ^ vp) | eq2;
+    uint32_t hp = vm | ~(hx | vp);
+    uint32_t hm = vp & hx;
+    hp_out = hp;
+    hm_out = hm;
+    uint32_t hps = __funnelshift_l(hp_in, hp, 1);  // (hp << 1) | h0.p
+    uint32_t hms = __funnelshift_l(hm_in, hm, 1);  // (hm << 1) | h0.m
+    vp = hms | ~(vx | hps);
+    vm = hps & vx;
+}
+
+// Stage the a-masks of columns [col_s, col_s + ncols) of `a` into shared memory.
+__device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint8_t* __restrict__ a, I col_s, int ncols, int lane) {
+    for (int c = lane; c < ncols; c += 32) {
+        uint32_t r = rank_acgt(a[col_s + c]);
+        sm.amask[c] = make_uint2(0u - (r & 1u), 0u - (r >> 1));
+    }
+    __syncwarp();
+}
+
+// Compute the right-edge column of a block.
+//   prev      : stored column to the left (rows outside it start from +1 deltas: init_v_with_overlap, blocks.rs:753-767)
+//   njs, nje  : rounded-out row range of the new block (multiples of 64)
+//   vout/cum  : nhw (p,m) words and nhw+1 running values of the new column
+//   fillvals  : if FILL, every column's V is also stored: fillvals[col * nhw + hw]   (simd::fill)
+// Horizontal deltas along the top edge are +1 (HMode::None, blocks.rs:728-734).
+// Returns the value at the bottom of the rounded range (bot_val); top_val is supplied by the caller.
+template <bool FILL>
+__device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const BlkView& prev, int ncols, I njs, I nje,
+                         uint2* __restrict__ vout, int32_t* __restrict__ cumout, Cost top_val_new, uint2* __restrict__ fillvals,
+                         unsigned long long& word_steps) {
+    const int lane = threadIdx.x & 31;
+    const int nhw = (nje - njs) >> 5;
+    const int nchunks = (nhw + 31) >> 5;
+    Cost running = top_val_new;
+    for (int c = 0; c < nchunks; c++) {
+        const int nact = min(32, nhw - 32 * c);
+        const int hw = 32 * c + lane;
+        const bool act_lane = lane < nact;
+        const I j0 = njs + 32 * hw;
+        uint32_t vp = ~0u, vm = 0u, b0 = 0u, b1 = 0u;
+        if (act_lane) {
+            if (!prev.ones && j0 >= prev.js && j0 < prev.je) {
+                uint2 pm = prev.v[(j0 - prev.js) >> 5];
+                vp = pm.x;
+                vm = pm.y;
+            }
+            uint2 bb = bprof[j0 >> 5];
+            b0 = bb.x;
+            b1 = bb.y;
+        }
+        uint32_t hp_o = 0u, hm_o = 0u;
+        const int T = ncols + nact - 1;
+        const bool hand_off = (c + 1 < nchunks);
+        for (int t = 0; t < T; t++) {
+            uint32_t hpi = __shfl_up_sync(FULL, hp_o, 1);
+            uint32_t hmi = __shfl_up_sync(FULL, hm_o, 1);
+            if (lane == 0) {
+                if (c == 0) {
+                    hpi = 0x80000000u;
+                    hmi = 0u;
+                } else {
+                    uint32_t x = (t < ncols) ? sm.hrow[t] : 0u;
+                    hpi = (x & 1u) << 31;
+                    hmi = (x & 2u) << 30;
+                }
+            }
+            const int col = t - lane;
+            if (act_lane && (unsigned)col < (unsigned)ncols) {
+                uint2 am = sm.amask[col];
+                myers_step(am.x, am.y, b0, b1, vp, vm, hpi, hmi, hp_o, hm_o);
+                if (hand_off && lane == nact - 1) sm.hrow[col] = (uint8_t)((hp_o >> 31) | ((hm_o >> 31) << 1));
+                if (FILL) fillvals[(size_t)col * nhw + hw] = make_uint2(vp, vm);
+            }
+        }
+        __syncwarp();
+        if (act_lane) vout[hw] = make_uint2(vp, vm);
+        // running values: cum[hw] = value at the top of half-word hw.
+        int val = act_lane ? (__popc(vp) - __popc(vm)) : 0;
+        int incl = val;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (act_lane) cumout[hw] = running + incl - val;
+        running += __shfl_sync(FULL, incl, 31);
+        word_steps += (unsigned long long)ncols * (unsigned long long)nact;
+    }
+    if (lane == 0) cumout[nhw] = running;
+    __syncwarp();
+    return running;
+}
+
+}  // namespace apa

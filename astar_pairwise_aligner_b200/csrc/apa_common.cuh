@@ -1,0 +1,108 @@
+// Shared device-side types and helpers of the B200 A*PA2 engine (sm_100a only).
+//
+// Everything here is written warp-per-pair: one warp owns one sequence pair. Scalar control state (ranges,
+// costs, cursors) is kept warp-uniform — every lane computes the same value — so cooperative steps (the
+// block-DP wavefront, popcount scans, ballots) can be called from anywhere without divergence.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace apa {
+
+typedef int32_t I;
+typedef int32_t Cost;
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WI = 64;   // reference word height (astarpa2/src/lib.rs:35). Ranges round to multiples of 64.
+constexpr int HW = 32;   // our DP lane height: one 32-row half-word per lane (same recurrence, A.4 of SURVEY).
+constexpr int BLOCK_W = 256;  // block_width of both presets (astarpa2/src/params.rs:84,111)
+
+// Per-pair status codes written by the kernels.
+enum Status : int32_t {
+    ST_PENDING = 0,
+    ST_DONE = 1,
+    ST_OVERFLOW = 2,   // scratch arena too small: host re-runs the pair with a larger arena
+    ST_BAD_INPUT = 3,  // byte outside ACGT
+    ST_ASSERT = 4,     // a reference panic path was reached
+};
+
+struct JRange {
+    I s, e;  // inclusive (astarpa2/src/ranges.rs:13-14)
+};
+__device__ __forceinline__ bool jr_empty(JRange r) { return r.s > r.e; }
+__device__ __forceinline__ JRange jr_union(JRange a, JRange b) { return JRange{min(a.s, b.s), max(a.e, b.e)}; }
+__device__ __forceinline__ JRange jr_inter(JRange a, JRange b) { return JRange{max(a.s, b.s), min(a.e, b.e)}; }
+// Rust: s / 64 * 64 truncates toward zero; next_multiple_of rounds up (ranges.rs:71-76).
+__device__ __forceinline__ I next_mult64(I x) {
+    I r = x % WI;
+    if (r < 0) r += WI;
+    return r == 0 ? x : x + (WI - r);
+}
+__device__ __forceinline__ I trunc_mult64(I x) { return x / WI * WI; }
+__device__ __forceinline__ JRange jr_round_out(JRange r) { return JRange{trunc_mult64(r.s), next_mult64(r.e)}; }
+__device__ __forceinline__ JRange jr_round_in(JRange r) { return JRange{next_mult64(r.s), trunc_mult64(r.e)}; }
+__device__ __forceinline__ I div_ceil_pos(I a, I b) {  // signed div_ceil, b > 0
+    I q = a / b, r = a % b;
+    return r > 0 ? q + 1 : q;
+}
+
+// Per-block metadata kept for the whole band-doubling search of one pair (astarpa2/src/block.rs:8-31).
+struct BlkMeta {
+    I orig_s, orig_e;  // original_j_range
+    I js, je;          // rounded-out j_range (multiples of 64)
+    I fs, fe;          // fixed_j_range (valid iff has_fixed)
+    Cost top_val, bot_val;
+    uint32_t v_off;     // byte offset of this block's V column inside the pair's arena (valid in the current pass)
+    uint16_t has_fixed;
+    uint16_t ones;      // column 0: all vertical deltas +1, nothing stored
+    I col_s, col_e;     // i_range (left-exclusive)
+};
+static_assert(sizeof(BlkMeta) == 48, "BlkMeta layout");
+
+// A read-only view of a stored right-edge column: V as (p,m) per 32-row half-word + running values.
+struct BlkView {
+    I js, je;            // rounded j_range
+    Cost top_val, bot_val;
+    const uint2* v;      // nhw entries
+    const int32_t* cum;  // nhw+1 entries: value at row js + 32*hw
+    int ones;
+    __device__ __forceinline__ int nhw() const { return (je - js) >> 5; }
+};
+
+// Block::index (astarpa2/src/block.rs:69-122): value at row j >= js; rows past je extend with +1.
+__device__ __forceinline__ Cost blk_index(const BlkView& b, I j) {
+    if (j > b.je) return b.bot_val + (j - b.je);
+    int off = j - b.js;
+    int hw = off >> 5, bit = off & 31;
+    if (b.ones) return b.top_val + off;
+    Cost base = b.cum[hw];
+    if (bit == 0) return base;
+    uint2 pm = b.v[hw];
+    uint32_t mask = (1u << bit) - 1u;
+    return base + __popc(pm.x & mask) - __popc(pm.y & mask);
+}
+// Block::get_diff (block.rs:134-145): vertical delta from row j to j+1, or NONE outside the stored words.
+constexpr int DIFF_NONE = 99;
+__device__ __forceinline__ int blk_get_diff(const BlkView& b, I j) {
+    if (j < b.js) return DIFF_NONE;
+    int off = j - b.js;
+    int hw = off >> 5;
+    if (hw >= b.nhw()) return DIFF_NONE;
+    if (b.ones) return 1;
+    uint2 pm = b.v[hw];
+    int bit = off & 31;
+    return (int)((pm.x >> bit) & 1u) - (int)((pm.y >> bit) & 1u);
+}
+
+// RankTransform("ACGT") of an upper-case base: A0 C1 G2 T3 (pa-bitpacking/src/profile.rs:113).
+__device__ __forceinline__ uint32_t rank_acgt(uint32_t c) {
+    uint32_t x = (c >> 1) & 3u;  // A0 C1 T2 G3  (this is also QGrams::char_to_bits, qgrams.rs:30-32)
+    return x ^ (x >> 1);         // -> A0 C1 G2 T3
+}
+__device__ __forceinline__ bool is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// CIGAR element: op in the top 2 bits, count in the low 30 (pa-types CigarElem; trace.rs:129-221).
+enum CigOp : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3 };
+__device__ __forceinline__ uint32_t cig_pack(uint32_t op, uint32_t cnt) { return (op << 30) | cnt; }
+
+}  // namespace apa

@@ -59,9 +59,10 @@ int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, cons
 /* Run the hot path on a resident batch; results stay in HBM. trace != 0 also produces CIGARs
  * (Aligner::align with trace = true, astarpa2/src/lib.rs:210-215; trace = false is AstarPa2::cost, lib.rs:177-179). */
 int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace);
-/* HBM -> host: costs[n_pairs]; if cigar_off != NULL also the CIGAR text pool: *cigar_pool is malloc'd (free with
- * apa_free), pair p's NUL-terminated text starts at cigar_off[p], strlen = cigar_off[p+1]-cigar_off[p]-1. */
-int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off);
+/* HBM -> host: costs[n_pairs]; if the three cigar arguments are non-NULL also the CIGAR text pool: *cigar_pool is
+ * malloc'd (free with apa_free); pair p's NUL-terminated text starts at (*cigar_pool)[cigar_off[p]] and has
+ * strlen cigar_len[p] (pairs finish in any order, so offsets are not monotone). */
+int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len);
 int apa_batch_get_stats(apa_batch* b, apa_batch_stats* out);
 void apa_batch_free(apa_engine* e, apa_batch* b);
 void apa_free(void* p);
@@ -69,7 +70,7 @@ void apa_free(void* p);
 /* Convenience: upload + run + download. */
 int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off,
                     const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool, int64_t* cigar_off,
-                    apa_batch_stats* stats);
+                    int64_t* cigar_len, apa_batch_stats* stats);
 
 /* Debug/test introspection: per-pass band log of one pair in the oracle's layout
  * (passes, then per pass: f_max, nblocks, nblocks x (j_s, j_e, fixed_s, fixed_e)). Returns int32 count or <0. */

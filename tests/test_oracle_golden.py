@@ -1,0 +1,111 @@
+"""CPU tests: pin the oracle (CPU restatement of the reference path) against the reference's own golden
+vectors and known-answer tests, then against an independent ground truth on a random grid
+shaped like pa-test's (pa-test/src/lib.rs:24-63)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
+PRESETS = list(range(10))  # 0 simple, 1 full, 2..9: configurations of astarpa2/src/tests.rs:19-119
+
+
+@pytest.mark.parametrize("idx", range(len(GOLD["pairs"])))
+def test_golden_pairs_cost_and_cigar(oracle, idx):
+    p = GOLD["pairs"][idx]
+    a, b = p["a"].encode(), p["b"].encode()
+    assert oracle.levenshtein(a, b) == p["cost"]
+    assert oracle.levenshtein_dp(a, b) == p["cost"]
+    for preset in PRESETS:
+        cost, cigar, _ = oracle.align(a, b, preset, True, self_check=True)
+        assert cost == p["cost"], (preset, p["src"])
+        assert oracle.cigar_verify(cigar, a, b) == cost  # pa-test/src/lib.rs:98
+        cost2, none, _ = oracle.align(a, b, preset, False)
+        assert cost2 == cost and none is None
+
+
+def test_example_c_costs(oracle):
+    # astarpa-c/example.c:23-29: cost 2 through astarpa2_simple and astarpa2_full
+    a, b = b"ACTCGCT", b"AACTCGTT"
+    assert oracle.align(a, b, oracle.PRESET_SIMPLE)[0] == 2
+    assert oracle.align(a, b, oracle.PRESET_FULL)[0] == 2
+
+
+def test_cigar_text_format(oracle):
+    # astarpa-c/example.cpp:16: "=I4=X=" is a valid optimal CIGAR text for this pair: count omitted when 1.
+    g = GOLD["cigar_format"]
+    assert oracle.cigar_verify(g["cigar"], g["a"].encode(), g["b"].encode()) == g["cost"]
+    # malformed texts are rejected by the checker
+    assert oracle.cigar_verify("1=I4=X=", g["a"].encode(), g["b"].encode()) == -1
+    assert oracle.cigar_verify("==I3=X=", g["a"].encode(), g["b"].encode()) == -1
+    cost, cigar, _ = oracle.align(g["a"].encode(), g["b"].encode(), oracle.PRESET_FULL)
+    assert cost == 2 and "1" not in cigar.replace("10", "").replace("11", "")
+
+
+def test_qgram_kat(oracle):
+    # pa-heuristic/src/matches/qgrams.rs:117-124
+    L = oracle.lib()
+    for s, q in GOLD["qgram"]["to_qgram"].items():
+        assert L.oracle_to_qgram(s.encode(), len(s)) == q
+    for c, v in GOLD["qgram"]["char_to_bits"].items():
+        assert L.oracle_to_qgram(c.encode(), 1) == v
+
+
+@pytest.mark.parametrize("h", [64, 128, 256, 512])
+def test_block_kernel_kat(oracle, apa, h):
+    # pa-bitpacking/benches/nw/main.rs:142-149: 256 columns x h rows, all-(+1) input deltas:
+    # sum of bottom horizontal deltas == levenshtein(a, b) - |b|.
+    a, _ = apa.generate_pair(256, 0.0, 0, 31415)
+    b, _ = apa.generate_pair(h, 0.0, 0, 27182)
+    hbuf = np.ones(256, dtype=np.uint8)
+    v = np.zeros(2 * (h // 64), dtype=np.uint64)
+    v[0::2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    s = oracle.lib().oracle_bp_compute(a, len(a), b, len(b), hbuf.ctypes.data, v.ctypes.data)
+    assert s == oracle.levenshtein(a, b) - len(b)
+
+
+def _grid(ns, es, models, seed0):
+    for n in ns:
+        for e in es:
+            for model in models:
+                yield n, e, model, seed0 + 1000 * n + model
+
+
+NS = [0, 1, 2, 3, 7, 10, 17, 20, 50, 100, 190, 254, 255, 256, 257, 258, 300, 500, 511, 512, 513, 515]
+ES = [0.0, 0.01, 0.05, 0.1, 0.2, 0.3, 0.5, 0.7, 1.0]
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_random_grid_against_ground_truth(oracle, apa, preset):
+    # pa-test/src/lib.rs:65-99: cost == Levenshtein (triple_accel there, full-matrix bit-vector here) and the
+    # CIGAR verifies. self_check = the reference's cfg!(test) incremental-vs-scratch assertion (blocks.rs:471-543).
+    for n, e, model, seed in _grid(NS, ES[preset % 3::3], range(4), 31415):
+        a, b = apa.generate_pair(n, e, model, seed)
+        lev = oracle.levenshtein(a, b)
+        cost, cigar, _ = oracle.align(a, b, preset, True, self_check=True)
+        assert cost == lev, (preset, n, e, model)
+        assert oracle.cigar_verify(cigar, a, b) == lev, (preset, n, e, model)
+
+
+@pytest.mark.parametrize("n,e", [(3000, 0.05), (10000, 0.05), (10000, 0.15), (30000, 0.08)])
+def test_presets_larger(oracle, apa, n, e):
+    a, b = apa.generate_pair(n, e, 0, 31415 + n)
+    lev = oracle.levenshtein(a, b)
+    for preset in (0, 1):
+        cost, cigar, st = oracle.align(a, b, preset, True, self_check=True)
+        assert cost == lev and oracle.cigar_verify(cigar, a, b) == lev
+        assert oracle.align(a, b, preset, False)[0] == lev
+
+
+def test_ground_truth_cross_check(oracle, apa):
+    for n, e, model, seed in _grid([0, 1, 5, 63, 64, 65, 130, 400], [0.0, 0.1, 0.5], range(4), 99):
+        a, b = apa.generate_pair(n, e, model, seed)
+        assert oracle.levenshtein(a, b) == oracle.levenshtein_dp(a, b)
+
+
+def test_bad_input_panics(oracle):
+    # BitProfile::build panics on bytes outside ACGT (pa-bitpacking/src/profile.rs:113)
+    with pytest.raises(oracle.OraclePanic):
+        oracle.align(b"ACGN", b"ACGT", 0)
