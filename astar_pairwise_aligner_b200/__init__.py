@@ -63,6 +63,9 @@ def load_library():
     L.apa_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
     L.apa_batch_free.argtypes = [C.c_void_p, C.c_void_p]
     L.apa_free.argtypes = [C.c_void_p]
+    L.apa_pinned_alloc.restype = C.c_void_p
+    L.apa_pinned_alloc.argtypes = [C.c_uint64]
+    L.apa_pinned_free.argtypes = [C.c_void_p]
     L.apa_generate_pair.restype = C.c_int64
     L.apa_generate_pair.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64]
     L.apa_generate_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64, vp, C.c_int]
@@ -116,6 +119,19 @@ def generate_batch(n_pairs, n, e, model=0, seed0=31415, threads=None):
     for p in range(n_pairs):
         b_all[b_off[p]:b_off[p + 1]] = b_buf[p * stride:p * stride + b_len[p]]
     return a_all[:n_pairs * n], a_off, b_all[:int(b_off[-1])], b_off
+
+
+def pinned_copy(arr):
+    """Copy a numpy array into page-locked host memory; returns a numpy view (keep it alive; never freed)."""
+    L = load_library()
+    arr = np.ascontiguousarray(arr)
+    p = L.apa_pinned_alloc(arr.nbytes)
+    if not p:
+        raise AstarPaError("pinned allocation failed: " + L.apa_last_error().decode())
+    buf = (C.c_uint8 * max(arr.nbytes, 1)).from_address(p)
+    out = np.frombuffer(buf, dtype=arr.dtype, count=arr.size).reshape(arr.shape)
+    out[...] = arr
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- engine

@@ -286,6 +286,19 @@ extern "C" void apa_engine_destroy(apa_engine* e) {
 
 extern "C" void apa_free(void* p) { free(p); }
 
+// Pinned (page-locked) host memory for the end-to-end path.
+extern "C" void* apa_pinned_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        set_err(APA_ERR_CUDA, "cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void apa_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     if (!b) return;
     if (e) cudaSetDevice(e->device);

@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py — the A*PA2 hot path on B200: GCUPS (effective DP cells/s) on synthetic n=100k, e=5% pairs.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic pairs (BASELINE.json configs[2]:
+n = 100 000, e = 5 %, with CIGAR traceback; --pairs pairs per GPU, weak scaling).
+`value`   : effective GCUPS = sum |a||b| / device time, inputs already resident in HBM (CUDA events on the
+            engine's stream around the kernels of each step).
+`e2e`     : the same metric through the public C-ABI batch call with HOST (pinned) buffers: H2D of the sequences,
+            kernels, D2H of costs + CIGAR text, every step.
+`roofline`: dominant kernel = apa_align_kernel (block DP + traceback). HBM: algorithmic bytes = 48 B per
+            64-row x 256-col lane-block x lane-blocks computed / kernel time vs the measured copy
+            peak; the kernel is INT32-ALU bound, so the int32 fraction is reported next to it.
+Inputs (2 GB at the default size) are larger than the 126 MB L2, so no explicit flush between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "GCUPS (effective DP cells/s, sum |a||b| / time) on n=100k e=5% pairs"
+UNIT = "GCUPS"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--preset", default=os.environ.get("APA_BENCH_PRESET", "simple"), choices=["simple", "full"])
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("APA_BENCH_PAIRS", "10000")), help="pairs per GPU")
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--e", type=float, default=0.05)
+    ap.add_argument("--no-trace", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(A, args, rank):
+    seed0 = 31415 + rank * args.pairs  # 31415: the reference's fixed seed (pa-test/src/lib.rs:51)
+    return A.generate_batch(args.pairs, args.n, args.e, 0, seed0)
+
+
+def cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, sample):
+    """Oracle (CPU port of the reference path) on a bounded sample, all host threads. Returns dict."""
+    import oracle_lib as O
+    threads = O.lib().oracle_hardware_threads()
+    if sample <= 0:
+        # calibrate on `threads` pairs, then size the sample for ~4 s of wall time
+        k = min(threads, len(a_off) - 1)
+        sec, *_ = O.align_batch(a_all[:a_off[k]], a_off[:k + 1], b_all[:b_off[k]], b_off[:k + 1], preset_id, trace, threads)
+        per_pair = max(sec, 1e-4) / 1.0  # k pairs ran concurrently on k threads: wall ~ one pair
+        sample = int(max(threads, min(len(a_off) - 1, 4.0 / per_pair * threads)))
+    sample = min(sample, len(a_off) - 1)
+    sec, costs, clens, cells, chash = O.align_batch(a_all[:a_off[sample]], a_off[:sample + 1], b_all[:b_off[sample]],
+                                                    b_off[:sample + 1], preset_id, trace, threads)
+    assert (costs >= 0).all(), "oracle panic in the CPU baseline"
+    eff = float(np.sum((a_off[1:sample + 1] - a_off[:sample]).astype(np.float64) * (b_off[1:sample + 1] - b_off[:sample])))
+    return {"value": eff / sec / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample} pairs of the same workload (n={args.n}, e={args.e}, preset {args.preset}, "
+                      f"{'with' if trace else 'no'} CIGAR), {sec:.2f} s wall on {threads} threads",
+            "computed_gcups": float(cells.sum()) / sec / 1e9, "bp_per_s": float(a_off[sample]) / sec, "seconds": sec,
+            "pairs": sample}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    trace = not args.no_trace
+    preset_id = {"simple": 0, "full": 1}[args.preset]
+    workload = (f"BASELINE configs[2]: {args.pairs} pairs/GPU, n={args.n}, e={args.e:g}, uniform errors, astarpa2_{args.preset}, "
+                f"{'cost+CIGAR' if trace else 'cost only'}; inputs {2 * args.pairs * args.n / 1e9:.2f} GB/GPU > L2 (no flush needed)")
+    config = {"workload": workload, "pairs_per_gpu": args.pairs, "n": args.n, "e": args.e, "preset": args.preset, "trace": trace,
+              "sharding": f"independent pairs, {world} rank(s), no data-path collective", "l2": "inputs larger than L2"}
+
+    import astar_pairwise_aligner_b200 as A
+
+    if args.impl == "reference":
+        # The reference's own CPU implementation of the path, restated (oracle port): the Rust crate cannot be
+        # built in this image (no cargo/rustc). Rank 0 only.
+        if rank != 0:
+            return
+        a_all, a_off, b_all, b_off = make_batch(A, args, 0)
+        first = cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, args.cpu_sample)
+        sample = first["pairs"]
+        secs = []
+        for it in range(args.warmup + args.steps):
+            r = cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, sample)
+            if it >= args.warmup:
+                secs.append(r["seconds"])
+            last = r
+        eff = float(np.sum((a_off[1:sample + 1] - a_off[:sample]).astype(np.float64) * (b_off[1:sample + 1] - b_off[:sample])))
+        val = eff * len(secs) / sum(secs) / 1e9
+        last["value"] = val
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+                          "cpu_baseline": last, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    a_all, a_off, b_all, b_off = make_batch(A, args, rank)
+    eng = A.Engine(local_rank)
+    eff_cells = float(np.sum((a_off[1:] - a_off[:-1]).astype(np.float64) * (b_off[1:] - b_off[:-1])))
+    total_bp = float(a_off[-1])
+    a_pin, b_pin = A.pinned_copy(a_all), A.pinned_copy(b_all)
+
+    # ---- resident-input timing (value)
+    batch = eng.upload(a_pin, a_off, b_pin, b_off)
+    for _ in range(args.warmup):
+        batch.run(preset_id, trace)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    kernel_ms, launches, st = 0.0, 0, None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.run(preset_id, trace)  # synchronises its stream; kernel_ms is CUDA-event time on that stream
+        st = batch.stats()
+        kernel_ms += st["kernel_ms"]
+        launches += st["kernel_launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    costs, pool, off, ln = batch.download_raw()
+    d2h_bytes = batch.stats()["d2h_bytes"]
+    batch.free_pool(pool)
+    ms_step = kernel_ms / args.steps
+
+    # ---- end-to-end through the public batch call with host buffers (e2e)
+    e2e_ms = []
+    h2d_bytes = 0
+    for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+        barrier()
+        t1 = time.perf_counter()
+        bt = eng.upload(a_pin, a_off, b_pin, b_off)
+        bt.run(preset_id, trace)
+        c2, pool2, off2, ln2 = bt.download_raw()
+        dt = (time.perf_counter() - t1) * 1e3
+        s2 = bt.stats()
+        h2d_bytes, d2h_bytes = s2["h2d_bytes"], s2["d2h_bytes"]
+        bt.free_pool(pool2)
+        bt.free()
+        if it > 0:
+            e2e_ms.append(dt)
+        assert (c2 == costs).all()
+    e2e_step = float(np.mean(e2e_ms)) if e2e_ms else float('nan')
+
+    # ---- reduce over ranks: max time, sum of work
+    agg = np.array([ms_step, e2e_step], dtype=np.float64)
+    work = np.array([eff_cells, float(st["computed_cells"]), total_bp, float(st["dp_word_steps"])], dtype=np.float64)
+    if dist is not None:
+        import torch
+        t_agg = torch.tensor(agg, device="cuda")
+        t_work = torch.tensor(work, device="cuda")
+        dist.all_reduce(t_agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_work, op=dist.ReduceOp.SUM)
+        agg, work = t_agg.cpu().numpy(), t_work.cpu().numpy()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms_step, e2e_step = float(agg[0]), float(agg[1])
+    eff_all, comp_all, bp_all, wsteps_all = work
+    value = eff_all / (ms_step / 1e3) / 1e9
+    hbm_peak, peak_src, sm_max = peaks()
+    # algorithmic HBM bytes: 48 B per (64 rows x 256 cols) lane-block = computed_cells * 48 / 16384 (per GPU, per launch)
+    comp_gpu = comp_all / world
+    alg_bytes = comp_gpu * 48.0 / 16384.0
+    achieved = alg_bytes / (ms_step / 1e3) / 1e9
+    # int32 ALU view: ~17 ALU-pipe instructions per 32-row word step; pipe peak = 148 SMs x 64 lanes/clk (B300_MICROARCH: rt_SMSP = 2)
+    sm_mhz = clocks.get("sm_mhz") or sm_max
+    int_ops = (wsteps_all / world) * 17.0
+    int_peak = 148 * 64 * sm_mhz * 1e6
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-vectors (i32 costs)",
+        "data": "synthetic", "config": config,
+        "computed_gcups": comp_all / (ms_step / 1e3) / 1e9, "aligned_bp_per_s": bp_all / (ms_step / 1e3),
+        "pairs_per_s": args.pairs * world / (ms_step / 1e3), "wall_ms_per_step": wall_ms / args.steps,
+        "passes_per_pair": st["passes"] / args.pairs, "retries": st["retries"],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "apa_align_kernel",
+                     "note": "INT32-ALU bound kernel: 0.003 algorithmic B/cell; see int32_* fields",
+                     "int32_ops_per_s": int_ops / (ms_step / 1e3), "int32_peak_ops_per_s": int_peak,
+                     "int32_frac": int_ops / (ms_step / 1e3) / int_peak},
+        "e2e": {"value": eff_all / (e2e_step / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                "ms_per_step": e2e_step},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1:
+        out["cpu_baseline"] = cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, args.cpu_sample)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,9 @@ int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar
 int apa_batch_get_stats(apa_batch* b, apa_batch_stats* out);
 void apa_batch_free(apa_engine* e, apa_batch* b);
 void apa_free(void* p);
+/* Page-locked host buffers for the end-to-end path (H2D/D2H at full PCIe rate). */
+void* apa_pinned_alloc(uint64_t bytes);
+void apa_pinned_free(void* p);
 
 /* Convenience: upload + run + download. */
 int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off,
