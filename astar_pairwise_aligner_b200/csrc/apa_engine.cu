@@ -13,6 +13,7 @@
 
 #include "../../include/astarpa.h"
 #include "../../include/astarpa_b200.h"
+#include "apa_gcsh.cuh"
 #include "apa_trace.cuh"
 
 using namespace apa;
@@ -148,7 +149,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
                 cost = dev_band_doubling(cx, sm, hh, h0);
                 if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
             } else {
-                cx.status = ST_ASSERT;  // GCSH path: see apa_gcsh.cuh (not linked in this build)
+                GcshH hh;
+                if (gcsh_build(cx, hh)) {
+                    Cost h0 = hh.h(0, 0);
+                    cost = dev_band_doubling(cx, sm, hh, h0);
+                    if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
+                }
             }
         }
         if (cx.status == ST_PENDING && bd.trace) {
@@ -397,7 +403,8 @@ static uint32_t estimate_arena(const apa_batch* b, int preset, int trace) {
                                                      : std::min<uint64_t>((uint64_t)b->max_m + 64, 2048);
     uint64_t vcols = nblk * (band_rows / 32 * 12 + 16);
     uint64_t tr = trace ? (DT_CACHE_ELEMS * 8 + 256 * (band_rows / 32) * 8 / 4 + (uint64_t)(b->max_n + b->max_m) / 4 * 4 + 65536) : 0;
-    uint64_t s = meta + vcols + tr + 16384;
+    uint64_t heur = preset == APA_PRESET_FULL ? 24ull * (uint64_t)b->max_n + 65536 : 0;  // k-mer table, matches, contours
+    uint64_t s = meta + vcols + tr + heur + 16384;
     s = (s + 1023) & ~1023ull;
     return (uint32_t)std::min<uint64_t>(s, 0xF0000000ull);
 }

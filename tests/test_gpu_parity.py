@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
 
-PRESETS = [0]  # extended to [0, 1] once the GCSH path is linked (see test_gpu_gcsh.py)
+PRESETS = [0, 1]  # astarpa2_simple, astarpa2_full
 
 
 def _check_pairs(apa, oracle, pairs, preset, trace=True):
@@ -98,17 +98,18 @@ def test_batch_mixed_lengths_gpu(apa, oracle, preset):
     _check_pairs(apa, oracle, pairs, preset)
 
 
-def test_band_log_matches_oracle(apa, oracle):
-    for n, e in [(3000, 0.1), (20000, 0.05)]:
+@pytest.mark.parametrize("preset", PRESETS)
+def test_band_log_matches_oracle(apa, oracle, preset):
+    for n, e in [(3000, 0.1), (20000, 0.05), (20000, 0.15)]:
         a, b = apa.generate_pair(n, e, 0, 5)
-        assert oracle.parse_band_log(_gpu_band_log(apa, a, b, 0)) == oracle.band_log(a, b, 0, True)
+        assert oracle.parse_band_log(_gpu_band_log(apa, a, b, preset)) == oracle.band_log(a, b, preset, True)
 
 
 def test_drop_in_symbols_gpu(apa):
     # astarpa-c/example.c:8-33 through ctypes: cost 2 through every entry point, CIGAR released by astarpa_free_cigar.
     L = apa.load_library()
     a, b = b"ACTCGCT", b"AACTCGTT"
-    for fn in (L.astarpa2_simple,):
+    for fn in (L.astarpa2_simple, L.astarpa2_full, L.astarpa):
         cig = C.c_void_p()
         ln = C.c_size_t()
         cost = fn(a, len(a), b, len(b), C.byref(cig), C.byref(ln))
