@@ -32,10 +32,13 @@ class BatchStats(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("computed_cells", C.c_uint64),
                 ("dp_word_steps", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("retries", C.c_uint64), ("fill_blocks", C.c_uint64), ("dt_blocks", C.c_uint64)]
+                ("retries", C.c_uint64), ("fill_blocks", C.c_uint64), ("dt_blocks", C.c_uint64),
+                ("phase_cycles", C.c_uint64 * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_cycles"] = list(d["phase_cycles"])
+        return d
 
 
 def lib_path():

@@ -17,6 +17,7 @@ struct PairCtx {
     const uint8_t* a;
     const uint8_t* b;
     const uint2* bprof;  // negated bit planes of b per 32 rows (profile.rs:124-131), zero padded to a multiple of 64 rows
+    const uint2* aprof;  // the same packing of a (used by the diagonal extensions)
     uint8_t* arena;      // per-pair scratch
     uint32_t arena_size;
     BlkMeta* meta;       // nblk + 1 entries (entry 0 = column 0)
@@ -30,6 +31,9 @@ struct PairCtx {
     unsigned long long word_steps, computed_cells;
     int passes;
     int fill_blocks, dt_blocks;
+    // phase timers (SM clock cycles of this warp): [0] heuristic build [1] block DP [2] passes total [3] traceback total
+    // [4] DT-trace [5] CIGAR text [6] h() calls [7] prune_block/update_contours
+    long long tphase[8];
     // optional band log (apa_debug_band_log): records of 7 ints {pass, f_max, block, j_s, j_e, fixed_s, fixed_e}
     int32_t* dbg;
     uint32_t dbg_cap, dbg_n;
@@ -168,7 +172,11 @@ template <class Hh>
 __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
     const int lane = threadIdx.x & 31;
     cx.passes++;
-    if (Hh::PRUNE) hh.update_contours();
+    if (Hh::PRUNE) {
+        long long t_u0 = clock64();
+        hh.update_contours();
+        cx.tphase[7] += clock64() - t_u0;
+    }
     cx.v_top = cx.v_base;  // blocks are recomputed in every pass
 
     // Column 0 (domain.rs:395-413, blocks.rs:146-179).
@@ -224,8 +232,10 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         stage_amask(sm, cx.a, is, ie - is, lane);
         uint2* vout = (uint2*)(cx.arena + off);
         int32_t* cumout = (int32_t*)(cx.arena + off + (size_t)nhw * 8);
+        long long t_dp0 = clock64();
         Cost bot_val = block_dp<false>(sm, cx.bprof, prev, ie - is, rounded.s, rounded.e, vout, cumout, top_val, nullptr,
                                        cx.word_steps);
+        cx.tphase[1] += clock64() - t_dp0;
         cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
 
         BlkMeta nm;
@@ -270,8 +280,10 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         dbg_log(cx, f_max, t, jr, stored);
 
         if (Hh::PRUNE) {
+            long long t_p0 = clock64();
             JRange inter = jr_inter(prev_fixed, next_fixed);
             if (!jr_empty(inter)) hh.prune_block(is, ie, inter.s, inter.e);
+            cx.tphase[7] += clock64() - t_p0;
         }
     }
     // dist = last_block.get(|b|) (domain.rs:520-522)

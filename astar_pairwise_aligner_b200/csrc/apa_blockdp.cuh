@@ -47,6 +47,53 @@ __device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint8_t* __restr
     __syncwarp();
 }
 
+// One chunk (<= 32 half-words) of the wavefront. FIRST: the chunk touches the top edge of the band (+1 deltas
+// enter lane 0); otherwise lane 0 reads the previous chunk's bottom deltas from sm.hrow. HAND_OFF: the last active
+// lane publishes its bottom deltas for the next chunk. The sweep is split into ramp-up / steady / ramp-down so the
+// steady state (all active lanes busy) runs without per-lane guards.
+template <bool FILL, bool FIRST, bool HAND_OFF>
+__device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint32_t b0, uint32_t b1, uint32_t& vp, uint32_t& vm,
+                                         uint2* __restrict__ fillcol /* fillvals + hw */, int nhw) {
+    const int lane = threadIdx.x & 31;
+    const bool act_lane = lane < nact;
+    const bool is_top = lane == 0;
+    const bool is_bot = lane == nact - 1;
+    const int r = act_lane ? lane : 0;  // idle lanes shadow lane 0 on valid addresses; their results are never stored
+    uint32_t hp_o = 0u, hm_o = 0u;
+    auto step = [&](int t, bool guarded) {
+        uint32_t hpi = __shfl_up_sync(FULL, hp_o, 1);
+        uint32_t hmi = __shfl_up_sync(FULL, hm_o, 1);
+        if (FIRST) {
+            hpi = is_top ? 0x80000000u : hpi;
+            hmi = is_top ? 0u : hmi;
+        } else {
+            uint32_t x = sm.hrow[min(t, ncols - 1)];
+            hpi = is_top ? ((x & 1u) << 31) : hpi;
+            hmi = is_top ? ((x & 2u) << 30) : hmi;
+        }
+        const int col = t - r;
+        if (!guarded || (unsigned)col < (unsigned)ncols) {
+            uint2 am = sm.amask[col];
+            myers_step(am.x, am.y, b0, b1, vp, vm, hpi, hmi, hp_o, hm_o);
+            if (HAND_OFF) {
+                if (is_bot) sm.hrow[col] = (uint8_t)((hp_o >> 31) | ((hm_o >> 31) << 1));
+            }
+            if (FILL) {
+                if (act_lane) fillcol[(size_t)col * nhw] = make_uint2(vp, vm);
+            }
+        }
+    };
+    int t = 0;
+    const int t_steady = min(nact - 1, ncols);  // first step at which every active lane has a valid column
+    for (; t < t_steady; t++) step(t, true);
+    if (nact - 1 < ncols) {
+#pragma unroll 4
+        for (; t < ncols; t++) step(t, false);
+    }
+    const int T = ncols + nact - 1;
+    for (; t < T; t++) step(t, true);
+}
+
 // Compute the right-edge column of a block.
 //   prev      : stored column to the left (rows outside it start from +1 deltas: init_v_with_overlap, blocks.rs:753-767)
 //   njs, nje  : rounded-out row range of the new block (multiples of 64)
@@ -78,29 +125,18 @@ __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const Bl
             b0 = bb.x;
             b1 = bb.y;
         }
-        uint32_t hp_o = 0u, hm_o = 0u;
-        const int T = ncols + nact - 1;
         const bool hand_off = (c + 1 < nchunks);
-        for (int t = 0; t < T; t++) {
-            uint32_t hpi = __shfl_up_sync(FULL, hp_o, 1);
-            uint32_t hmi = __shfl_up_sync(FULL, hm_o, 1);
-            if (lane == 0) {
-                if (c == 0) {
-                    hpi = 0x80000000u;
-                    hmi = 0u;
-                } else {
-                    uint32_t x = (t < ncols) ? sm.hrow[t] : 0u;
-                    hpi = (x & 1u) << 31;
-                    hmi = (x & 2u) << 30;
-                }
-            }
-            const int col = t - lane;
-            if (act_lane && (unsigned)col < (unsigned)ncols) {
-                uint2 am = sm.amask[col];
-                myers_step(am.x, am.y, b0, b1, vp, vm, hpi, hmi, hp_o, hm_o);
-                if (hand_off && lane == nact - 1) sm.hrow[col] = (uint8_t)((hp_o >> 31) | ((hm_o >> 31) << 1));
-                if (FILL) fillvals[(size_t)col * nhw + hw] = make_uint2(vp, vm);
-            }
+        uint2* fillcol = FILL ? fillvals + hw : nullptr;
+        if (c == 0) {
+            if (hand_off)
+                dp_chunk<FILL, true, true>(sm, ncols, nact, b0, b1, vp, vm, fillcol, nhw);
+            else
+                dp_chunk<FILL, true, false>(sm, ncols, nact, b0, b1, vp, vm, fillcol, nhw);
+        } else {
+            if (hand_off)
+                dp_chunk<FILL, false, true>(sm, ncols, nact, b0, b1, vp, vm, fillcol, nhw);
+            else
+                dp_chunk<FILL, false, false>(sm, ncols, nact, b0, b1, vp, vm, fillcol, nhw);
         }
         __syncwarp();
         if (act_lane) vout[hw] = make_uint2(vp, vm);

@@ -101,6 +101,51 @@ __device__ __forceinline__ uint32_t rank_acgt(uint32_t c) {
 }
 __device__ __forceinline__ bool is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
+// ---- 2-bit-plane packed sequences: prof[hw] = (negated rank bit0, negated rank bit1) of 32 consecutive bases.
+// Every per-pair plane array carries two zero half-words of padding, so extract32 may read prof[hw + 1].
+__device__ __forceinline__ uint2 extract32(const uint2* __restrict__ prof, I pos) {  // bits of bases [pos, pos + 32)
+    int hw = pos >> 5, sh = pos & 31;
+    uint2 lo = prof[hw], hi = prof[hw + 1];
+    return make_uint2(__funnelshift_r(lo.x, hi.x, sh), __funnelshift_r(lo.y, hi.y, sh));
+}
+__device__ __forceinline__ uint2 extract32_end(const uint2* __restrict__ prof, I pos) {  // bit 31 = base pos - 1 (pos >= 1)
+    if (pos >= 32) return extract32(prof, pos - 32);
+    uint2 x = prof[0];
+    int sh = 32 - pos;
+    return make_uint2(x.x << sh, x.y << sh);
+}
+// extend_right (pa-heuristic/src/matches/prepruning.rs:25-32): advance (i, j) along the diagonal while a[i] == b[j],
+// i < end_i, j < m; 32 bases per iteration.
+__device__ __forceinline__ void extend_right_packed(const uint2* __restrict__ ap, const uint2* __restrict__ bp, I m, I& i, I j, I end_i) {
+    for (;;) {
+        int len = min(32, min(end_i - i, m - j));
+        if (len <= 0) return;
+        uint2 A = extract32(ap, i), B = extract32(bp, j);
+        uint32_t mm = (A.x ^ B.x) | (A.y ^ B.y);
+        if (len < 32) mm |= 0xffffffffu << len;
+        int run = mm ? __ffs(mm) - 1 : 32;
+        i += run;
+        j += run;
+        if (run < 32) return;
+    }
+}
+// extend_left (astarpa2/src/blocks/trace.rs:443-451): step (i, j) back while a[i-1] == b[j-1], i > i0, j > 0.
+__device__ __forceinline__ I extend_left_packed(const uint2* __restrict__ ap, const uint2* __restrict__ bp, I& i, I i0, I& j) {
+    I cnt = 0;
+    for (;;) {
+        int len = min(32, min(i - i0, j));
+        if (len <= 0) return cnt;
+        uint2 A = extract32_end(ap, i), B = extract32_end(bp, j);
+        uint32_t mm = (A.x ^ B.x) | (A.y ^ B.y);
+        if (len < 32) mm |= 0x80000000u >> len;
+        int run = mm ? __clz(mm) : 32;
+        i -= run;
+        j -= run;
+        cnt += run;
+        if (run < 32) return cnt;
+    }
+}
+
 // CIGAR element: op in the top 2 bits, count in the low 30 (pa-types CigarElem; trace.rs:129-221).
 enum CigOp : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3 };
 __device__ __forceinline__ uint32_t cig_pack(uint32_t op, uint32_t cnt) { return (op << 30) | cnt; }

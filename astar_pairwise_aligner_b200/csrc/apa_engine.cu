@@ -38,8 +38,10 @@ struct BatchDev {
     const uint8_t* b_all;
     const int64_t* a_off;
     const int64_t* b_off;
-    const int64_t* bp_off;  // per pair offset into bprof, in 32-row half-words
+    const int64_t* bp_off;  // per pair offset into bprof, in 32-row half-words (two padding half-words per pair)
     uint2* bprof;
+    const int64_t* ap_off;  // the same for a
+    uint2* aprof;
     int32_t* status;  // per pair
     int32_t* bad;     // per pair: input byte outside ACGT (written once by the pack kernel)
     int32_t* cost;    // per pair
@@ -53,7 +55,7 @@ struct BatchDev {
     char* pool;
     unsigned long long* pool_cursor;
     unsigned long long pool_cap;
-    unsigned long long* stats;  // [0] word_steps [1] computed_cells [2] passes [3] fill_blocks [4] dt_blocks
+    unsigned long long* stats;  // [0] word_steps [1] computed_cells [2] passes [3] fill_blocks [4] dt_blocks [5..12] phase cycles
     int preset;
     int trace;
     int32_t* dbg;  // band log of the (single) pair, or nullptr
@@ -73,8 +75,25 @@ __global__ void apa_pack_kernel(BatchDev bd) {
     const int64_t nhw = ((m + 63) / 64) * 2;
     uint2* out = bd.bprof + bd.bp_off[p];
     bool bad = false;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) bad |= !is_acgt(a[i]);
-    for (int64_t hw = threadIdx.x; hw < nhw; hw += blockDim.x) {
+    {
+        const int64_t nhw_a = ((n + 63) / 64) * 2;
+        uint2* outa = bd.aprof + bd.ap_off[p];
+        for (int64_t hw = threadIdx.x; hw < nhw_a + 2; hw += blockDim.x) {
+            uint32_t b0 = 0, b1 = 0;
+            for (int t = 0; t < 32; t++) {
+                int64_t i = hw * 32 + t;
+                if (i < n) {
+                    uint32_t c = a[i];
+                    bad |= !is_acgt(c);
+                    uint32_t r = rank_acgt(c);
+                    b0 |= ((r & 1u) ^ 1u) << t;
+                    b1 |= ((r >> 1) ^ 1u) << t;
+                }
+            }
+            outa[hw] = make_uint2(b0, b1);
+        }
+    }
+    for (int64_t hw = threadIdx.x; hw < nhw + 2; hw += blockDim.x) {
         uint32_t b0 = 0, b1 = 0;
         int64_t j0 = hw * 32;
         for (int t = 0; t < 32; t++) {
@@ -96,7 +115,7 @@ constexpr int WARPS_PER_CTA = 4;
 
 // K1+K3 fused per pair: a persistent warp pulls pairs from the device work queue and runs the band-doubling
 // search, the traceback and the CIGAR text emission for each.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev bd) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchDev bd) {
     __shared__ WarpSmem smem[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -104,6 +123,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + wib;
     uint8_t* arena = bd.arena + (size_t)slot * bd.arena_size;
     unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0;
+    long long acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     for (;;) {
         unsigned long long q = 0;
@@ -122,6 +142,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
         cx.a = bd.a_all + bd.a_off[p];
         cx.b = bd.b_all + bd.b_off[p];
         cx.bprof = bd.bprof + bd.bp_off[p];
+        cx.aprof = bd.aprof + bd.ap_off[p];
         cx.arena = arena;
         cx.arena_size = bd.arena_size;
         cx.nblk = (cx.n + BLOCK_W - 1) / BLOCK_W;
@@ -135,6 +156,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
         cx.word_steps = cx.computed_cells = 0;
         cx.passes = 0;
         cx.fill_blocks = cx.dt_blocks = 0;
+        for (int t = 0; t < 8; t++) cx.tphase[t] = 0;
         cx.dbg = bd.dbg;
         cx.dbg_cap = bd.dbg_cap;
         cx.dbg_n = 0;
@@ -146,13 +168,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
             if (bd.preset == APA_PRESET_SIMPLE) {
                 GapH hh{cx.n, cx.m};
                 Cost h0 = hh.h(0, 0);
+                long long t0 = clock64();
                 cost = dev_band_doubling(cx, sm, hh, h0);
+                cx.tphase[2] += clock64() - t0;
                 if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
             } else {
                 GcshH hh;
-                if (gcsh_build(cx, hh)) {
+                long long t0 = clock64();
+                bool built = gcsh_build(cx, hh);
+                cx.tphase[0] += clock64() - t0;
+                if (built) {
                     Cost h0 = hh.h(0, 0);
+                    t0 = clock64();
                     cost = dev_band_doubling(cx, sm, hh, h0);
+                    cx.tphase[2] += clock64() - t0;
+                    cx.tphase[6] += hh.t_h;
                     if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
                 }
             }
@@ -164,8 +194,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
             cw.count = 0;
             cw.pend_cnt = 0;
             cw.pend_op = 0;
-            if (dev_trace(cx, sm, cw, cost)) {
+            long long t0 = clock64();
+            bool traced = dev_trace(cx, sm, cw, cost);
+            cx.tphase[3] += clock64() - t0;
+            if (traced) {
+                t0 = clock64();
                 cig_off = emit_cigar_text(cw, bd.pool, bd.pool_cursor, bd.pool_cap, &cig_len);
+                cx.tphase[5] += clock64() - t0;
                 if (cig_off < 0) cx.status = ST_OVERFLOW;
             }
         }
@@ -181,6 +216,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
         acc_pass += cx.passes;
         acc_fill += cx.fill_blocks;
         acc_dt += cx.dt_blocks;
+        for (int t = 0; t < 8; t++) acc_t[t] += cx.tphase[t];
     }
     if (lane == 0) {
         atomicAdd(&bd.stats[0], acc_steps);
@@ -188,6 +224,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) apa_align_kernel(BatchDev 
         atomicAdd(&bd.stats[2], acc_pass);
         atomicAdd(&bd.stats[3], acc_fill);
         atomicAdd(&bd.stats[4], acc_dt);
+        for (int t = 0; t < 8; t++) atomicAdd(&bd.stats[5 + t], (unsigned long long)acc_t[t]);
     }
 }
 
@@ -227,12 +264,12 @@ struct apa_engine {
 
 struct apa_batch {
     uint64_t n_pairs = 0;
-    std::vector<int64_t> a_off, b_off, bp_off;
-    uint64_t total_a = 0, total_b = 0, total_hw = 0;
+    std::vector<int64_t> a_off, b_off, bp_off, ap_off;
+    uint64_t total_a = 0, total_b = 0, total_hw = 0, total_hw_a = 0;
     I max_n = 0, max_m = 0;
     uint8_t *d_a = nullptr, *d_b = nullptr;
-    int64_t *d_a_off = nullptr, *d_b_off = nullptr, *d_bp_off = nullptr;
-    uint2* d_bprof = nullptr;
+    int64_t *d_a_off = nullptr, *d_b_off = nullptr, *d_bp_off = nullptr, *d_ap_off = nullptr;
+    uint2 *d_bprof = nullptr, *d_aprof = nullptr;
     int32_t *d_status = nullptr, *d_cost = nullptr, *d_bad = nullptr;
     int64_t *d_cig_off = nullptr, *d_cig_len = nullptr;
     uint32_t* d_order = nullptr;
@@ -314,6 +351,8 @@ extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     cudaFree(b->d_b_off);
     cudaFree(b->d_bp_off);
     cudaFree(b->d_bprof);
+    cudaFree(b->d_aprof);
+    cudaFree(b->d_ap_off);
     cudaFree(b->d_status);
     cudaFree(b->d_bad);
     cudaFree(b->d_cost);
@@ -334,7 +373,8 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
     b->a_off.assign(a_off, a_off + n_pairs + 1);
     b->b_off.assign(b_off, b_off + n_pairs + 1);
     b->bp_off.resize(n_pairs + 1);
-    uint64_t hw = 0;
+    b->ap_off.resize(n_pairs + 1);
+    uint64_t hw = 0, hwa = 0;
     for (uint64_t p = 0; p < n_pairs; p++) {
         int64_t n = a_off[p + 1] - a_off[p], m = b_off[p + 1] - b_off[p];
         if (n < 0 || m < 0 || n >= (1ll << 31) - 1024 || m >= (1ll << 31) - 1024) {
@@ -344,10 +384,14 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
         b->max_n = std::max<I>(b->max_n, (I)n);
         b->max_m = std::max<I>(b->max_m, (I)m);
         b->bp_off[p] = (int64_t)hw;
-        hw += (uint64_t)((m + 63) / 64) * 2;
+        hw += (uint64_t)((m + 63) / 64) * 2 + 2;
+        b->ap_off[p] = (int64_t)hwa;
+        hwa += (uint64_t)((n + 63) / 64) * 2 + 2;
     }
     b->bp_off[n_pairs] = (int64_t)hw;
+    b->ap_off[n_pairs] = (int64_t)hwa;
     b->total_hw = hw;
+    b->total_hw_a = hwa;
     b->total_a = (uint64_t)(a_off[n_pairs] - a_off[0]);
     b->total_b = (uint64_t)(b_off[n_pairs] - b_off[0]);
     // Rebase offsets to the start of the copied ranges.
@@ -371,6 +415,8 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
     CUDA_TRY(cudaMalloc(&b->d_b_off, (n_pairs + 1) * 8));
     CUDA_TRY(cudaMalloc(&b->d_bp_off, (n_pairs + 1) * 8));
     CUDA_TRY(cudaMalloc(&b->d_bprof, std::max<uint64_t>(hw, 2) * 8));
+    CUDA_TRY(cudaMalloc(&b->d_aprof, std::max<uint64_t>(hwa, 2) * 8));
+    CUDA_TRY(cudaMalloc(&b->d_ap_off, (n_pairs + 1) * 8));
     CUDA_TRY(cudaMalloc(&b->d_status, std::max<uint64_t>(n_pairs, 1) * 4));
     CUDA_TRY(cudaMalloc(&b->d_cost, std::max<uint64_t>(n_pairs, 1) * 4));
     CUDA_TRY(cudaMalloc(&b->d_bad, std::max<uint64_t>(n_pairs, 1) * 4));
@@ -383,6 +429,7 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
     CUDA_TRY(cudaMemcpyAsync(b->d_a_off, ao.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_b_off, bo.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_bp_off, b->bp_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_ap_off, b->ap_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_pairs) CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), n_pairs * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -437,6 +484,8 @@ extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace)
     bd.b_off = b->d_b_off;
     bd.bp_off = b->d_bp_off;
     bd.bprof = b->d_bprof;
+    bd.ap_off = b->d_ap_off;
+    bd.aprof = b->d_aprof;
     bd.status = b->d_status;
     bd.bad = b->d_bad;
     bd.cost = b->d_cost;
@@ -467,7 +516,7 @@ extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace)
     std::vector<uint32_t> pending;  // empty = all pairs in the uploaded order
     b->h_status.assign(b->n_pairs, 0);
     for (int attempt = 0; attempt < 8; attempt++) {
-        int ctas_per_sm = 4;
+        int ctas_per_sm = 8;
         uint64_t want_slots = (uint64_t)e->sm_count * ctas_per_sm * WARPS_PER_CTA;
         uint64_t n_work = attempt == 0 ? b->n_pairs : pending.size();
         uint64_t slots = std::min<uint64_t>(want_slots, ((n_work + WARPS_PER_CTA - 1) / WARPS_PER_CTA) * WARPS_PER_CTA);
@@ -528,6 +577,7 @@ extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace)
     b->stats.passes = h_q[4];
     b->stats.fill_blocks = h_q[5];
     b->stats.dt_blocks = h_q[6];
+    for (int t = 0; t < 8; t++) b->stats.phase_cycles[t] = h_q[7 + t];
     b->ran = true;
     for (uint64_t p = 0; p < b->n_pairs; p++) {
         if (b->h_status[p] == ST_BAD_INPUT) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT in pair " + std::to_string(p));

@@ -47,6 +47,7 @@ struct GcshH {
     int hint;
     bool dirty;
     unsigned long long h_calls;
+    long long t_h;
 
     // Seeds::potential (seeds.rs:79-81) for fixed-length seeds at 0, k, 2k, ...: number of seeds starting at >= i.
     __device__ __forceinline__ Cost pot(I i) const {
@@ -93,14 +94,19 @@ struct GcshH {
     // CSHI::h / h_with_hint (csh.rs:341-376): P(u) - layer(T(u)), or max(gap, potential) to the target in layer 0.
     __device__ Cost h(I i, I j) {
         h_calls++;
+        long long t0 = clock64();
         Cost p = pot(i);
         int val = score(i - j - p, j - i - p);
+        Cost r;
         if (val == 0) {
             I d = (n - i) - (m - j);
             Cost gap = d < 0 ? -d : d;
-            return max(gap, p);  // potential_distance(pos, target) = P(pos) (seeds.rs:84-88: no seed covers i = n)
+            r = max(gap, p);  // potential_distance(pos, target) = P(pos) (seeds.rs:84-88: no seed covers i = n)
+        } else {
+            r = p - val;
         }
-        return p - val;
+        t_h += clock64() - t0;
+        return r;
     }
     // HintContours::new over the active arrows (hint_contours.rs:213-255) == state after update_layers.
     __device__ void build_layers() {
@@ -165,30 +171,6 @@ struct GcshH {
 };
 
 // ------------------------------------------------------------------------------------------------ local pruning
-// extend_right (prepruning.rs:25-32), one diagonal per lane.
-__device__ __forceinline__ void lane_extend_right(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, I m, I& i, I j, I end_i) {
-    while (i < end_i && j < m && a[i] == b[j]) {
-        i++;
-        j++;
-    }
-}
-// Warp-cooperative extend_right from one point.
-__device__ __forceinline__ I coop_extend_right(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, I m, I i, I j, I end_i) {
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        I ii = i + lane, jj = j + lane;
-        bool ok = ii < end_i && jj < m && a[ii] == b[jj];
-        unsigned bal = __ballot_sync(FULL, ok);
-        int run = __ffs(~bal) - 1;
-        if (run < 0) {
-            i += 32;
-            j += 32;
-            continue;
-        }
-        return i + run;
-    }
-}
-
 struct NmpdView {  // next_match_per_diag (matches.rs:147-148): diagonal -> start.i of the left-most kept match, default MAX
     I* v;
     I dmin, dmax;
@@ -196,7 +178,7 @@ struct NmpdView {  // next_match_per_diag (matches.rs:147-148): diagonal -> star
 };
 
 // preserve_for_local_pruning (prepruning.rs:95-203) for an exact match starting at (si, sj). Warp-uniform result.
-__device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, I si, I sj,
+__device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I si, I sj,
                                                const NmpdView& nm) {
     const int lane = threadIdx.x & 31;
     const I ei = si + GCSH_K, ej = sj + GCSH_K;
@@ -207,7 +189,8 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint8_t* __
     const Cost end_pot = H.pot(end_i);
     const int pd = start_pot - end_pot;  // <= GCSH_P
     // g = 0
-    I f0 = coop_extend_right(a, b, H.m, ei, ej, end_i);
+    I f0 = ei;
+    extend_right_packed(ap, bp, H.m, f0, ej, end_i);
     if (f0 >= end_i) return true;
     if (nm.get(ei - ej) <= f0) return true;
     // lanes 0 .. 2*pd hold the front; lane d <-> diagonal e + (d - pd)
@@ -238,7 +221,7 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint8_t* __
             I dd = ei - ej + (lane - pd);
             I j = fr - dd;
             I old_i = fr;
-            lane_extend_right(a, b, H.m, fr, j, end_i);
+            extend_right_packed(ap, bp, H.m, fr, j, end_i);
             I nmv = nm.get(dd);
             ok = (fr >= end_i) || (old_i <= nmv && nmv <= fr);
         }
@@ -263,6 +246,7 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     H.ttx = n - m;  // transform(target): P(n) = 0
     H.tty = m - n;
     H.h_calls = 0;
+    H.t_h = 0;
     H.hint = 0;
     H.dirty = false;
     H.nlayers = 0;
@@ -385,7 +369,7 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
                 // MatchBuilder::push (matches.rs:205-247)
                 const Cost p = H.pot(si);
                 const bool pass_t = (si - jj - p <= H.ttx) && (jj - si - p <= H.tty);
-                if (pass_t && dev_preserve_for_local_pruning(H, a, b, si, jj, nm)) {
+                if (pass_t && dev_preserve_for_local_pruning(H, cx.aprof, cx.bprof, si, jj, nm)) {
                     if (M >= mcap) {
                         cx.status = ST_OVERFLOW;
                         return false;

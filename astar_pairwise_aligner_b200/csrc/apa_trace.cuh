@@ -49,34 +49,6 @@ __device__ __forceinline__ void cig_flush(PairCtx& cx, CigarWriter& cw) {
     cw.pend_cnt = 0;
 }
 
-// Warp-cooperative greedy backward matching: number of equal characters a[i-1-k] == b[j-1-k], k = 0.., while
-// i-k > i0 and j-k > 0 (extend_left, trace.rs:443-451).
-__device__ __forceinline__ I coop_extend_left(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, I i, I i0, I j) {
-    const int lane = threadIdx.x & 31;
-    I cnt = 0;
-    for (;;) {
-        I ii = i - cnt - lane, jj = j - cnt - lane;
-        bool ok = ii > i0 && jj > 0 && a[ii - 1] == b[jj - 1];
-        unsigned bal = __ballot_sync(FULL, ok);
-        int run = __ffs(~bal) - 1;  // leading matches; -1 when all 32 match
-        if (run < 0) {
-            cnt += 32;
-            continue;
-        }
-        return cnt + run;
-    }
-}
-// Per-lane version (each lane extends its own diagonal).
-__device__ __forceinline__ I lane_extend_left(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, I& i, I i0, I& j) {
-    I cnt = 0;
-    while (i > i0 && j > 0 && a[i - 1] == b[j - 1]) {
-        i--;
-        j--;
-        cnt++;
-    }
-    return cnt;
-}
-
 // A column of the dense (re-filled) region or a stored sparse block, as seen by parent().
 struct ColRef {
     BlkView v;       // for fill columns: js/je/top_val set, v points at the column's words, cum == nullptr
@@ -138,8 +110,6 @@ __device__ __forceinline__ ColRef fill_col(const TraceState& ts, int c) {
 __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceState& ts, const BlkView& prev, I block_start,
                              int2* cache) {
     const int lane = threadIdx.x & 31;
-    const uint8_t* a = cx.a;
-    const uint8_t* b = cx.b;
     const I si = ts.ti, sj = ts.tj;
     const Cost g_st = ts.g;
     auto idx = [](int g, int d) { return g * g + g + d; };
@@ -155,8 +125,8 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
     int found_d = 0;
     bool found = false;
     {
-        I ext = coop_extend_left(a, b, si, block_start, sj);
-        I i = si - ext, j = sj - ext;
+        I i = si, j = sj;
+        I ext = extend_left_packed(cx.aprof, cx.bprof, i, block_start, j);
         if (lane == 0) cache[0] = make_int2(i, (ext << 2) | 1);
         __syncwarp();
         if (reached(i, j, g_st)) found = true;
@@ -190,7 +160,7 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
                 I i = best, ext = 0;
                 if (best != INT32_MAX) {
                     I j = sj - (si - i) - d;
-                    ext = lane_extend_left(a, b, i, block_start, j);
+                    ext = extend_left_packed(cx.aprof, cx.bprof, i, block_start, j);
                     ok = reached(i, j, g_st - ng);
                     min_fr = min(min_fr, (I)(2u * (uint32_t)i - (uint32_t)d));
                     min_i = min(min_i, i);
@@ -304,7 +274,10 @@ __device__ bool dev_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, Cost cost)
             const BlkMeta pm = cx.meta[ts.top - 1];
             if (pm.col_e < ts.ti - 1) {
                 const BlkView prev = view_of(cx, pm);
-                if (dev_dt_trace(cx, sm, cw, ts, prev, pm.col_e, cache)) {
+                long long t_dt0 = clock64();
+                bool dt_ok = dev_dt_trace(cx, sm, cw, ts, prev, pm.col_e, cache);
+                cx.tphase[4] += clock64() - t_dt0;
+                if (dt_ok) {
                     cx.dt_blocks++;
                     if (cx.status != ST_PENDING) return false;
                     continue;
@@ -376,10 +349,8 @@ __device__ bool dev_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, Cost cost)
                 }
             }
             // Greedy matching.
-            I cnt = coop_extend_left(cx.a, cx.b, ts.ti, 0, ts.tj);
+            I cnt = extend_left_packed(cx.aprof, cx.bprof, ts.ti, 0, ts.tj);
             if (cnt > 0) {
-                ts.ti -= cnt;
-                ts.tj -= cnt;
                 cig_push(cx, cw, OP_MATCH, (uint32_t)cnt);
             } else {
                 int vd = col_get_diff(block, ts.tj - 1);

@@ -265,6 +265,8 @@ def main():
         "e2e": {"value": eff_all / (e2e_step / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": e2e_step},
         "gpu_launches": int(launches), "clocks": clocks,
+        "phase_cycles": dict(zip(["heuristic_build", "block_dp", "passes_total", "trace_total", "dt_trace", "cigar_text", "h_queries", "prune_update"],
+                                 [int(x) for x in st["phase_cycles"]])),
     }
     if world == 1:
         out["cpu_baseline"] = cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, args.cpu_sample)

@@ -45,6 +45,9 @@ typedef struct apa_batch_stats {
     uint64_t kernel_launches;
     uint64_t retries;        /* pairs re-run with a larger scratch arena */
     uint64_t fill_blocks, dt_blocks; /* traceback: blocks re-filled / solved by DT-trace (TraceStats, trace.rs:3-14) */
+    /* SM-clock cycles summed over warps: [0] heuristic build [1] block DP [2] passes total [3] traceback total
+     * [4] DT-trace [5] CIGAR text [6] h() queries [7] match pruning + contour rebuilds */
+    uint64_t phase_cycles[8];
 } apa_batch_stats;
 
 const char* apa_last_error(void);
