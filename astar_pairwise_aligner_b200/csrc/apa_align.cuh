@@ -173,9 +173,9 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
     const int lane = threadIdx.x & 31;
     cx.passes++;
     if (Hh::PRUNE) {
-        long long t_u0 = clock64();
+        long long t_u0 = APA_TIC();
         hh.update_contours();
-        cx.tphase[7] += clock64() - t_u0;
+        APA_TOC(cx.tphase[7], t_u0);
     }
     cx.v_top = cx.v_base;  // blocks are recomputed in every pass
 
@@ -232,10 +232,10 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         stage_amask(sm, cx.a, is, ie - is, lane);
         uint2* vout = (uint2*)(cx.arena + off);
         int32_t* cumout = (int32_t*)(cx.arena + off + (size_t)nhw * 8);
-        long long t_dp0 = clock64();
+        long long t_dp0 = APA_TIC();
         Cost bot_val = block_dp<false>(sm, cx.bprof, prev, ie - is, rounded.s, rounded.e, vout, cumout, top_val, nullptr,
                                        cx.word_steps);
-        cx.tphase[1] += clock64() - t_dp0;
+        APA_TOC(cx.tphase[1], t_dp0);
         cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
 
         BlkMeta nm;
@@ -280,10 +280,10 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         dbg_log(cx, f_max, t, jr, stored);
 
         if (Hh::PRUNE) {
-            long long t_p0 = clock64();
+            long long t_p0 = APA_TIC();
             JRange inter = jr_inter(prev_fixed, next_fixed);
             if (!jr_empty(inter)) hh.prune_block(is, ie, inter.s, inter.e);
-            cx.tphase[7] += clock64() - t_p0;
+            APA_TOC(cx.tphase[7], t_p0);
         }
     }
     // dist = last_block.get(|b|) (domain.rs:520-522)

@@ -17,6 +17,7 @@ namespace apa {
 struct WarpSmem {
     uint2 amask[BLOCK_W];   // per column of the current block: (0 - rank bit0, 0 - rank bit1) of a[i]  (profile.rs:117-121)
     uint8_t hrow[BLOCK_W];  // bottom horizontal deltas of the previous chunk: bit0 = +1, bit1 = -1
+    int32_t dt_i[2][96];    // DT-trace fronts of the current and previous level: column reached on diagonal d at [d + 48]
 };
 
 // One 32-row x 1-column Myers step (myers.rs:27-55 on a 32-bit word).

@@ -7,6 +7,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Phase timers (clock64 around the phases of a pair) cost registers; build with -DAPA_PHASE_TIMERS=1 to get
+// apa_batch_stats.phase_cycles filled in (make TIMERS=1).
+#ifndef APA_PHASE_TIMERS
+#define APA_PHASE_TIMERS 0
+#endif
+#if APA_PHASE_TIMERS
+#define APA_TIC() clock64()
+#define APA_TOC(acc, t0) ((acc) += clock64() - (t0))
+#else
+#define APA_TIC() 0ll
+#define APA_TOC(acc, t0) ((void)(t0))
+#endif
+
 namespace apa {
 
 typedef int32_t I;

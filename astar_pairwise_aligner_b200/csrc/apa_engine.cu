@@ -168,20 +168,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchD
             if (bd.preset == APA_PRESET_SIMPLE) {
                 GapH hh{cx.n, cx.m};
                 Cost h0 = hh.h(0, 0);
-                long long t0 = clock64();
+                long long t0 = APA_TIC();
                 cost = dev_band_doubling(cx, sm, hh, h0);
-                cx.tphase[2] += clock64() - t0;
+                APA_TOC(cx.tphase[2], t0);
                 if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
             } else {
                 GcshH hh;
-                long long t0 = clock64();
+                long long t0 = APA_TIC();
                 bool built = gcsh_build(cx, hh);
-                cx.tphase[0] += clock64() - t0;
+                APA_TOC(cx.tphase[0], t0);
                 if (built) {
                     Cost h0 = hh.h(0, 0);
-                    t0 = clock64();
+                    t0 = APA_TIC();
                     cost = dev_band_doubling(cx, sm, hh, h0);
-                    cx.tphase[2] += clock64() - t0;
+                    APA_TOC(cx.tphase[2], t0);
                     cx.tphase[6] += hh.t_h;
                     if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
                 }
@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchD
             cw.count = 0;
             cw.pend_cnt = 0;
             cw.pend_op = 0;
-            long long t0 = clock64();
+            long long t0 = APA_TIC();
             bool traced = dev_trace(cx, sm, cw, cost);
-            cx.tphase[3] += clock64() - t0;
+            APA_TOC(cx.tphase[3], t0);
             if (traced) {
-                t0 = clock64();
+                t0 = APA_TIC();
                 cig_off = emit_cigar_text(cw, bd.pool, bd.pool_cursor, bd.pool_cap, &cig_len);
-                cx.tphase[5] += clock64() - t0;
+                APA_TOC(cx.tphase[5], t0);
                 if (cig_off < 0) cx.status = ST_OVERFLOW;
             }
         }

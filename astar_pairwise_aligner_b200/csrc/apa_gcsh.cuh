@@ -38,8 +38,9 @@ struct GcshH {
     I* px;             // transform(start).0
     I* py;             // transform(start).1
     uint8_t* active;   // MatchStatus::Active
-    int* next;         // next point in the same layer
-    int* layer_head;   // [0 .. M+1]; layer 0 is the sentinel (contains every query)
+    int* next;         // next point in the same layer's overflow list
+    int* layer_head;   // [0 .. M+1] overflow list (third and later points of a layer); -1 = none
+    int4* layer_pts;   // [0 .. M+1] first two points of each layer inline: (x0, y0, x1, y1); x = INT32_MIN when unused
     int nlayers;       // highest non-empty layer
     const uint32_t* base;  // [nseeds+1] first match of each seed in by_start order
     uint32_t* before_end;  // ActiveRange.before.end per seed
@@ -56,6 +57,10 @@ struct GcshH {
     }
     // RotateToFrontContour::contains on layer w (rotate_to_front.rs:32-44), without the rotation.
     __device__ __forceinline__ bool contains(int w, I qx, I qy) const {
+        const int4 p = layer_pts[w];  // one 16-byte load answers most probes (~1.5 points per layer)
+        if (qx <= p.x && qy <= p.y) return true;
+        if (p.z == INT32_MIN) return false;
+        if (qx <= p.z && qy <= p.w) return true;
         for (int idx = layer_head[w]; idx >= 0; idx = next[idx])
             if (qx <= px[idx] && qy <= py[idx]) return true;
         return false;
@@ -94,7 +99,7 @@ struct GcshH {
     // CSHI::h / h_with_hint (csh.rs:341-376): P(u) - layer(T(u)), or max(gap, potential) to the target in layer 0.
     __device__ Cost h(I i, I j) {
         h_calls++;
-        long long t0 = clock64();
+        long long t0 = APA_TIC();
         Cost p = pot(i);
         int val = score(i - j - p, j - i - p);
         Cost r;
@@ -105,13 +110,16 @@ struct GcshH {
         } else {
             r = p - val;
         }
-        t_h += clock64() - t0;
+        APA_TOC(t_h, t0);
         return r;
     }
     // HintContours::new over the active arrows (hint_contours.rs:213-255) == state after update_layers.
     __device__ void build_layers() {
         const int lane = threadIdx.x & 31;
-        for (int w = lane; w <= nlayers + 1 && w <= M + 1; w += 32) layer_head[w] = -1;
+        for (int w = lane; w <= nlayers + 1 && w <= M + 1; w += 32) {
+            layer_head[w] = -1;
+            layer_pts[w] = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);
+        }
         __syncwarp();
         nlayers = 0;
         hint = 0;
@@ -121,9 +129,20 @@ struct GcshH {
             if (!(ex <= ttx && ey <= tty)) continue;
             int v = score(ex, ey) + 1;
             if (lane == 0) {
+                int4 p = (v > nlayers) ? make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN) : layer_pts[v];
                 if (v > nlayers) layer_head[v] = -1;
-                next[idx] = layer_head[v];
-                layer_head[v] = idx;
+                if (p.x == INT32_MIN) {
+                    p.x = px[idx];
+                    p.y = py[idx];
+                    layer_pts[v] = p;
+                } else if (p.z == INT32_MIN) {
+                    p.z = px[idx];
+                    p.w = py[idx];
+                    layer_pts[v] = p;
+                } else {
+                    next[idx] = layer_head[v];
+                    layer_head[v] = idx;
+                }
             }
             if (v > nlayers) nlayers = v;
             hint = v;
@@ -254,7 +273,7 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
 
     // capacity for matches scales with the arena (re-run with a larger arena on overflow)
     const uint32_t avail = cx.hi_bot - cx.v_top;
-    int mcap = (int)min((uint32_t)(1u << 30), avail / 160u);
+    int mcap = (int)min((uint32_t)(1u << 30), avail / 180u);
     if (mcap < 64) {
         cx.status = ST_OVERFLOW;
         return false;
@@ -269,6 +288,7 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     uint32_t off_py = arena_alloc(cx, (uint32_t)mcap * 4u);
     uint32_t off_next = arena_alloc(cx, (uint32_t)mcap * 4u);
     uint32_t off_lh = arena_alloc(cx, (uint32_t)(mcap + 2) * 4u);
+    uint32_t off_lp = arena_alloc(cx, (uint32_t)(mcap + 2) * 16u);
     uint32_t off_act = arena_alloc(cx, (uint32_t)mcap);
     const uint32_t live_end = cx.v_top;
     // ---- dead after the precomputation
@@ -427,6 +447,7 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     H.py = (I*)(cx.arena + off_py);
     H.next = (int*)(cx.arena + off_next);
     H.layer_head = (int*)(cx.arena + off_lh);
+    H.layer_pts = (int4*)(cx.arena + off_lp);
     H.active = cx.arena + off_act;
     H.base = cnt;
     H.before_end = before_end;
@@ -447,7 +468,10 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     cx.v_top = live_end;
     cx.v_base = live_end;
     H.nlayers = 0;
-    if (lane == 0) H.layer_head[0] = -1;
+    if (lane == 0) {
+        H.layer_head[0] = -1;
+        H.layer_pts[0] = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);
+    }
     __syncwarp();
     H.build_layers();
     return true;

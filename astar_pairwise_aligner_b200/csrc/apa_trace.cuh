@@ -106,14 +106,17 @@ __device__ __forceinline__ ColRef fill_col(const TraceState& ts, int c) {
 }
 
 // dt_trace_block (trace.rs:231-416). Returns true on success and updates ts.(ti,tj,g).
-// cache: DT_CACHE_ELEMS int2 {i, (ext << 2) | (parent_d + 1)}; element (g,d) at g*g+g+d.
+// Lanes = diagonals. The fronts (column reached per diagonal) of the current and previous level live in shared
+// memory; the per-element record (extension length, parent diagonal) needed only for the final backtrack goes to
+// `rec` in the arena: element (g,d) at g*g+g+d holds (ext << 2) | (parent_d + 1).
 __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceState& ts, const BlkView& prev, I block_start,
-                             int2* cache) {
+                             int32_t* rec) {
     const int lane = threadIdx.x & 31;
     const I si = ts.ti, sj = ts.tj;
     const Cost g_st = ts.g;
     auto idx = [](int g, int d) { return g * g + g + d; };
     int8_t* chain = (int8_t*)sm.hrow;  // d of each level on the final path
+    constexpr int DOFF = 48;
 
     // reference closure extend_left_simd_and_check (trace.rs:313-329)
     auto reached = [&](I i, I j, Cost target) -> bool {
@@ -127,12 +130,17 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
     {
         I i = si, j = sj;
         I ext = extend_left_packed(cx.aprof, cx.bprof, i, block_start, j);
-        if (lane == 0) cache[0] = make_int2(i, (ext << 2) | 1);
+        if (lane == 0) {
+            sm.dt_i[0][DOFF] = i;
+            rec[0] = (ext << 2) | 1;
+        }
         __syncwarp();
         if (reached(i, j, g_st)) found = true;
     }
     while (!found) {
         const int ng = g + 1;
+        const int32_t* cur = sm.dt_i[g & 1];
+        int32_t* nxt = sm.dt_i[ng & 1];
         // expand + extend level ng, one diagonal per lane
         I min_fr = INT32_MAX, min_i = INT32_MAX;
         int succ_d = INT32_MAX;
@@ -143,15 +151,15 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
             bool in = d <= d_hi + 1;
             if (in) {
                 if (d - 1 >= d_lo && d - 1 <= d_hi) {  // from d-1: (fr.i, -1) insertion
-                    I y = cache[idx(g, d - 1)].x;
+                    I y = cur[DOFF + d - 1];
                     if (y < best) best = y, pd = -1;
                 }
                 if (d >= d_lo && d <= d_hi) {  // from d: (fr.i - 1, 0) substitution
-                    I y = cache[idx(g, d)].x - 1;
+                    I y = cur[DOFF + d] - 1;
                     if (y < best) best = y, pd = 0;
                 }
                 if (d + 1 >= d_lo && d + 1 <= d_hi) {  // from d+1: (fr.i - 1, +1) deletion
-                    I y = cache[idx(g, d + 1)].x - 1;
+                    I y = cur[DOFF + d + 1] - 1;
                     if (y < best) best = y, pd = 1;
                 }
             }
@@ -165,7 +173,8 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
                     min_fr = min(min_fr, (I)(2u * (uint32_t)i - (uint32_t)d));
                     min_i = min(min_i, i);
                 }
-                cache[idx(ng, d)] = make_int2(i, (ext << 2) | (pd + 1));
+                nxt[DOFF + d] = i;
+                rec[idx(ng, d)] = (ext << 2) | (pd + 1);
             }
             unsigned bal = __ballot_sync(FULL, ok);
             if (bal && succ_d == INT32_MAX) succ_d = base + (__ffs(bal) - 1);
@@ -189,14 +198,14 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
         // x-drop: shrink diagonals more than fr_drop behind (trace.rs:396-414)
         const I thr = (I)((uint32_t)min_fr + (uint32_t)DT_FR_DROP);
         while (d_lo < d_hi) {
-            I i = cache[idx(g, d_lo)].x;
+            I i = nxt[DOFF + d_lo];
             if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_lo) > thr)
                 d_lo++;
             else
                 break;
         }
         while (d_lo < d_hi) {
-            I i = cache[idx(g, d_hi)].x;
+            I i = nxt[DOFF + d_hi];
             if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_hi) > thr)
                 d_hi--;
             else
@@ -212,18 +221,18 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
             int dd = d;
             for (int l = g; l >= 0; l--) {
                 chain[l] = (int8_t)dd;
-                if (l > 0) dd += (cache[idx(l, dd)].y & 3) - 1;
+                if (l > 0) dd += (rec[idx(l, dd)] & 3) - 1;
             }
         }
         __syncwarp();
         for (int l = 0; l <= g; l++) {
             int dl = chain[l];
-            int2 e = cache[idx(l, dl)];
+            int e = rec[idx(l, dl)];
             if (l > 0) {
-                int pd = (e.y & 3) - 1;
+                int pd = (e & 3) - 1;
                 cig_push(cx, cw, pd == -1 ? OP_INS : (pd == 0 ? OP_SUB : OP_DEL), 1);
             }
-            I ext = e.y >> 2;
+            I ext = e >> 2;
             if (ext > 0) cig_push(cx, cw, OP_MATCH, (uint32_t)ext);
         }
         __syncwarp();
@@ -250,9 +259,9 @@ __device__ bool dev_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, Cost cost)
     ts.ftop0 = 0;
     // DT cache + dense region live above the V column store of the final pass.
     const uint32_t trace_base = cx.v_top;
-    uint32_t cache_off = arena_alloc(cx, DT_CACHE_ELEMS * 8u);
+    uint32_t cache_off = arena_alloc(cx, DT_CACHE_ELEMS * 4u);
     if (cx.status != ST_PENDING) return false;
-    int2* cache = (int2*)(cx.arena + cache_off);
+    int32_t* cache = (int32_t*)(cx.arena + cache_off);
     const uint32_t fill_base = cx.v_top;
     (void)trace_base;
 
@@ -274,9 +283,9 @@ __device__ bool dev_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, Cost cost)
             const BlkMeta pm = cx.meta[ts.top - 1];
             if (pm.col_e < ts.ti - 1) {
                 const BlkView prev = view_of(cx, pm);
-                long long t_dt0 = clock64();
+                long long t_dt0 = APA_TIC();
                 bool dt_ok = dev_dt_trace(cx, sm, cw, ts, prev, pm.col_e, cache);
-                cx.tphase[4] += clock64() - t_dt0;
+                APA_TOC(cx.tphase[4], t_dt0);
                 if (dt_ok) {
                     cx.dt_blocks++;
                     if (cx.status != ST_PENDING) return false;

@@ -119,6 +119,19 @@ def test_drop_in_symbols_gpu(apa):
         L.astarpa_free_cigar(cig)
 
 
+def test_drop_in_c_program_gpu(apa, tmp_path):
+    # A C caller compiled against include/astarpa.h and linked to libastarpa_c.so, like astarpa-c/example.c.
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "dropin_example")
+    libdir = os.path.dirname(apa.lib_path())
+    subprocess.check_call(["gcc", "-O1", os.path.join(HERE, "dropin_example.c"), "-I", os.path.join(root, "include"), "-L", libdir,
+                           "-lastarpa_c", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" ok") == 4
+
+
 def test_bad_input_gpu(apa):
     with pytest.raises(apa.AstarPaError):
         apa.AstarPa2(0, True).align_batch([(b"ACGT", b"ACGT"), (b"ACGN", b"ACGT")])
