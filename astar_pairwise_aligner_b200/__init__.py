@@ -65,6 +65,8 @@ def load_library():
     L.apa_batch_download.argtypes = [C.c_void_p, C.c_void_p, vp, C.POINTER(C.c_void_p), vp, vp]
     L.apa_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
     L.apa_batch_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.apa_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(C.c_void_p), vp, vp,
+                                  C.POINTER(BatchStats)]
     L.apa_free.argtypes = [C.c_void_p]
     L.apa_pinned_alloc.restype = C.c_void_p
     L.apa_pinned_alloc.argtypes = [C.c_uint64]
@@ -162,6 +164,29 @@ class Engine:
 
     def upload(self, a_all, a_off, b_all, b_off):
         return Batch(self, a_all, a_off, b_all, b_off)
+
+    def align_batch_raw(self, a_all, a_off, b_all, b_off, preset=PRESET_FULL, trace=True):
+        """apa_align_batch: host buffers in, host buffers out (the bases stream to HBM while the kernel runs).
+        Returns (costs, pool pointer or None, cigar_off, cigar_len, stats dict); release the pool with free_pool()."""
+        a_all = np.ascontiguousarray(a_all, dtype=np.uint8)
+        b_all = np.ascontiguousarray(b_all, dtype=np.uint8)
+        a_off = np.ascontiguousarray(a_off, dtype=np.int64)
+        b_off = np.ascontiguousarray(b_off, dtype=np.int64)
+        n = len(a_off) - 1
+        costs = np.zeros(max(n, 1), dtype=np.int64)
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        ln = np.zeros(max(n, 1), dtype=np.int64)
+        pool = C.c_void_p()
+        st = BatchStats()
+        ap = a_all.ctypes.data if a_all.size else None
+        bp = b_all.ctypes.data if b_all.size else None
+        _check(self._L.apa_align_batch(self._h, preset, int(trace), n, ap, a_off.ctypes.data, bp, b_off.ctypes.data, costs.ctypes.data,
+                                       C.byref(pool), off.ctypes.data, ln.ctypes.data, C.byref(st)))
+        return costs[:n], pool, off[:n], ln[:n], st.as_dict()
+
+    def free_pool(self, pool):
+        if pool and pool.value:
+            self._L.apa_free(pool)
 
     def block_compute(self, a: bytes, b: bytes, v=None):
         """pa_bitpacking::simd::compute on the GPU with +1 top deltas. Returns (bottom_sum, h_out, v_out)."""
@@ -283,12 +308,12 @@ class AstarPa2:
     def align_batch(self, pairs):
         """pairs: list of (a, b) byte strings over ACGT. Returns (costs ndarray, list of CIGAR strings or None)."""
         eng = _engine(self.device)
-        batch = eng.upload(*_concat(pairs))
-        try:
-            batch.run(self.preset, self.trace)
-            return batch.download(cigars=self.trace)
-        finally:
-            batch.free()
+        costs, pool, off, ln, _ = eng.align_batch_raw(*_concat(pairs), self.preset, self.trace)
+        cigars = None
+        if self.trace and pool.value:
+            cigars = [C.string_at(pool.value + int(off[p]), int(ln[p])).decode() for p in range(len(pairs))]
+        eng.free_pool(pool)
+        return costs, cigars
 
     def align(self, a: bytes, b: bytes):
         """Aligner::align (astarpa2/src/lib.rs:210-215): (cost, cigar or None)."""

@@ -43,7 +43,6 @@ struct BatchDev {
     const int64_t* ap_off;  // the same for a
     uint2* aprof;
     int32_t* status;  // per pair
-    int32_t* bad;     // per pair: input byte outside ACGT (written once by the pack kernel)
     int32_t* cost;    // per pair
     int64_t* cig_off;
     int64_t* cig_len;
@@ -58,57 +57,53 @@ struct BatchDev {
     unsigned long long* stats;  // [0] word_steps [1] computed_cells [2] passes [3] fill_blocks [4] dt_blocks [5..12] phase cycles
     int preset;
     int trace;
+    const volatile uint32_t* ready;  // streaming upload: number of pairs (in work order) whose bases are in HBM; nullptr = all
     int32_t* dbg;  // band log of the (single) pair, or nullptr
     uint32_t dbg_cap;
     uint32_t* dbg_n;
 };
 
-// K0: negated bit planes of b per 32 rows (BitProfile::build for b, pa-bitpacking/src/profile.rs:124-131) and
-// input validation (the reference panics on bytes outside ACGT, profile.rs:113).
-__global__ void apa_pack_kernel(BatchDev bd) {
-    const uint64_t p = blockIdx.x;
-    if (p >= bd.n_pairs) return;
-    const uint8_t* a = bd.a_all + bd.a_off[p];
-    const uint8_t* b = bd.b_all + bd.b_off[p];
-    const int64_t n = bd.a_off[p + 1] - bd.a_off[p];
-    const int64_t m = bd.b_off[p + 1] - bd.b_off[p];
-    const int64_t nhw = ((m + 63) / 64) * 2;
-    uint2* out = bd.bprof + bd.bp_off[p];
+// K0 (fused into the align kernel): negated bit planes per 32 bases (BitProfile::build for b,
+// pa-bitpacking/src/profile.rs:124-131; the same packing of a feeds the diagonal extensions) and input validation
+// (the reference panics on bytes outside ACGT, profile.rs:113). Each lane packs one 32-base group per iteration.
+__device__ bool dev_pack_planes(const uint8_t* __restrict__ seq, int64_t len, uint2* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nhw = ((len + 63) / 64) * 2 + 2;  // + two zero half-words of padding
     bool bad = false;
-    {
-        const int64_t nhw_a = ((n + 63) / 64) * 2;
-        uint2* outa = bd.aprof + bd.ap_off[p];
-        for (int64_t hw = threadIdx.x; hw < nhw_a + 2; hw += blockDim.x) {
-            uint32_t b0 = 0, b1 = 0;
+    for (int64_t hw = lane; hw < nhw; hw += 32) {
+        uint32_t b0 = 0, b1 = 0;
+        const int64_t j0 = hw * 32;
+        if (j0 + 32 <= len && ((reinterpret_cast<uintptr_t>(seq + j0) & 3) == 0)) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(seq + j0);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                uint32_t x = w[q];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    uint32_t c = (x >> (8 * t)) & 0xffu;
+                    bad |= !is_acgt(c);
+                    uint32_t r = rank_acgt(c);
+                    b0 |= ((r & 1u) ^ 1u) << (4 * q + t);
+                    b1 |= ((r >> 1) ^ 1u) << (4 * q + t);
+                }
+            }
+        } else {
             for (int t = 0; t < 32; t++) {
-                int64_t i = hw * 32 + t;
-                if (i < n) {
-                    uint32_t c = a[i];
+                int64_t j = j0 + t;
+                if (j < len) {
+                    uint32_t c = seq[j];
                     bad |= !is_acgt(c);
                     uint32_t r = rank_acgt(c);
                     b0 |= ((r & 1u) ^ 1u) << t;
                     b1 |= ((r >> 1) ^ 1u) << t;
                 }
             }
-            outa[hw] = make_uint2(b0, b1);
-        }
-    }
-    for (int64_t hw = threadIdx.x; hw < nhw + 2; hw += blockDim.x) {
-        uint32_t b0 = 0, b1 = 0;
-        int64_t j0 = hw * 32;
-        for (int t = 0; t < 32; t++) {
-            int64_t j = j0 + t;
-            if (j < m) {
-                uint32_t c = b[j];
-                bad |= !is_acgt(c);
-                uint32_t r = rank_acgt(c);
-                b0 |= ((r & 1u) ^ 1u) << t;
-                b1 |= ((r >> 1) ^ 1u) << t;
-            }
         }
         out[hw] = make_uint2(b0, b1);
     }
-    if (bad) bd.bad[p] = 1;
+    bad = __any_sync(FULL, bad);
+    __syncwarp();
+    return !bad;
 }
 
 constexpr int WARPS_PER_CTA = 4;
@@ -130,11 +125,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchD
         if (lane == 0) q = atomicAdd(bd.queue, 1ull);
         q = __shfl_sync(FULL, q, 0);
         if (q >= bd.n_order) break;
-        const uint32_t p = bd.order[q];
-        if (bd.bad[p]) {
-            if (lane == 0) bd.status[p] = ST_BAD_INPUT;
-            continue;
+        if (bd.ready) {  // streaming upload: wait until this pair's bases have landed in HBM
+            if (lane == 0) {
+                while (*bd.ready <= (uint32_t)q) __nanosleep(500);
+            }
+            __syncwarp();
         }
+        const uint32_t p = bd.order[q];
 
         PairCtx cx;
         cx.n = (I)(bd.a_off[p + 1] - bd.a_off[p]);
@@ -143,6 +140,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchD
         cx.b = bd.b_all + bd.b_off[p];
         cx.bprof = bd.bprof + bd.bp_off[p];
         cx.aprof = bd.aprof + bd.ap_off[p];
+        {
+            bool ok_a = dev_pack_planes(cx.a, cx.n, bd.aprof + bd.ap_off[p]);
+            bool ok_b = dev_pack_planes(cx.b, cx.m, bd.bprof + bd.bp_off[p]);
+            if (!(ok_a && ok_b)) {
+                if (lane == 0) bd.status[p] = ST_BAD_INPUT;
+                continue;
+            }
+        }
         cx.arena = arena;
         cx.arena_size = bd.arena_size;
         cx.nblk = (cx.n + BLOCK_W - 1) / BLOCK_W;
@@ -256,6 +261,9 @@ struct apa_engine {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // streaming uploads overlap the persistent kernel
+    uint32_t* d_ready = nullptr;
+    uint32_t* h_ready = nullptr;  // pinned: cumulative pair counts per upload chunk
     cudaEvent_t ev[6] = {};
     unsigned long long* d_queue = nullptr;   // [0] queue head, [1] pool cursor, [2..] stats
     uint8_t* d_arena = nullptr;
@@ -270,12 +278,15 @@ struct apa_batch {
     uint8_t *d_a = nullptr, *d_b = nullptr;
     int64_t *d_a_off = nullptr, *d_b_off = nullptr, *d_bp_off = nullptr, *d_ap_off = nullptr;
     uint2 *d_bprof = nullptr, *d_aprof = nullptr;
-    int32_t *d_status = nullptr, *d_cost = nullptr, *d_bad = nullptr;
+    int32_t *d_status = nullptr, *d_cost = nullptr;
     int64_t *d_cig_off = nullptr, *d_cig_len = nullptr;
     uint32_t* d_order = nullptr;
     char* d_pool = nullptr;
     uint64_t pool_cap = 0;
-    bool packed = false;
+    // streaming upload (apa_align_batch): bases are copied chunk by chunk while the kernel already runs
+    const uint8_t *h_a = nullptr, *h_b = nullptr;
+    std::vector<uint32_t> chunk_end;  // pairs (in work order) available after each chunk
+    std::vector<uint32_t> chunk_pair_end;  // pair index (exclusive) of each chunk: chunks are contiguous index ranges
     bool ran = false;
     int trace = 0;
     apa_batch_stats stats{};
@@ -310,6 +321,9 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     eng->device = device;
     eng->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&eng->d_ready, 64));
+    CUDA_TRY(cudaHostAlloc((void**)&eng->h_ready, 256 * sizeof(uint32_t), cudaHostAllocDefault));
     for (auto& ev : eng->ev) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMalloc(&eng->d_queue, 16 * sizeof(unsigned long long)));
     *out = eng;
@@ -324,6 +338,9 @@ extern "C" void apa_engine_destroy(apa_engine* e) {
     for (auto& ev : e->ev)
         if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->d_ready) cudaFree(e->d_ready);
+    if (e->h_ready) cudaFreeHost(e->h_ready);
     delete e;
 }
 
@@ -354,7 +371,6 @@ extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     cudaFree(b->d_aprof);
     cudaFree(b->d_ap_off);
     cudaFree(b->d_status);
-    cudaFree(b->d_bad);
     cudaFree(b->d_cost);
     cudaFree(b->d_cig_off);
     cudaFree(b->d_cig_len);
@@ -363,8 +379,8 @@ extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     delete b;
 }
 
-extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all,
-                                const int64_t* b_off, apa_batch** out) {
+static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all,
+                         const int64_t* b_off, bool defer_data, apa_batch** out) {
     *out = nullptr;
     if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
     CUDA_TRY(cudaSetDevice(e->device));
@@ -400,12 +416,33 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
     for (auto& x : bo) x -= b_off[0];
     b->a_off = ao;
     b->b_off = bo;
-    // Work order: largest estimated work first.
+    // Work order: largest estimated work first. With a streaming upload the batch is cut into chunks of
+    // contiguous pairs (about 32 MB of bases each) that become available one after the other; pairs are sorted inside
+    // each chunk only.
     std::vector<uint32_t> order(n_pairs);
     std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    auto by_size = [&](uint32_t x, uint32_t y) {
         return (ao[x + 1] - ao[x]) + (bo[x + 1] - bo[x]) > (ao[y + 1] - ao[y]) + (bo[y + 1] - bo[y]);
-    });
+    };
+    if (defer_data && n_pairs) {
+        const uint64_t total = b->total_a + b->total_b;
+        const uint64_t n_chunks = std::min<uint64_t>(200, std::max<uint64_t>(1, total / (32ull << 20)));
+        const uint64_t per = (total + n_chunks - 1) / n_chunks;
+        uint64_t acc = 0, start = 0;
+        for (uint64_t p = 0; p < n_pairs; p++) {
+            acc += (uint64_t)(ao[p + 1] - ao[p]) + (uint64_t)(bo[p + 1] - bo[p]);
+            if (acc >= per || p + 1 == n_pairs) {
+                std::stable_sort(order.begin() + start, order.begin() + p + 1, by_size);
+                b->chunk_pair_end.push_back((uint32_t)(p + 1));
+                acc = 0;
+                start = p + 1;
+            }
+        }
+        b->h_a = a_all + a_off[0];
+        b->h_b = b_all + b_off[0];
+    } else {
+        std::stable_sort(order.begin(), order.end(), by_size);
+    }
 
     cudaStream_t st = e->stream;
     CUDA_TRY(cudaEventRecord(e->ev[0], st));
@@ -419,13 +456,13 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
     CUDA_TRY(cudaMalloc(&b->d_ap_off, (n_pairs + 1) * 8));
     CUDA_TRY(cudaMalloc(&b->d_status, std::max<uint64_t>(n_pairs, 1) * 4));
     CUDA_TRY(cudaMalloc(&b->d_cost, std::max<uint64_t>(n_pairs, 1) * 4));
-    CUDA_TRY(cudaMalloc(&b->d_bad, std::max<uint64_t>(n_pairs, 1) * 4));
-    CUDA_TRY(cudaMemsetAsync(b->d_bad, 0, std::max<uint64_t>(n_pairs, 1) * 4, st));
     CUDA_TRY(cudaMalloc(&b->d_cig_off, std::max<uint64_t>(n_pairs, 1) * 8));
     CUDA_TRY(cudaMalloc(&b->d_cig_len, std::max<uint64_t>(n_pairs, 1) * 8));
     CUDA_TRY(cudaMalloc(&b->d_order, std::max<uint64_t>(n_pairs, 1) * 8));  // [0,n): work order, [n,2n): retry list
-    if (b->total_a) CUDA_TRY(cudaMemcpyAsync(b->d_a, a_all + a_off[0], b->total_a, cudaMemcpyHostToDevice, st));
-    if (b->total_b) CUDA_TRY(cudaMemcpyAsync(b->d_b, b_all + b_off[0], b->total_b, cudaMemcpyHostToDevice, st));
+    if (!defer_data) {
+        if (b->total_a) CUDA_TRY(cudaMemcpyAsync(b->d_a, a_all + a_off[0], b->total_a, cudaMemcpyHostToDevice, st));
+        if (b->total_b) CUDA_TRY(cudaMemcpyAsync(b->d_b, b_all + b_off[0], b->total_b, cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(b->d_a_off, ao.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_b_off, bo.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_bp_off, b->bp_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -436,9 +473,14 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
     b->stats.h2d_ms = ms;
-    b->stats.h2d_bytes = b->total_a + b->total_b + 3 * (n_pairs + 1) * 8 + n_pairs * 4;
+    b->stats.h2d_bytes = b->total_a + b->total_b + 4 * (n_pairs + 1) * 8 + n_pairs * 4;
     *out = b;
     return APA_OK;
+}
+
+extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all,
+                                const int64_t* b_off, apa_batch** out) {
+    return batch_prepare(e, n_pairs, a_all, a_off, b_all, b_off, false, out);
 }
 
 static uint32_t estimate_arena(const apa_batch* b, int preset, int trace) {
@@ -456,7 +498,7 @@ static uint32_t estimate_arena(const apa_batch* b, int preset, int trace) {
     return (uint32_t)std::min<uint64_t>(s, 0xF0000000ull);
 }
 
-extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace) {
+static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool stream_data) {
     if (!e || !b) return set_err(APA_ERR_NO_DEVICE, "null engine/batch");
     if (preset != APA_PRESET_SIMPLE && preset != APA_PRESET_FULL) return set_err(APA_ERR_BAD_INPUT, "unknown preset");
     CUDA_TRY(cudaSetDevice(e->device));
@@ -487,7 +529,6 @@ extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace)
     bd.ap_off = b->d_ap_off;
     bd.aprof = b->d_aprof;
     bd.status = b->d_status;
-    bd.bad = b->d_bad;
     bd.cost = b->d_cost;
     bd.cig_off = b->d_cig_off;
     bd.cig_len = b->d_cig_len;
@@ -507,11 +548,6 @@ extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace)
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
     CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, 16 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(b->d_status, 0, b->n_pairs * 4, st));
-    if (!b->packed) {
-        apa_pack_kernel<<<(unsigned)b->n_pairs, 256, 0, st>>>(bd);
-        b->stats.kernel_launches++;
-        b->packed = true;
-    }
     uint32_t arena_size = estimate_arena(b, preset, trace);
     std::vector<uint32_t> pending;  // empty = all pairs in the uploaded order
     b->h_status.assign(b->n_pairs, 0);
@@ -542,9 +578,29 @@ extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace)
             bd.order = b->d_order + b->n_pairs;
             CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(unsigned long long), st));
         }
+        const bool streaming = stream_data && attempt == 0 && !b->chunk_pair_end.empty();
+        bd.ready = streaming ? e->d_ready : nullptr;
+        if (streaming) {
+            CUDA_TRY(cudaMemsetAsync(e->d_ready, 0, 4, st));
+            CUDA_TRY(cudaStreamSynchronize(st));  // offsets, order, zeroed queue are in place before anything overlaps
+        }
         apa_align_kernel<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
         b->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
+        if (streaming) {
+            // H2D of the bases, chunk by chunk on the copy stream, while the persistent kernel already consumes them.
+            uint32_t p0 = 0;
+            for (size_t c = 0; c < b->chunk_pair_end.size(); c++) {
+                const uint32_t p1 = b->chunk_pair_end[c];
+                const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
+                if (a1 > a0) CUDA_TRY(cudaMemcpyAsync(b->d_a + a0, b->h_a + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream));
+                if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(b->d_b + b0, b->h_b + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, e->copy_stream));
+                e->h_ready[c] = p1;
+                CUDA_TRY(cudaMemcpyAsync(e->d_ready, &e->h_ready[c], 4, cudaMemcpyHostToDevice, e->copy_stream));
+                p0 = p1;
+            }
+            CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+        }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         pending.clear();
@@ -587,6 +643,8 @@ extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace)
     return APA_OK;
 }
 
+extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace) { return batch_run(e, b, preset, trace, false); }
+
 extern "C" int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len) {
     if (!e || !b || !b->ran) return set_err(APA_ERR_BAD_INPUT, "batch has not been run");
     CUDA_TRY(cudaSetDevice(e->device));
@@ -626,9 +684,11 @@ extern "C" int apa_batch_get_stats(apa_batch* b, apa_batch_stats* out) {
 extern "C" int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off,
                                const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool, int64_t* cigar_off,
                                int64_t* cigar_len, apa_batch_stats* stats) {
+    // Host buffers in, host buffers out: the bases stream to HBM in chunks while the persistent kernel is already
+    // aligning the pairs that have arrived (H2D overlaps compute); results come back in one D2H at the end.
     apa_batch* b = nullptr;
-    int rc = apa_batch_upload(e, n_pairs, a_all, a_off, b_all, b_off, &b);
-    if (rc == APA_OK) rc = apa_batch_run(e, b, preset, trace);
+    int rc = batch_prepare(e, n_pairs, a_all, a_off, b_all, b_off, true, &b);
+    if (rc == APA_OK) rc = batch_run(e, b, preset, trace, true);
     if (rc == APA_OK) rc = apa_batch_download(e, b, costs, cigar_pool, cigar_off, cigar_len);
     if (rc == APA_OK && stats) *stats = b->stats;
     apa_batch_free(e, b);
@@ -690,7 +750,7 @@ extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, c
         *bottom_sum = (int64_t)na;
         return APA_OK;
     }
-    // host-side profile of b in the device layout (same as apa_pack_kernel)
+    // host-side profile of b in the device layout (same as dev_pack_planes)
     std::vector<uint2> bp(nhw);
     for (uint64_t hw = 0; hw < nhw; hw++) {
         uint32_t b0 = 0, b1 = 0;

@@ -426,6 +426,7 @@ __device__ long long emit_cigar_text(const CigarWriter& cw, char* pool, unsigned
                                      long long* out_len) {
     const int lane = threadIdx.x & 31;
     const uint32_t* elems = (const uint32_t*)(cw.arena + cw.arena_size - 4u * cw.count);
+    __syncwarp();  // the elements were stored by lane 0 (cig_store); every lane reads them below
     // pass 1: total length
     unsigned long long total = 0;
     for (uint32_t k = lane; k < cw.count; k += 32) {

@@ -211,14 +211,10 @@ def main():
     for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         barrier()
         t1 = time.perf_counter()
-        bt = eng.upload(a_pin, a_off, b_pin, b_off)
-        bt.run(preset_id, trace)
-        c2, pool2, off2, ln2 = bt.download_raw()
+        c2, pool2, off2, ln2, s2 = eng.align_batch_raw(a_pin, a_off, b_pin, b_off, preset_id, trace)  # the public batch call
         dt = (time.perf_counter() - t1) * 1e3
-        s2 = bt.stats()
         h2d_bytes, d2h_bytes = s2["h2d_bytes"], s2["d2h_bytes"]
-        bt.free_pool(pool2)
-        bt.free()
+        eng.free_pool(pool2)
         if it > 0:
             e2e_ms.append(dt)
         assert (c2 == costs).all()
