@@ -236,11 +236,13 @@ struct Blocks {
         size_t nb = ve - vs;
         switch (mode) {
             case HMode::None: {
-                std::vector<H> tmp(na, H::one());
+                static thread_local std::vector<H> tmp;
+                tmp.assign(na, H::one());
                 return bp_compute(pa, na, pb, nb, tmp.data(), v);
             }
             case HMode::Input: {
-                std::vector<H> tmp(h.begin() + ir.s, h.begin() + ir.e);
+                static thread_local std::vector<H> tmp;
+                tmp.assign(h.begin() + ir.s, h.begin() + ir.e);
                 return bp_compute(pa, na, pb, nb, tmp.data(), v);
             }
             case HMode::Update: return bp_compute(pa, na, pb, nb, h.data() + ir.s, v);

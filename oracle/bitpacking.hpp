@@ -90,12 +90,110 @@ inline void myers_compute_block(H& h0, V& v, const Bits& ca, const Bits& cb) {
     v = V{hm | ~(vx | hp), hp & vx};
 }
 
+// ---- anti-diagonal SIMD strip, mirroring the reference's layout: L = 4 lanes of u64 x N = 2 vectors = 8 words per
+// strip (pa-bitpacking/src/lib.rs:54, astarpa2/src/blocks.rs:721, simd.rs:229-315). Lane q of the strip holds word
+// 7 - q, so that at "time" t the lanes touch the contiguous columns t-7 .. t of a and h. The corner triangles are done
+// with the scalar step, as in the reference (simd.rs:243-247,310-314). Any topological order yields identical v / h.
+typedef uint64_t v4u __attribute__((vector_size(32)));
+struct Unzipped {  // "Unzip bits of a so we can directly use unaligned reads later" (simd.rs:137-139)
+    std::vector<uint64_t> a0, a1, hp, hm;
+};
+static inline v4u loadu(const uint64_t* p) {
+    v4u r;
+    __builtin_memcpy(&r, p, 32);
+    return r;
+}
+static inline void storeu(uint64_t* p, v4u v) { __builtin_memcpy(p, &v, 32); }
+static inline void myers_step_v4(v4u& hp0, v4u& hm0, v4u& vp, v4u& vm, v4u eq) {  // myers.rs:61-91
+    v4u vx = eq | vm;
+    v4u eq2 = eq | hm0;
+    v4u hx = (((eq2 & vp) + vp) ^ vp) | eq2;
+    v4u hp = vm | ~(hx | vp);
+    v4u hm = vp & hx;
+    v4u hpw = hp >> 63;
+    v4u hmw = hm >> 63;
+    hp = (hp << 1) | hp0;
+    hm = (hm << 1) | hm0;
+    hp0 = hpw;
+    hm0 = hmw;
+    vp = hm | ~(vx | hp);
+    vm = hp & vx;
+}
+// One strip of 8 words over all na columns. h lives in uz.hp / uz.hm (0/1 per column).
+inline void strip8(const Bits* a, Unzipped& uz, size_t na, const Bits* b8, V* v8) {
+    auto scalar = [&](size_t i, size_t j) {
+        H h{uz.hp[i], uz.hm[i]};
+        myers_compute_block(h, v8[j], a[i], b8[j]);
+        uz.hp[i] = h.p;
+        uz.hm[i] = h.m;
+    };
+    if (na < 16) {
+        for (size_t j = 0; j < 8; j++)
+            for (size_t i = 0; i < na; i++) scalar(i, j);
+        return;
+    }
+    // top-left triangle: word j, columns 0 .. 6-j
+    for (size_t j = 0; j < 8; j++)
+        for (size_t i = 0; i + j < 7; i++) scalar(i, j);
+    // lanes: q = 0..7 <-> word 7 - q ; vectors lo = lanes 0..3 (words 7..4), hi = lanes 4..7 (words 3..0)
+    v4u b0lo, b1lo, b0hi, b1hi, vplo, vmlo, vphi, vmhi;
+    for (int q = 0; q < 4; q++) {
+        b0lo[q] = b8[7 - q].b0;
+        b1lo[q] = b8[7 - q].b1;
+        vplo[q] = v8[7 - q].p;
+        vmlo[q] = v8[7 - q].m;
+        b0hi[q] = b8[3 - q].b0;
+        b1hi[q] = b8[3 - q].b1;
+        vphi[q] = v8[3 - q].p;
+        vmhi[q] = v8[3 - q].m;
+    }
+    const uint64_t* a0 = uz.a0.data();
+    const uint64_t* a1 = uz.a1.data();
+    uint64_t* hp = uz.hp.data();
+    uint64_t* hm = uz.hm.data();
+    for (size_t t = 7; t < na; t++) {  // lane q handles column t - 7 + q
+        const size_t c = t - 7;
+        v4u eqlo = (loadu(a0 + c) ^ b0lo) & (loadu(a1 + c) ^ b1lo);
+        v4u eqhi = (loadu(a0 + c + 4) ^ b0hi) & (loadu(a1 + c + 4) ^ b1hi);
+        v4u hplo = loadu(hp + c), hmlo = loadu(hm + c), hphi = loadu(hp + c + 4), hmhi = loadu(hm + c + 4);
+        myers_step_v4(hplo, hmlo, vplo, vmlo, eqlo);
+        myers_step_v4(hphi, hmhi, vphi, vmhi, eqhi);
+        storeu(hp + c, hplo);
+        storeu(hm + c, hmlo);
+        storeu(hp + c + 4, hphi);
+        storeu(hm + c + 4, hmhi);
+    }
+    for (int q = 0; q < 4; q++) {
+        v8[7 - q] = V{vplo[q], vmlo[q]};
+        v8[3 - q] = V{vphi[q], vmhi[q]};
+    }
+    // bottom-right triangle: word j, columns na-j .. na-1
+    for (size_t j = 1; j < 8; j++)
+        for (size_t i = na - j; i < na; i++) scalar(i, j);
+}
+
 // simd::compute semantics (simd.rs:98-226): rectangle a[0..na) x b[0..nb) words.
 // h: top deltas in, bottom deltas out; v: left deltas in, right deltas out. Returns sum of bottom h.
 // (The reference's non-exact padded mode returns the same number and leaves h unspecified; every caller
 //  that reads h uses exact mode, blocks.rs:740-746. We always compute exactly.)
 inline Cost bp_compute(const Bits* a, size_t na, const Bits* b, size_t nb, H* h, V* v) {
-    for (size_t j = 0; j < nb; j++) {
+    size_t j = 0;
+    if (nb >= 8 && na >= 16) {
+        static thread_local Unzipped uz;
+        uz.a0.resize(na);
+        uz.a1.resize(na);
+        uz.hp.resize(na);
+        uz.hm.resize(na);
+        for (size_t i = 0; i < na; i++) {
+            uz.a0[i] = a[i].b0;
+            uz.a1[i] = a[i].b1;
+            uz.hp[i] = h[i].p;
+            uz.hm[i] = h[i].m;
+        }
+        for (; j + 8 <= nb; j += 8) strip8(a, uz, na, b + j, v + j);
+        for (size_t i = 0; i < na; i++) h[i] = H{uz.hp[i], uz.hm[i]};
+    }
+    for (; j < nb; j++) {  // remaining rows: scalar::row (scalar.rs:37-46)
         V vj = v[j];
         const Bits cb = b[j];
         for (size_t i = 0; i < na; i++) myers_compute_block(h[i], vj, a[i], cb);

@@ -140,18 +140,25 @@ struct Match {  // matches.rs:54-61
     bool is_active() const { return pruned == Active; }
 };
 
-struct CenteredVec {  // matches.rs:94-127 — semantically a total map diag -> I with a default.
-    std::unordered_map<I, I> m;
+struct CenteredVec {  // matches.rs:94-127 — a vector centred on 0 that grows on demand; reads outside return the default.
+    std::vector<I> vec;
     I def;
-    explicit CenteredVec(I d) : def(d) {}
+    explicit CenteredVec(I d) : vec(1, d), def(d) {}
     I index(I idx) const {
-        auto it = m.find(idx);
-        return it == m.end() ? def : it->second;
+        int64_t k = (int64_t)idx + (int64_t)(vec.size() / 2);
+        return (k < 0 || k >= (int64_t)vec.size()) ? def : vec[(size_t)k];
     }
     I& index_mut(I idx) {
-        auto it = m.find(idx);
-        if (it == m.end()) it = m.emplace(idx, def).first;
-        return it->second;
+        int64_t half = (int64_t)(vec.size() / 2);
+        int64_t mag = idx < 0 ? -(int64_t)idx : (int64_t)idx;
+        if (mag > half) {
+            int64_t new_half = std::max<int64_t>(mag, (int64_t)vec.size());
+            std::vector<I> nv((size_t)(2 * new_half + 1), def);
+            std::copy(vec.begin(), vec.end(), nv.begin() + (new_half - half));
+            vec.swap(nv);
+            half = new_half;
+        }
+        return vec[(size_t)((int64_t)idx + half)];
     }
 };
 
@@ -274,9 +281,26 @@ inline Matches find_matches_hash_a(const uint8_t* a, size_t n, const uint8_t* b,
     CenteredVec next_match_per_diag(I_MAX);
     std::vector<I> fr, next_fr;
 
-    // hash_to_smallvec: hash the chunked k-mers of a (SmallVec push order = increasing i).
-    std::unordered_map<uint32_t, std::vector<I>> h;
-    for (I i = 0; i + k <= (I)n; i += k) h[(uint32_t)QGrams::to_qgram(a + i, k)].push_back(i);
+    // hash_to_smallvec: hash the chunked k-mers of a (SmallVec push order = increasing i). Flat open-addressing
+    // table key -> first seed, duplicates chained in increasing i (stands in for FxHashMap<u32, SmallVec<[I; 2]>>).
+    const size_t nseeds = n >= (size_t)k ? (n - k) / k + 1 : 0;
+    size_t tsize = 16;
+    while (tsize < 2 * nseeds + 2) tsize <<= 1;
+    std::vector<uint32_t> tkey(tsize, 0);
+    std::vector<I> thead(tsize, -1), ttail(tsize, -1), tnext(nseeds, -1);
+    auto slot_of = [&](uint32_t key) { return (size_t)((key * 0x9E3779B1u) >> 7) & (tsize - 1); };
+    for (size_t sidx = 0; sidx < nseeds; sidx++) {
+        uint32_t key = (uint32_t)QGrams::to_qgram(a + sidx * k, k);
+        size_t sl = slot_of(key);
+        while (thead[sl] >= 0 && tkey[sl] != key) sl = (sl + 1) & (tsize - 1);
+        if (thead[sl] < 0) {
+            tkey[sl] = key;
+            thead[sl] = ttail[sl] = (I)sidx;
+        } else {
+            tnext[ttail[sl]] = (I)sidx;
+            ttail[sl] = (I)sidx;
+        }
+    }
 
     auto push = [&](Match mt) {  // MatchBuilder::push, matches.rs:205-247
         out.pushed++;
@@ -298,11 +322,22 @@ inline Matches find_matches_hash_a(const uint8_t* a, size_t n, const uint8_t* b,
     };
 
     // b_qgrams_rev: all windows of b, right to left (qgrams.rs:81-97).
-    for (I j = (I)m - k; j >= 0; j--) {
-        uint32_t key = (uint32_t)QGrams::to_qgram(b + j, k);
-        auto it = h.find(key);
-        if (it == h.end()) continue;
-        for (I i : it->second) push(Match{Pos{i, j}, Pos{i + k, j + k}, 0, 1, Active});
+    {
+        // rolling key, right to left: q >>= 2; q |= bits(c) << 2(k-1)  (qgrams.rs:81-97)
+        uint64_t q = 0;
+        const unsigned leftshift = 2 * (unsigned)(k - 1);
+        for (I j = (I)m - 1; j >= 0; j--) {
+            q = (q >> 2) | (QGrams::char_to_bits(b[j]) << leftshift);
+            if (j > (I)m - k) continue;
+            uint32_t key = (uint32_t)q;
+            size_t sl = slot_of(key);
+            while (thead[sl] >= 0 && tkey[sl] != key) sl = (sl + 1) & (tsize - 1);
+            if (thead[sl] < 0) continue;
+            for (I sidx = thead[sl]; sidx >= 0; sidx = tnext[sidx]) {
+                I i = sidx * k;
+                push(Match{Pos{i, j}, Pos{i + k, j + k}, 0, 1, Active});
+            }
+        }
     }
     // matches.sort(); finish(): sort again, dedup by (start,end) keeping the first (lowest cost).
     std::stable_sort(out.matches.begin(), out.matches.end(), match_key_less);
