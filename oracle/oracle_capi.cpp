@@ -8,6 +8,8 @@
 // cost == Levenshtein on pa-test's 8 pairs and astarpa's regression pairs, example.c cost 2,
 // example.cpp CIGAR text format, the pa-bitpacking block KAT, qgram KATs. Exact A*PA2 CIGAR strings and
 // band shapes are NOT pinned by any reference test ("parity unpinned" for those).
+#include <malloc.h>
+
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -257,6 +259,11 @@ int64_t oracle_gcsh_info(const uint8_t* a, size_t n, const uint8_t* b, size_t m,
 double oracle_align_batch(int preset, int trace, size_t n_pairs, const uint8_t* a_all, const int64_t* a_off,
                           const uint8_t* b_all, const int64_t* b_off, int n_threads, int64_t* costs,
                           int64_t* cigar_lens, int64_t* computed_cells, uint64_t* cigar_hash) {
+    // Keep large vectors on the per-thread heaps instead of mmap/munmap per pair (page-fault and mmap-lock storms with
+    // many threads would otherwise dominate; the Rust reference would use a pooling allocator in such a setting).
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_ARENA_MAX, 256);
     std::atomic<size_t> next{0};
     AstarPa2Params params = preset_params(preset);
     auto t0 = std::chrono::steady_clock::now();
