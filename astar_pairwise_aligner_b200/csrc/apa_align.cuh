@@ -14,8 +14,6 @@ namespace apa {
 // Everything one warp needs to know about its pair.
 struct PairCtx {
     I n, m;
-    const uint8_t* a;
-    const uint8_t* b;
     const uint2* bprof;  // negated bit planes of b per 32 rows (profile.rs:124-131), zero padded to a multiple of 64 rows
     const uint2* aprof;  // the same packing of a (used by the diagonal extensions)
     uint8_t* arena;      // per-pair scratch
@@ -229,7 +227,7 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         uint32_t off = arena_alloc(cx, (uint32_t)nhw * 8u + (uint32_t)(nhw + 1) * 4u);
         if (cx.status != ST_PENDING) return PASS_NONE;
         Cost top_val = blk_index(prev, rounded.s) + (ie - is);
-        stage_amask(sm, cx.a, is, ie - is, lane);
+        stage_amask(sm, cx.aprof, is, ie - is, lane);
         uint2* vout = (uint2*)(cx.arena + off);
         int32_t* cumout = (int32_t*)(cx.arena + off + (size_t)nhw * 8);
         long long t_dp0 = APA_TIC();

@@ -39,11 +39,14 @@ __device__ __forceinline__ void myers_step(uint32_t a0, uint32_t a1, uint32_t b0
     vm = hps & vx;
 }
 
-// Stage the a-masks of columns [col_s, col_s + ncols) of `a` into shared memory.
-__device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint8_t* __restrict__ a, I col_s, int ncols, int lane) {
-    for (int c = lane; c < ncols; c += 32) {
-        uint32_t r = rank_acgt(a[col_s + c]);
-        sm.amask[c] = make_uint2(0u - (r & 1u), 0u - (r >> 1));
+// Stage the a-masks of columns [col_s, col_s + ncols) into shared memory from the packed planes of a
+// (col_s is a multiple of 256, so the block starts on a half-word boundary). Stored planes are negated rank bits:
+// mask = 0 - rank_bit = stored_bit - 1.
+__device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restrict__ aprof, I col_s, int ncols, int lane) {
+    const int hw0 = col_s >> 5;
+    for (int k = 0; 32 * k < ncols; k++) {
+        const uint2 pl = aprof[hw0 + k];
+        sm.amask[32 * k + lane] = make_uint2(((pl.x >> lane) & 1u) - 1u, ((pl.y >> lane) & 1u) - 1u);
     }
     __syncwarp();
 }

@@ -3,12 +3,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/astarpa.h"
@@ -17,6 +21,8 @@
 #include "apa_trace.cuh"
 
 using namespace apa;
+
+extern "C" int apa_pack_planes_host(const uint8_t* seq, int64_t len, int64_t hw_begin, int64_t hw_end, uint32_t* out);
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
@@ -34,8 +40,6 @@ static int set_err(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------ kernels
 struct BatchDev {
     uint64_t n_pairs;
-    const uint8_t* a_all;
-    const uint8_t* b_all;
     const int64_t* a_off;
     const int64_t* b_off;
     const int64_t* bp_off;  // per pair offset into bprof, in 32-row half-words (two padding half-words per pair)
@@ -63,54 +67,11 @@ struct BatchDev {
     uint32_t* dbg_n;
 };
 
-// K0 (fused into the align kernel): negated bit planes per 32 bases (BitProfile::build for b,
-// pa-bitpacking/src/profile.rs:124-131; the same packing of a feeds the diagonal extensions) and input validation
-// (the reference panics on bytes outside ACGT, profile.rs:113). Each lane packs one 32-base group per iteration.
-__device__ bool dev_pack_planes(const uint8_t* __restrict__ seq, int64_t len, uint2* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nhw = ((len + 63) / 64) * 2 + 2;  // + two zero half-words of padding
-    bool bad = false;
-    for (int64_t hw = lane; hw < nhw; hw += 32) {
-        uint32_t b0 = 0, b1 = 0;
-        const int64_t j0 = hw * 32;
-        if (j0 + 32 <= len && ((reinterpret_cast<uintptr_t>(seq + j0) & 3) == 0)) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(seq + j0);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                uint32_t x = w[q];
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    uint32_t c = (x >> (8 * t)) & 0xffu;
-                    bad |= !is_acgt(c);
-                    uint32_t r = rank_acgt(c);
-                    b0 |= ((r & 1u) ^ 1u) << (4 * q + t);
-                    b1 |= ((r >> 1) ^ 1u) << (4 * q + t);
-                }
-            }
-        } else {
-            for (int t = 0; t < 32; t++) {
-                int64_t j = j0 + t;
-                if (j < len) {
-                    uint32_t c = seq[j];
-                    bad |= !is_acgt(c);
-                    uint32_t r = rank_acgt(c);
-                    b0 |= ((r & 1u) ^ 1u) << t;
-                    b1 |= ((r >> 1) ^ 1u) << t;
-                }
-            }
-        }
-        out[hw] = make_uint2(b0, b1);
-    }
-    bad = __any_sync(FULL, bad);
-    __syncwarp();
-    return !bad;
-}
-
 constexpr int WARPS_PER_CTA = 4;
 
 // K1+K3 fused per pair: a persistent warp pulls pairs from the device work queue and runs the band-doubling
 // search, the traceback and the CIGAR text emission for each.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchDev bd) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 12) apa_align_kernel(BatchDev bd) {
     __shared__ WarpSmem smem[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -136,18 +97,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchD
         PairCtx cx;
         cx.n = (I)(bd.a_off[p + 1] - bd.a_off[p]);
         cx.m = (I)(bd.b_off[p + 1] - bd.b_off[p]);
-        cx.a = bd.a_all + bd.a_off[p];
-        cx.b = bd.b_all + bd.b_off[p];
         cx.bprof = bd.bprof + bd.bp_off[p];
         cx.aprof = bd.aprof + bd.ap_off[p];
-        {
-            bool ok_a = dev_pack_planes(cx.a, cx.n, bd.aprof + bd.ap_off[p]);
-            bool ok_b = dev_pack_planes(cx.b, cx.m, bd.bprof + bd.bp_off[p]);
-            if (!(ok_a && ok_b)) {
-                if (lane == 0) bd.status[p] = ST_BAD_INPUT;
-                continue;
-            }
-        }
         cx.arena = arena;
         cx.arena_size = bd.arena_size;
         cx.nblk = (cx.n + BLOCK_W - 1) / BLOCK_W;
@@ -235,7 +186,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel(BatchD
 
 // Stand-alone block-DP rectangle (apa_block_compute): one warp, arbitrary top deltas are not needed by the hot
 // path (HMode::None only), so h_in must be all +1; h_out is reconstructed column by column for the KAT.
-__global__ void apa_block_kernel(const uint8_t* a, int na, const uint2* bprof, int nhw, uint2* v, int32_t* cum, uint2* fillvals) {
+__global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof, int nhw, uint2* v, int32_t* cum, uint2* fillvals) {
     __shared__ WarpSmem sm;
     const int lane = threadIdx.x & 31;
     BlkView prev;
@@ -250,13 +201,17 @@ __global__ void apa_block_kernel(const uint8_t* a, int na, const uint2* bprof, i
     // the rectangle may be wider than one block: sweep it in 256-column slabs, each slab's right column feeding the next
     for (int c0 = 0; c0 < na; c0 += BLOCK_W) {
         int nc = min(BLOCK_W, na - c0);
-        stage_amask(sm, a, c0, nc, lane);
+        stage_amask(sm, aprof, c0, nc, lane);
         block_dp<true>(sm, bprof, prev, nc, 0, nhw * 32, v, cum, 0, fillvals + (size_t)c0 * nhw, ws);
         __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+struct apa_engine;
+static cudaError_t eng_alloc(apa_engine* e, void** out, size_t bytes);
+static void eng_release(apa_engine* e, void* p);
+
 struct apa_engine {
     int device = 0;
     int sm_count = 0;
@@ -264,7 +219,13 @@ struct apa_engine {
     cudaStream_t copy_stream = nullptr;  // streaming uploads overlap the persistent kernel
     uint32_t* d_ready = nullptr;
     uint32_t* h_ready = nullptr;  // pinned: cumulative pair counts per upload chunk
+    uint32_t* h_stage = nullptr;  // pinned staging for the packed planes (grow-only)
+    size_t h_stage_cap = 0;
     cudaEvent_t ev[6] = {};
+    // Device-buffer cache: cudaMalloc/cudaFree of multi-GB buffers costs milliseconds each and synchronises the device,
+    // so buffers released by a batch are kept for the next one (grow-only, per engine).
+    std::unordered_map<void*, size_t> live;
+    std::vector<std::pair<void*, size_t>> free_blocks;
     unsigned long long* d_queue = nullptr;   // [0] queue head, [1] pool cursor, [2..] stats
     uint8_t* d_arena = nullptr;
     size_t arena_total = 0;
@@ -275,7 +236,6 @@ struct apa_batch {
     std::vector<int64_t> a_off, b_off, bp_off, ap_off;
     uint64_t total_a = 0, total_b = 0, total_hw = 0, total_hw_a = 0;
     I max_n = 0, max_m = 0;
-    uint8_t *d_a = nullptr, *d_b = nullptr;
     int64_t *d_a_off = nullptr, *d_b_off = nullptr, *d_bp_off = nullptr, *d_ap_off = nullptr;
     uint2 *d_bprof = nullptr, *d_aprof = nullptr;
     int32_t *d_status = nullptr, *d_cost = nullptr;
@@ -285,6 +245,8 @@ struct apa_batch {
     uint64_t pool_cap = 0;
     // streaming upload (apa_align_batch): bases are copied chunk by chunk while the kernel already runs
     const uint8_t *h_a = nullptr, *h_b = nullptr;
+    int64_t h_a_off0 = 0, h_b_off0 = 0;
+    double pack_ms = 0;
     std::vector<uint32_t> chunk_end;  // pairs (in work order) available after each chunk
     std::vector<uint32_t> chunk_pair_end;  // pair index (exclusive) of each chunk: chunks are contiguous index ranges
     bool ran = false;
@@ -296,6 +258,39 @@ struct apa_batch {
     uint32_t dbg_cap = 0;
     uint32_t* d_dbg_n = nullptr;
 };
+
+static cudaError_t eng_alloc(apa_engine* e, void** out, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    int best = -1;
+    for (size_t k = 0; k < e->free_blocks.size(); k++) {
+        size_t cap = e->free_blocks[k].second;
+        if (cap >= bytes && cap <= 2 * bytes + (1u << 20) && (best < 0 || cap < e->free_blocks[best].second)) best = (int)k;
+    }
+    if (best >= 0) {
+        *out = e->free_blocks[best].first;
+        e->live[*out] = e->free_blocks[best].second;
+        e->free_blocks.erase(e->free_blocks.begin() + best);
+        return cudaSuccess;
+    }
+    cudaError_t ce = cudaMalloc(out, bytes);
+    if (ce != cudaSuccess) {  // drop the cache and retry once
+        for (auto& fb : e->free_blocks) cudaFree(fb.first);
+        e->free_blocks.clear();
+        ce = cudaMalloc(out, bytes);
+    }
+    if (ce == cudaSuccess) e->live[*out] = bytes;
+    return ce;
+}
+static void eng_release(apa_engine* e, void* p) {
+    if (!p) return;
+    auto it = e ? e->live.find(p) : decltype(e->live.find(p)){};
+    if (!e || it == e->live.end()) {
+        cudaFree(p);
+        return;
+    }
+    e->free_blocks.emplace_back(p, it->second);
+    e->live.erase(it);
+}
 
 extern "C" const char* apa_last_error(void) { return g_last_error.c_str(); }
 
@@ -333,6 +328,8 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
 extern "C" void apa_engine_destroy(apa_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    for (auto& fb : e->free_blocks) cudaFree(fb.first);
+    for (auto& lv : e->live) cudaFree(lv.first);
     if (e->d_arena) cudaFree(e->d_arena);
     if (e->d_queue) cudaFree(e->d_queue);
     for (auto& ev : e->ev)
@@ -341,10 +338,50 @@ extern "C" void apa_engine_destroy(apa_engine* e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->d_ready) cudaFree(e->d_ready);
     if (e->h_ready) cudaFreeHost(e->h_ready);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
     delete e;
 }
 
-extern "C" void apa_free(void* p) { free(p); }
+// CIGAR text pools are handed out in page-locked memory (D2H at full PCIe rate) and recycled: apa_free() returns a
+// pool to a small process-wide cache instead of unpinning it (cudaHostAlloc / cudaFreeHost cost tens of milliseconds).
+static std::mutex g_pin_mu;
+static std::unordered_map<void*, size_t> g_pin_live;              // handed out
+static std::vector<std::pair<void*, size_t>> g_pin_free;          // cached
+static void* pinned_pool_get(size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    int best = -1;
+    for (size_t k = 0; k < g_pin_free.size(); k++)
+        if (g_pin_free[k].second >= bytes && (best < 0 || g_pin_free[k].second < g_pin_free[best].second)) best = (int)k;
+    void* p = nullptr;
+    size_t cap = 0;
+    if (best >= 0) {
+        p = g_pin_free[best].first;
+        cap = g_pin_free[best].second;
+        g_pin_free.erase(g_pin_free.begin() + best);
+    } else {
+        cap = bytes + bytes / 4 + 4096;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    }
+    g_pin_live[p] = cap;
+    return p;
+}
+extern "C" void apa_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        auto it = g_pin_live.find(p);
+        if (it != g_pin_live.end()) {
+            if (g_pin_free.size() < 4) {
+                g_pin_free.emplace_back(p, it->second);
+            } else {
+                cudaFreeHost(p);
+            }
+            g_pin_live.erase(it);
+            return;
+        }
+    }
+    free(p);
+}
 
 // Pinned (page-locked) host memory for the end-to-end path.
 extern "C" void* apa_pinned_alloc(uint64_t bytes) {
@@ -362,22 +399,71 @@ extern "C" void apa_pinned_free(void* p) {
 extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     if (!b) return;
     if (e) cudaSetDevice(e->device);
-    cudaFree(b->d_a);
-    cudaFree(b->d_b);
-    cudaFree(b->d_a_off);
-    cudaFree(b->d_b_off);
-    cudaFree(b->d_bp_off);
-    cudaFree(b->d_bprof);
-    cudaFree(b->d_aprof);
-    cudaFree(b->d_ap_off);
-    cudaFree(b->d_status);
-    cudaFree(b->d_cost);
-    cudaFree(b->d_cig_off);
-    cudaFree(b->d_cig_len);
-    cudaFree(b->d_order);
-    cudaFree(b->d_pool);
+    eng_release(e, b->d_a_off);
+    eng_release(e, b->d_b_off);
+    eng_release(e, b->d_bp_off);
+    eng_release(e, b->d_bprof);
+    eng_release(e, b->d_aprof);
+    eng_release(e, b->d_ap_off);
+    eng_release(e, b->d_status);
+    eng_release(e, b->d_cost);
+    eng_release(e, b->d_cig_off);
+    eng_release(e, b->d_cig_len);
+    eng_release(e, b->d_order);
+    eng_release(e, b->d_pool);
     delete b;
 }
+
+// ---- host packing tasks -------------------------------------------------------------------------------------------
+struct PackTask {
+    const uint8_t* seq;
+    int64_t len;
+    int64_t hw_begin, hw_end;  // half-words of this sequence (padding half-words included: they pack to zero)
+    uint32_t* out;             // staging address of half-word 0 of this sequence
+    uint32_t chunk;
+};
+
+struct Packer {  // packs all tasks with a few host threads; per-chunk completion counters let the caller pipeline
+    std::vector<PackTask> tasks;
+    std::vector<std::atomic<int>> remaining;  // per chunk
+    std::atomic<size_t> next{0};
+    std::atomic<int> bad{0};
+    std::vector<std::thread> threads;
+    explicit Packer(size_t n_chunks) : remaining(n_chunks) {
+        for (auto& r : remaining) r.store(0);
+    }
+    void add(const PackTask& t) {
+        tasks.push_back(t);
+        remaining[t.chunk].fetch_add(1);
+    }
+    void start(int n_threads) {
+        for (int t = 0; t < n_threads; t++)
+            threads.emplace_back([this]() {
+                for (;;) {
+                    size_t k = next.fetch_add(1);
+                    if (k >= tasks.size()) break;
+                    const PackTask& tk = tasks[k];
+                    if (apa_pack_planes_host(tk.seq, tk.len, tk.hw_begin, tk.hw_end, tk.out)) bad.store(1);
+                    remaining[tk.chunk].fetch_sub(1, std::memory_order_release);
+                }
+            });
+    }
+    void wait_chunk(size_t c) {
+        while (remaining[c].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    }
+    void join() {
+        for (auto& t : threads) t.join();
+        threads.clear();
+    }
+    ~Packer() { join(); }
+};
+
+static int pack_threads() {
+    unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(16u, hc ? hc : 4u));
+}
+
+static int upload_planes(apa_engine* e, apa_batch* b, bool streaming);
 
 static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all,
                          const int64_t* b_off, bool defer_data, apa_batch** out) {
@@ -410,7 +496,11 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     b->total_hw_a = hwa;
     b->total_a = (uint64_t)(a_off[n_pairs] - a_off[0]);
     b->total_b = (uint64_t)(b_off[n_pairs] - b_off[0]);
-    // Rebase offsets to the start of the copied ranges.
+    b->h_a = a_all;
+    b->h_b = b_all;
+    b->h_a_off0 = a_off[0];
+    b->h_b_off0 = b_off[0];
+    // Offsets rebased to the first pair (only lengths matter on the device).
     std::vector<int64_t> ao(b->a_off), bo(b->b_off);
     for (auto& x : ao) x -= a_off[0];
     for (auto& x : bo) x -= b_off[0];
@@ -424,57 +514,111 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     auto by_size = [&](uint32_t x, uint32_t y) {
         return (ao[x + 1] - ao[x]) + (bo[x + 1] - bo[x]) > (ao[y + 1] - ao[y]) + (bo[y + 1] - bo[y]);
     };
-    if (defer_data && n_pairs) {
+    if (n_pairs) {
         const uint64_t total = b->total_a + b->total_b;
-        const uint64_t n_chunks = std::min<uint64_t>(200, std::max<uint64_t>(1, total / (32ull << 20)));
+        const uint64_t n_chunks = defer_data ? std::min<uint64_t>(200, std::max<uint64_t>(1, total / (32ull << 20))) : 1;
         const uint64_t per = (total + n_chunks - 1) / n_chunks;
         uint64_t acc = 0, start = 0;
         for (uint64_t p = 0; p < n_pairs; p++) {
             acc += (uint64_t)(ao[p + 1] - ao[p]) + (uint64_t)(bo[p + 1] - bo[p]);
-            if (acc >= per || p + 1 == n_pairs) {
+            if ((acc >= per && b->chunk_pair_end.size() + 1 < n_chunks) || p + 1 == n_pairs) {
                 std::stable_sort(order.begin() + start, order.begin() + p + 1, by_size);
                 b->chunk_pair_end.push_back((uint32_t)(p + 1));
                 acc = 0;
                 start = p + 1;
             }
         }
-        b->h_a = a_all + a_off[0];
-        b->h_b = b_all + b_off[0];
-    } else {
-        std::stable_sort(order.begin(), order.end(), by_size);
     }
 
     cudaStream_t st = e->stream;
     CUDA_TRY(cudaEventRecord(e->ev[0], st));
-    CUDA_TRY(cudaMalloc(&b->d_a, std::max<uint64_t>(b->total_a, 16) + 64));
-    CUDA_TRY(cudaMalloc(&b->d_b, std::max<uint64_t>(b->total_b, 16) + 64));
-    CUDA_TRY(cudaMalloc(&b->d_a_off, (n_pairs + 1) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_b_off, (n_pairs + 1) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_bp_off, (n_pairs + 1) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_bprof, std::max<uint64_t>(hw, 2) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_aprof, std::max<uint64_t>(hwa, 2) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_ap_off, (n_pairs + 1) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_status, std::max<uint64_t>(n_pairs, 1) * 4));
-    CUDA_TRY(cudaMalloc(&b->d_cost, std::max<uint64_t>(n_pairs, 1) * 4));
-    CUDA_TRY(cudaMalloc(&b->d_cig_off, std::max<uint64_t>(n_pairs, 1) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_cig_len, std::max<uint64_t>(n_pairs, 1) * 8));
-    CUDA_TRY(cudaMalloc(&b->d_order, std::max<uint64_t>(n_pairs, 1) * 8));  // [0,n): work order, [n,2n): retry list
-    if (!defer_data) {
-        if (b->total_a) CUDA_TRY(cudaMemcpyAsync(b->d_a, a_all + a_off[0], b->total_a, cudaMemcpyHostToDevice, st));
-        if (b->total_b) CUDA_TRY(cudaMemcpyAsync(b->d_b, b_all + b_off[0], b->total_b, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_a_off, (n_pairs + 1) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_b_off, (n_pairs + 1) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_bp_off, (n_pairs + 1) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_bprof, std::max<uint64_t>(hw, 2) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_aprof, std::max<uint64_t>(hwa, 2) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_ap_off, (n_pairs + 1) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_status, std::max<uint64_t>(n_pairs, 1) * 4));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_cost, std::max<uint64_t>(n_pairs, 1) * 4));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_cig_off, std::max<uint64_t>(n_pairs, 1) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_cig_len, std::max<uint64_t>(n_pairs, 1) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_order, std::max<uint64_t>(n_pairs, 1) * 8));  // [0,n): work order, [n,2n): retry list
+    // pinned staging for the packed planes: [aprof | bprof]
+    const size_t stage_words = (size_t)(hwa + hw) * 2 + 16;
+    if (e->h_stage_cap < stage_words) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr;
+        e->h_stage_cap = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&e->h_stage, stage_words * 4, cudaHostAllocDefault));
+        e->h_stage_cap = stage_words;
     }
     CUDA_TRY(cudaMemcpyAsync(b->d_a_off, ao.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_b_off, bo.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_bp_off, b->bp_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_ap_off, b->ap_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_pairs) CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), n_pairs * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->stats.h2d_bytes = (hwa + hw) * 8 + 4 * (n_pairs + 1) * 8 + n_pairs * 4;
+    if (!defer_data) {
+        int rc = upload_planes(e, b, /*streaming=*/false);
+        if (rc != APA_OK) {
+            apa_batch_free(e, b);
+            return rc;
+        }
+    }
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
     b->stats.h2d_ms = ms;
-    b->stats.h2d_bytes = b->total_a + b->total_b + 4 * (n_pairs + 1) * 8 + n_pairs * 4;
     *out = b;
+    return APA_OK;
+}
+
+// Pack the bases on host threads into the pinned staging buffer and copy the planes to HBM, chunk by chunk. With
+// streaming the copies go to the copy stream and each chunk is followed by the ready counter the running kernel polls.
+static int upload_planes(apa_engine* e, apa_batch* b, bool streaming) {
+    const size_t n_chunks = b->chunk_pair_end.size();
+    if (n_chunks == 0) return APA_OK;
+    auto tp0 = std::chrono::steady_clock::now();
+    uint32_t* stage_a = e->h_stage;
+    uint32_t* stage_b = e->h_stage + (size_t)b->total_hw_a * 2;
+    Packer pk(n_chunks);
+    const int64_t SEG = 1 << 15;  // half-words per task (1 Mi bases)
+    uint32_t p0 = 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const uint32_t p1 = b->chunk_pair_end[c];
+        for (uint32_t p = p0; p < p1; p++) {
+            const int64_t n = b->a_off[p + 1] - b->a_off[p], m = b->b_off[p + 1] - b->b_off[p];
+            const int64_t nhw_a = b->ap_off[p + 1] - b->ap_off[p], nhw_b = b->bp_off[p + 1] - b->bp_off[p];
+            const uint8_t* sa = b->h_a + b->h_a_off0 + b->a_off[p];
+            const uint8_t* sb = b->h_b + b->h_b_off0 + b->b_off[p];
+            for (int64_t h0 = 0; h0 < nhw_a; h0 += SEG)
+                pk.add(PackTask{sa, n, h0, std::min(nhw_a, h0 + SEG), stage_a + (size_t)b->ap_off[p] * 2, (uint32_t)c});
+            for (int64_t h0 = 0; h0 < nhw_b; h0 += SEG)
+                pk.add(PackTask{sb, m, h0, std::min(nhw_b, h0 + SEG), stage_b + (size_t)b->bp_off[p] * 2, (uint32_t)c});
+        }
+        p0 = p1;
+    }
+    pk.start(pack_threads());
+    cudaStream_t cs = streaming ? e->copy_stream : e->stream;
+    p0 = 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const uint32_t p1 = b->chunk_pair_end[c];
+        pk.wait_chunk(c);
+        const int64_t a0 = b->ap_off[p0], a1 = b->ap_off[p1], b0 = b->bp_off[p0], b1 = b->bp_off[p1];
+        if (a1 > a0) CUDA_TRY(cudaMemcpyAsync(b->d_aprof + a0, stage_a + (size_t)a0 * 2, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cs));
+        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(b->d_bprof + b0, stage_b + (size_t)b0 * 2, (size_t)(b1 - b0) * 8, cudaMemcpyHostToDevice, cs));
+        if (streaming) {
+            e->h_ready[c] = p1;
+            CUDA_TRY(cudaMemcpyAsync(e->d_ready, &e->h_ready[c], 4, cudaMemcpyHostToDevice, cs));
+        }
+        p0 = p1;
+    }
+    pk.join();
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    b->pack_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+    if (pk.bad.load()) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT (the reference panics here: pa-bitpacking/src/profile.rs:113)");
     return APA_OK;
 }
 
@@ -513,15 +657,13 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     // CIGAR text pool: text length <= |a| + |b| per pair (+ NUL).
     uint64_t pool_need = trace ? (b->total_a + b->total_b + b->n_pairs + 64) : 16;
     if (b->pool_cap < pool_need) {
-        cudaFree(b->d_pool);
+        eng_release(e, b->d_pool);
         b->d_pool = nullptr;
-        CUDA_TRY(cudaMalloc(&b->d_pool, pool_need));
+        CUDA_TRY(eng_alloc(e, (void**)&b->d_pool, pool_need));
         b->pool_cap = pool_need;
     }
     BatchDev bd{};
     bd.n_pairs = b->n_pairs;
-    bd.a_all = b->d_a;
-    bd.b_all = b->d_b;
     bd.a_off = b->d_a_off;
     bd.b_off = b->d_b_off;
     bd.bp_off = b->d_bp_off;
@@ -552,7 +694,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     std::vector<uint32_t> pending;  // empty = all pairs in the uploaded order
     b->h_status.assign(b->n_pairs, 0);
     for (int attempt = 0; attempt < 8; attempt++) {
-        int ctas_per_sm = 8;
+        int ctas_per_sm = 12;
         uint64_t want_slots = (uint64_t)e->sm_count * ctas_per_sm * WARPS_PER_CTA;
         uint64_t n_work = attempt == 0 ? b->n_pairs : pending.size();
         uint64_t slots = std::min<uint64_t>(want_slots, ((n_work + WARPS_PER_CTA - 1) / WARPS_PER_CTA) * WARPS_PER_CTA);
@@ -588,18 +730,16 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         b->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
         if (streaming) {
-            // H2D of the bases, chunk by chunk on the copy stream, while the persistent kernel already consumes them.
-            uint32_t p0 = 0;
-            for (size_t c = 0; c < b->chunk_pair_end.size(); c++) {
-                const uint32_t p1 = b->chunk_pair_end[c];
-                const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
-                if (a1 > a0) CUDA_TRY(cudaMemcpyAsync(b->d_a + a0, b->h_a + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream));
-                if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(b->d_b + b0, b->h_b + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, e->copy_stream));
-                e->h_ready[c] = p1;
-                CUDA_TRY(cudaMemcpyAsync(e->d_ready, &e->h_ready[c], 4, cudaMemcpyHostToDevice, e->copy_stream));
-                p0 = p1;
+            // host threads pack the bases while the persistent kernel already consumes the chunks that have landed
+            int rc = upload_planes(e, b, /*streaming=*/true);
+            if (rc != APA_OK) {
+                // let the kernel drain (the ready counter must reach n_pairs), then report
+                e->h_ready[255] = (uint32_t)b->n_pairs;
+                cudaMemcpyAsync(e->d_ready, &e->h_ready[255], 4, cudaMemcpyHostToDevice, e->copy_stream);
+                cudaStreamSynchronize(e->copy_stream);
+                cudaStreamSynchronize(st);
+                return rc;
             }
-            CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
         }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -657,7 +797,7 @@ extern "C" int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, c
     uint64_t bytes = b->n_pairs * 4;
     char* pool = nullptr;
     if (b->trace && cigar_pool && cigar_off && cigar_len) {
-        pool = (char*)malloc(std::max<uint64_t>(b->pool_used, 1));
+        pool = (char*)pinned_pool_get(std::max<uint64_t>(b->pool_used, 1));
         if (!pool) return set_err(APA_ERR_TOO_LARGE, "host allocation of the CIGAR pool failed");
         CUDA_TRY(cudaMemcpyAsync(pool, b->d_pool, b->pool_used, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(cigar_off, b->d_cig_off, b->n_pairs * 8, cudaMemcpyDeviceToHost, st));
@@ -687,9 +827,18 @@ extern "C" int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_
     // Host buffers in, host buffers out: the bases stream to HBM in chunks while the persistent kernel is already
     // aligning the pairs that have arrived (H2D overlaps compute); results come back in one D2H at the end.
     apa_batch* b = nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     int rc = batch_prepare(e, n_pairs, a_all, a_off, b_all, b_off, true, &b);
+    auto t1 = std::chrono::steady_clock::now();
     if (rc == APA_OK) rc = batch_run(e, b, preset, trace, true);
+    auto t2 = std::chrono::steady_clock::now();
     if (rc == APA_OK) rc = apa_batch_download(e, b, costs, cigar_pool, cigar_off, cigar_len);
+    auto t3 = std::chrono::steady_clock::now();
+    if (getenv("APA_DEBUG_TIMING")) {
+        auto ms = [](auto x, auto y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
+        fprintf(stderr, "[apa_align_batch] prepare %.1f ms, run %.1f ms (pack+h2d %.1f ms), download %.1f ms\n", ms(t0, t1), ms(t1, t2),
+                b ? b->pack_ms : 0.0, ms(t2, t3));
+    }
     if (rc == APA_OK && stats) *stats = b->stats;
     apa_batch_free(e, b);
     return rc;
@@ -750,39 +899,26 @@ extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, c
         *bottom_sum = (int64_t)na;
         return APA_OK;
     }
-    // host-side profile of b in the device layout (same as dev_pack_planes)
-    std::vector<uint2> bp(nhw);
-    for (uint64_t hw = 0; hw < nhw; hw++) {
-        uint32_t b0 = 0, b1 = 0;
-        for (int t = 0; t < 32; t++) {
-            uint64_t j = hw * 32 + t;
-            if (j < mb) {
-                uint32_t c = b[j];
-                if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) return set_err(APA_ERR_BAD_INPUT, "byte outside ACGT");
-                uint32_t x = (c >> 1) & 3u, r = x ^ (x >> 1);
-                b0 |= ((r & 1u) ^ 1u) << t;
-                b1 |= ((r >> 1) ^ 1u) << t;
-            }
-        }
-        bp[hw] = make_uint2(b0, b1);
-    }
-    for (uint64_t i = 0; i < na; i++)
-        if (!(a[i] == 'A' || a[i] == 'C' || a[i] == 'G' || a[i] == 'T')) return set_err(APA_ERR_BAD_INPUT, "byte outside ACGT");
+    // host-side planes of a and b in the device layout (+2 padding half-words)
+    const uint64_t nhw_a = ((na + 63) / 64) * 2;
+    std::vector<uint2> bp(nhw + 2), apl(nhw_a + 2);
+    if (apa_pack_planes_host(b, (int64_t)mb, 0, (int64_t)nhw + 2, (uint32_t*)bp.data()) |
+        apa_pack_planes_host(a, (int64_t)na, 0, (int64_t)nhw_a + 2, (uint32_t*)apl.data()))
+        return set_err(APA_ERR_BAD_INPUT, "byte outside ACGT");
     std::vector<uint2> vv(nhw);
     for (uint64_t w = 0; w < nwords; w++) {
         vv[2 * w] = make_uint2((uint32_t)v[2 * w], (uint32_t)v[2 * w + 1]);
         vv[2 * w + 1] = make_uint2((uint32_t)(v[2 * w] >> 32), (uint32_t)(v[2 * w + 1] >> 32));
     }
-    uint8_t* d_a;
-    uint2 *d_bp, *d_v, *d_fill;
+    uint2 *d_a, *d_bp, *d_v, *d_fill;
     int32_t* d_cum;
-    CUDA_TRY(cudaMalloc(&d_a, na));
-    CUDA_TRY(cudaMalloc(&d_bp, nhw * 8));
+    CUDA_TRY(cudaMalloc(&d_a, (nhw_a + 2) * 8));
+    CUDA_TRY(cudaMalloc(&d_bp, (nhw + 2) * 8));
     CUDA_TRY(cudaMalloc(&d_v, nhw * 8));
     CUDA_TRY(cudaMalloc(&d_cum, (nhw + 1) * 4));
     CUDA_TRY(cudaMalloc(&d_fill, na * nhw * 8));
-    CUDA_TRY(cudaMemcpy(d_a, a, na, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d_bp, bp.data(), nhw * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_a, apl.data(), (nhw_a + 2) * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_bp, bp.data(), (nhw + 2) * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_v, vv.data(), nhw * 8, cudaMemcpyHostToDevice));
     apa_block_kernel<<<1, 32, 0, e->stream>>>(d_a, (int)na, d_bp, (int)nhw, d_v, d_cum, d_fill);
     CUDA_TRY(cudaGetLastError());
@@ -851,7 +987,7 @@ static uint64_t align_one(int preset, const uint8_t* a, uintptr_t a_len, const u
     uint8_t* out = (uint8_t*)malloc((size_t)clen + 1);
     memcpy(out, pool + coff, (size_t)clen);
     out[clen] = 0;
-    free(pool);
+    apa_free(pool);
     *cigar_ptr = out;
     *cigar_len = (uintptr_t)clen;
     return (uint64_t)cost;

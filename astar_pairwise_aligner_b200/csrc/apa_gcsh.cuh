@@ -256,8 +256,6 @@ __device__ __forceinline__ uint32_t kmer_hash(uint32_t key, int log_t) { return 
 // block store can reuse their space. Returns false on arena overflow (cx.status set).
 __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     const int lane = threadIdx.x & 31;
-    const uint8_t* a = cx.a;
-    const uint8_t* b = cx.b;
     const I n = cx.n, m = cx.m;
     H.n = n;
     H.m = m;
@@ -323,13 +321,9 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     for (I s0 = 0; s0 < ns; s0 += 32) {
         I s = s0 + lane;
         if (s < ns) {
-            uint32_t key = 0;
-#pragma unroll
-            for (int t = 0; t < GCSH_K; t++) {
-                uint32_t r = rank_acgt(a[s * GCSH_K + t]);
-                key |= (r & 1u) << t;
-                key |= (r >> 1) << (GCSH_K + t);
-            }
+            const uint2 w = extract32(cx.aprof, s * GCSH_K);  // planes are stored negated
+            const uint32_t km = (1u << GCSH_K) - 1u;
+            const uint32_t key = (~w.x & km) | ((~w.y & km) << GCSH_K);
             uint32_t slot = kmer_hash(key, log_t);
             unsigned long long want = ((unsigned long long)(uint32_t)s << 32) | key;  // uint2{key, seed}
             for (;;) {
@@ -343,7 +337,6 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
 
     // ---- scan all windows of b right to left (b_qgrams_rev, qgrams.rs:81-97), push matches in arrival order
     int M = 0;
-    const int nhw_b = ((m + 63) / 64) * 2;
     // next larger seed with this key after `after` (or the smallest when after < 0); returns count via cnt_out
     auto probe = [&](uint32_t key, I after, int& cnt_out) -> I {
         uint32_t slot = kmer_hash(key, log_t);
@@ -368,12 +361,8 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
         int c = 0;
         I seed0 = INT32_MAX;
         if (j >= 0) {
-            int hw = j >> 5, sh = j & 31;
-            uint2 lo = cx.bprof[hw];
-            uint2 hi = (hw + 1 < nhw_b) ? cx.bprof[hw + 1] : make_uint2(0u, 0u);
-            uint32_t p0 = ~__funnelshift_r(lo.x, hi.x, sh) & kmask;  // planes are stored negated
-            uint32_t p1 = ~__funnelshift_r(lo.y, hi.y, sh) & kmask;
-            key = p0 | (p1 << GCSH_K);
+            const uint2 w = extract32(cx.bprof, j);  // planes are stored negated
+            key = (~w.x & kmask) | ((~w.y & kmask) << GCSH_K);
             seed0 = probe(key, -1, c);
         }
         unsigned bal = __ballot_sync(FULL, c > 0);

@@ -307,7 +307,7 @@ __device__ bool dev_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, Cost cost)
                 const I jr_s = bm.js, jr_e = ts.tj;
                 ts.top -= 1;  // pop_last_block
                 I height = min(jr_e - jr_s, (ie - is) * 5 / 4);
-                stage_amask(sm, cx.a, is, ie - is, lane);
+                stage_amask(sm, cx.aprof, is, ie - is, lane);
                 for (;;) {
                     JRange r = jr_round_out(JRange{max(jr_e - height, pm.js), jr_e});
                     const int fnhw = (r.e - r.s) >> 5;

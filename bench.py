@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--preset", default=os.environ.get("APA_BENCH_PRESET", "simple"), choices=["simple", "full"])
+    ap.add_argument("--preset", default=os.environ.get("APA_BENCH_PRESET", "full"), choices=["simple", "full"])
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("APA_BENCH_PAIRS", "10000")), help="pairs per GPU")
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--e", type=float, default=0.05)
@@ -107,10 +107,22 @@ def make_batch(A, args, rank):
     return A.generate_batch(args.pairs, args.n, args.e, 0, seed0)
 
 
+def cpu_quota():
+    """CPUs this container may actually use (cgroup v2 cpu.max), or None when unlimited/unknown."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        return None
+
+
 def cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, sample):
     """Oracle (CPU port of the reference path) on a bounded sample, all host threads. Returns dict."""
     import oracle_lib as O
     threads = O.lib().oracle_hardware_threads()
+    quota = cpu_quota()
+    if quota:  # more threads than the cgroup CPU quota only adds contention
+        threads = max(1, min(threads, int(round(quota))))
     if sample <= 0:
         # calibrate on `threads` pairs, then size the sample for ~4 s of wall time
         k = min(threads, len(a_off) - 1)
@@ -126,7 +138,8 @@ def cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, sample):
             "sample": f"{sample} pairs of the same workload (n={args.n}, e={args.e}, preset {args.preset}, "
                       f"{'with' if trace else 'no'} CIGAR), {sec:.2f} s wall on {threads} threads",
             "computed_gcups": float(cells.sum()) / sec / 1e9, "bp_per_s": float(a_off[sample]) / sec, "seconds": sec,
-            "pairs": sample}
+            "pairs": sample, "pairs_per_s": sample / sec, "hardware_threads": O.lib().oracle_hardware_threads(),
+            "cgroup_cpu_quota": quota}
 
 
 def main():

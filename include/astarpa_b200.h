@@ -63,7 +63,7 @@ int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, cons
  * (Aligner::align with trace = true, astarpa2/src/lib.rs:210-215; trace = false is AstarPa2::cost, lib.rs:177-179). */
 int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace);
 /* HBM -> host: costs[n_pairs]; if the three cigar arguments are non-NULL also the CIGAR text pool: *cigar_pool is
- * malloc'd (free with apa_free); pair p's NUL-terminated text starts at (*cigar_pool)[cigar_off[p]] and has
+ * callee-allocated page-locked host memory (release it with apa_free, which recycles it); pair p's NUL-terminated text starts at (*cigar_pool)[cigar_off[p]] and has
  * strlen cigar_len[p] (pairs finish in any order, so offsets are not monotone). */
 int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len);
 int apa_batch_get_stats(apa_batch* b, apa_batch_stats* out);
