@@ -71,8 +71,7 @@ constexpr int WARPS_PER_CTA = 4;
 
 // K1+K3 fused per pair: a persistent warp pulls pairs from the device work queue and runs the band-doubling
 // search, the traceback and the CIGAR text emission for each.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 12) apa_align_kernel(BatchDev bd) {
-    __shared__ WarpSmem smem[WARPS_PER_CTA];
+__device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* smem) {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     WarpSmem& sm = smem[wib];
@@ -182,6 +181,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 12) apa_align_kernel(Batch
         atomicAdd(&bd.stats[4], acc_dt);
         for (int t = 0; t < 8; t++) atomicAdd(&bd.stats[5 + t], (unsigned long long)acc_t[t]);
     }
+}
+
+// Two register budgets of the same kernel: 64 registers (8 CTAs = 32 warps per SM, few spills) and 40 registers
+// (12 CTAs = 48 warps per SM). The host picks per batch: the number of warp slots is chosen so that the pairs fill
+// whole waves, and the variant follows from the slots needed per SM.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel_r64(BatchDev bd) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    apa_align_body(bd, smem);
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_align_kernel_r48(BatchDev bd) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    apa_align_body(bd, smem);
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 12) apa_align_kernel_r40(BatchDev bd) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    apa_align_body(bd, smem);
 }
 
 // Stand-alone block-DP rectangle (apa_block_compute): one warp, arbitrary top deltas are not needed by the hot
@@ -691,13 +706,17 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, 16 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(b->d_status, 0, b->n_pairs * 4, st));
     uint32_t arena_size = estimate_arena(b, preset, trace);
+    if (const char* ev = getenv("APA_ARENA_BYTES")) arena_size = (uint32_t)std::max<long long>(65536, atoll(ev));  // tests: force the overflow/retry path
     std::vector<uint32_t> pending;  // empty = all pairs in the uploaded order
     b->h_status.assign(b->n_pairs, 0);
     for (int attempt = 0; attempt < 8; attempt++) {
-        int ctas_per_sm = 12;
-        uint64_t want_slots = (uint64_t)e->sm_count * ctas_per_sm * WARPS_PER_CTA;
+        // Slots (resident warps). Measured on B200 (profiles/README.md): throughput grows with resident warps up to
+        // ~40 per SM even though the last wave is then only partly full; equalising the waves was slower.
         uint64_t n_work = attempt == 0 ? b->n_pairs : pending.size();
-        uint64_t slots = std::min<uint64_t>(want_slots, ((n_work + WARPS_PER_CTA - 1) / WARPS_PER_CTA) * WARPS_PER_CTA);
+        const uint64_t max_slots = (uint64_t)e->sm_count * 10 * WARPS_PER_CTA;
+        uint64_t slots = ((n_work + WARPS_PER_CTA - 1) / WARPS_PER_CTA) * WARPS_PER_CTA;
+        slots = std::min<uint64_t>(slots, max_slots);
+        if (const char* ev = getenv("APA_SLOTS")) slots = std::max<uint64_t>(WARPS_PER_CTA, ((uint64_t)atoll(ev) / WARPS_PER_CTA) * WARPS_PER_CTA);
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         uint64_t budget = (uint64_t)free_b + e->arena_total;
@@ -726,7 +745,15 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             CUDA_TRY(cudaMemsetAsync(e->d_ready, 0, 4, st));
             CUDA_TRY(cudaStreamSynchronize(st));  // offsets, order, zeroed queue are in place before anything overlaps
         }
-        apa_align_kernel<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
+        // register variant: 64 registers when the slots fit 8 CTAs per SM
+        int regs = slots <= (uint64_t)e->sm_count * 8 * WARPS_PER_CTA ? 64 : (slots <= (uint64_t)e->sm_count * 10 * WARPS_PER_CTA ? 48 : 40);
+        if (const char* ev = getenv("APA_REGS")) regs = atoi(ev);
+        if (regs >= 64)
+            apa_align_kernel_r64<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
+        else if (regs >= 48)
+            apa_align_kernel_r48<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
+        else
+            apa_align_kernel_r40<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
         b->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
         if (streaming) {

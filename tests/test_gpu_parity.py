@@ -132,6 +132,29 @@ def test_drop_in_c_program_gpu(apa, tmp_path):
     assert out.stdout.count(" ok") == 4
 
 
+def test_arena_overflow_retry_gpu(apa, oracle, monkeypatch):
+    # A deliberately tiny scratch arena: pairs overflow (ST_OVERFLOW) and are re-run with 4x arenas until they fit.
+    monkeypatch.setenv("APA_ARENA_BYTES", "65536")
+    pairs = [apa.generate_pair(n, 0.08, 0, 900 + n) for n in (200, 5000, 20000, 40000)]
+    for preset in PRESETS:
+        _check_pairs(apa, oracle, pairs, preset)
+    eng = apa._engine(0)
+    bt = eng.upload(*apa._concat(pairs))
+    bt.run(1, True)
+    assert bt.stats()["retries"] > 0
+    bt.free()
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_million_bp_pair_gpu(apa, oracle, preset):
+    # BASELINE configs[3]/[4] sizes (n = 1 000 000): cost against the oracle, CIGAR verified against the pair.
+    a, b = apa.generate_pair(1000000, 0.05 if preset == 0 else 0.15, 0, 77)
+    cost, cigar = apa.AstarPa2(preset, True).align(a, b)
+    assert oracle.cigar_verify(cigar, a, b) == cost
+    oc, ocg, _ = oracle.align(a, b, preset, True)
+    assert cost == oc and cigar == ocg
+
+
 def test_bad_input_gpu(apa):
     with pytest.raises(apa.AstarPaError):
         apa.AstarPa2(0, True).align_batch([(b"ACGT", b"ACGT"), (b"ACGN", b"ACGT")])
