@@ -102,6 +102,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def traffic_per_launch(args, computed_cells_gpu):
+    """DRAM bytes (read + write) of apa_align_kernel per launch, GB, scaled from the one `ncu --set full` capture of this
+    workload shape (profiles/r1_full_align_kernel_ncu_full.txt: 74.2 GB for 4736 pairs of n=100k, e=5 %, astarpa2_full,
+    i.e. 15.7 MB per pair against ~1.2 KB/pair of algorithmic bytes: scratch-arena data is re-read from DRAM because
+    thousands of concurrent pairs overflow the 126 MB L2). None for shapes that were not captured."""
+    if args.preset == "full" and args.n == 100000 and abs(args.e - 0.05) < 1e-9 and not args.no_trace:
+        return 74.234046 / 4736 * args.pairs
+    return None
+
+
 def make_batch(A, args, rank):
     seed0 = 31415 + rank * args.pairs  # 31415: the reference's fixed seed (pa-test/src/lib.rs:51)
     return A.generate_batch(args.pairs, args.n, args.e, 0, seed0)
@@ -266,7 +276,8 @@ def main():
         "computed_gcups": comp_all / (ms_step / 1e3) / 1e9, "aligned_bp_per_s": bp_all / (ms_step / 1e3),
         "pairs_per_s": args.pairs * world / (ms_step / 1e3), "wall_ms_per_step": wall_ms / args.steps,
         "passes_per_pair": st["passes"] / args.pairs, "retries": st["retries"],
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic_per_launch(args, comp_gpu), "traffic_unit": "GB per launch (dram read + write)",
                      "peak_source": peak_src, "kernel": "apa_align_kernel",
                      "note": "INT32-ALU bound kernel: 0.003 algorithmic B/cell; see int32_* fields",
                      "int32_ops_per_s": int_ops / (ms_step / 1e3), "int32_peak_ops_per_s": int_peak,
@@ -274,9 +285,10 @@ def main():
         "e2e": {"value": eff_all / (e2e_step / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": e2e_step},
         "gpu_launches": int(launches), "clocks": clocks,
-        "phase_cycles": dict(zip(["heuristic_build", "block_dp", "passes_total", "trace_total", "dt_trace", "cigar_text", "h_queries", "prune_update"],
-                                 [int(x) for x in st["phase_cycles"]])),
     }
+    if any(st["phase_cycles"]):  # only with a TIMERS=1 build
+        out["phase_cycles"] = dict(zip(["heuristic_build", "block_dp", "passes_total", "trace_total", "dt_trace", "cigar_text", "h_queries",
+                                        "prune_update"], [int(x) for x in st["phase_cycles"]]))
     if world == 1:
         out["cpu_baseline"] = cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, args.cpu_sample)
     print(json.dumps(out))
