@@ -132,6 +132,32 @@ def test_drop_in_c_program_gpu(apa, tmp_path):
     assert out.stdout.count(" ok") == 4
 
 
+@pytest.mark.parametrize("preset", PRESETS)
+def test_hard_shapes_gpu(apa, oracle, preset):
+    """Shapes the uniform generator does not produce: low-complexity / tandem-repeat sequences (many identical k-mers:
+    duplicate seeds per window, crowded diagonals), very unequal lengths, unrelated sequences, high divergence."""
+    rng = np.random.default_rng(11)
+
+    def rnd(n):
+        return bytes(rng.choice(list(b"ACGT"), size=n).astype(np.uint8))
+
+    pairs = [
+        (b"A" * 600, b"A" * 613),
+        (b"ACGT" * 200, b"ACGT" * 190 + b"AC"),
+        (b"ACGTTGCAAGTC" * 60, b"ACGTTGCAAGTC" * 61),          # period = k = 12: every seed identical
+        (b"AACCGGTT" * 90 + rnd(300), rnd(250) + b"AACCGGTT" * 95),
+        (rnd(3000), rnd(40)),
+        (rnd(25), rnd(2500)),
+        (rnd(4000), rnd(4100)),                                  # unrelated: distance ~ 0.53 n
+        (b"", rnd(300)),
+        (rnd(300), b""),
+        (b"ACGTACGTACG", b"ACGTACGTACG"),                        # n < k
+    ]
+    pairs += [apa.generate_pair(n, e, model, 4000 + n + model) for n, e, model in
+              [(6000, 0.3, 0), (6000, 0.5, 1), (9000, 0.3, 2), (12000, 0.2, 3), (20000, 0.25, 0)]]
+    _check_pairs(apa, oracle, pairs, preset)
+
+
 def test_arena_overflow_retry_gpu(apa, oracle, monkeypatch):
     # A deliberately tiny scratch arena: pairs overflow (ST_OVERFLOW) and are re-run with 4x arenas until they fit.
     monkeypatch.setenv("APA_ARENA_BYTES", "65536")
