@@ -61,6 +61,7 @@ struct BatchDev {
     unsigned long long* stats;  // [0] word_steps [1] computed_cells [2] passes [3] fill_blocks [4] dt_blocks [5..12] phase cycles
     int preset;
     int trace;
+    uint32_t q0;        // phase-split path: first work-order position of this wave (arena slot = q - q0)
     const volatile uint32_t* ready;  // streaming upload: number of pairs (in work order) whose bases are in HBM; nullptr = all
     int32_t* dbg;  // band log of the (single) pair, or nullptr
     uint32_t dbg_cap;
@@ -181,6 +182,148 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         atomicAdd(&bd.stats[4], acc_dt);
         for (int t = 0; t < 8; t++) atomicAdd(&bd.stats[5 + t], (unsigned long long)acc_t[t]);
     }
+}
+
+// ---- phase-split path ---------------------------------------------------------------------------------------------
+// The same per-pair work cut into three persistent kernels — (0) heuristic build, (1) band-doubling passes, (2) traceback
+// + CIGAR text — run back to back over a wave of pairs. Every pair of the wave owns an arena for the whole wave; the
+// warp-uniform state (PairCtx, GcshH, cost) is parked in the arena header between phases. Compared with the fused kernel
+// each phase kernel has a smaller instruction footprint (the fused one stalls on instruction fetch: 'no_instruction' is
+// the #3 stall reason in profiles/r1_full_final_n20k_ncu_full.txt) and fewer live registers.
+struct PairState {
+    PairCtx cx;
+    GcshH hh;
+    Cost cost;
+    Cost h0;
+};
+constexpr uint32_t ARENA_HEADER = 512;
+static_assert(sizeof(PairState) <= ARENA_HEADER, "PairState must fit the arena header");
+
+template <int PHASE>
+__device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* smem) {
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    WarpSmem& sm = smem[wib];
+    unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0;
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(bd.queue + 8 + PHASE, 1ull) + bd.q0;
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= bd.n_order) break;
+        if (PHASE <= 1 && bd.ready) {
+            if (lane == 0) {
+                while (*bd.ready <= (uint32_t)q) __nanosleep(500);
+            }
+            __syncwarp();
+        }
+        const uint32_t p = bd.order[q];
+        uint8_t* arena = bd.arena + (size_t)(q - bd.q0) * bd.arena_size;
+        PairState* ps = (PairState*)arena;
+        PairCtx cx;
+        if (PHASE == 0) {
+            cx.n = (I)(bd.a_off[p + 1] - bd.a_off[p]);
+            cx.m = (I)(bd.b_off[p + 1] - bd.b_off[p]);
+            cx.bprof = bd.bprof + bd.bp_off[p];
+            cx.aprof = bd.aprof + bd.ap_off[p];
+            cx.arena = arena;
+            cx.arena_size = bd.arena_size;
+            cx.nblk = (cx.n + BLOCK_W - 1) / BLOCK_W;
+            cx.nblk_alloc = 0;
+            cx.meta = (BlkMeta*)(arena + ARENA_HEADER);
+            uint32_t meta_bytes = ((uint32_t)(cx.nblk + 1) * (uint32_t)sizeof(BlkMeta) + 15u) & ~15u;
+            cx.v_base = ARENA_HEADER + meta_bytes;
+            cx.v_top = cx.v_base;
+            cx.hi_bot = bd.arena_size;
+            cx.status = ST_PENDING;
+            cx.word_steps = cx.computed_cells = 0;
+            cx.passes = 0;
+            cx.fill_blocks = cx.dt_blocks = 0;
+            for (int t = 0; t < 8; t++) cx.tphase[t] = 0;
+            cx.dbg = bd.dbg;
+            cx.dbg_cap = bd.dbg_cap;
+            cx.dbg_n = 0;
+            if (cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
+            GcshH hh;
+            if (cx.status == ST_PENDING && bd.preset == APA_PRESET_FULL) gcsh_build(cx, hh);
+            __syncwarp();
+            if (lane == 0) {
+                ps->cx = cx;
+                if (bd.preset == APA_PRESET_FULL) ps->hh = hh;
+                ps->cost = -1;
+            }
+            __syncwarp();
+            continue;
+        }
+        cx = ps->cx;
+        Cost cost = ps->cost;
+        if (PHASE == 1) {
+            if (cx.status == ST_PENDING) {
+                if (bd.preset == APA_PRESET_SIMPLE) {
+                    GapH hh{cx.n, cx.m};
+                    Cost h0 = hh.h(0, 0);
+                    cost = dev_band_doubling(cx, sm, hh, h0);
+                    if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
+                } else {
+                    GcshH hh = ps->hh;
+                    Cost h0 = hh.h(0, 0);
+                    cost = dev_band_doubling(cx, sm, hh, h0);
+                    if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ps->cx = cx;
+                ps->cost = cost;
+            }
+            __syncwarp();
+            if (bd.trace) continue;
+        }
+        // PHASE 2, or PHASE 1 of a cost-only run: finish the pair
+        long long cig_off = -1, cig_len = 0;
+        if (PHASE == 2 && cx.status == ST_PENDING && bd.trace) {
+            CigarWriter cw;
+            cw.arena = arena;
+            cw.arena_size = bd.arena_size;
+            cw.count = 0;
+            cw.pend_cnt = 0;
+            cw.pend_op = 0;
+            if (dev_trace(cx, sm, cw, cost)) {
+                cig_off = emit_cigar_text(cw, bd.pool, bd.pool_cursor, bd.pool_cap, &cig_len);
+                if (cig_off < 0) cx.status = ST_OVERFLOW;
+            }
+        }
+        if (lane == 0) {
+            bd.status[p] = cx.status == ST_PENDING ? ST_DONE : cx.status;
+            bd.cost[p] = cost;
+            bd.cig_off[p] = cig_off;
+            bd.cig_len[p] = cig_len;
+        }
+        if (bd.dbg_n && lane == 0) *bd.dbg_n = cx.dbg_n;
+        acc_steps += cx.word_steps;
+        acc_cells += cx.computed_cells;
+        acc_pass += cx.passes;
+        acc_fill += cx.fill_blocks;
+        acc_dt += cx.dt_blocks;
+    }
+    if (PHASE >= 1 && lane == 0) {
+        atomicAdd(&bd.stats[0], acc_steps);
+        atomicAdd(&bd.stats[1], acc_cells);
+        atomicAdd(&bd.stats[2], acc_pass);
+        atomicAdd(&bd.stats[3], acc_fill);
+        atomicAdd(&bd.stats[4], acc_dt);
+    }
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_phase_build_kernel(BatchDev bd) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    apa_phase_body<0>(bd, smem);
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_phase_pass_kernel(BatchDev bd) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    apa_phase_body<1>(bd, smem);
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_phase_trace_kernel(BatchDev bd) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    apa_phase_body<2>(bd, smem);
 }
 
 // Two register budgets of the same kernel: 64 registers (8 CTAs = 32 warps per SM, few spills) and 40 registers
@@ -336,6 +479,16 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     CUDA_TRY(cudaHostAlloc((void**)&eng->h_ready, 256 * sizeof(uint32_t), cudaHostAllocDefault));
     for (auto& ev : eng->ev) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMalloc(&eng->d_queue, 16 * sizeof(unsigned long long)));
+    {   // load every kernel now: lazy first-use loading must never happen while a persistent kernel is spinning
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_align_kernel_r64));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_align_kernel_r48));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_align_kernel_r40));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_build_kernel));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_kernel));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_trace_kernel));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_block_kernel));
+    }
     *out = eng;
     return APA_OK;
 }
@@ -652,7 +805,7 @@ static uint32_t estimate_arena(const apa_batch* b, int preset, int trace) {
     uint64_t vcols = nblk * (band_rows / 32 * 12 + 16);
     uint64_t tr = trace ? (DT_CACHE_ELEMS * 8 + 256 * (band_rows / 32) * 8 / 4 + (uint64_t)(b->max_n + b->max_m) / 4 * 4 + 65536) : 0;
     uint64_t heur = preset == APA_PRESET_FULL ? 24ull * (uint64_t)b->max_n + 65536 : 0;  // k-mer table, matches, contours
-    uint64_t s = meta + vcols + tr + heur + 16384;
+    uint64_t s = ARENA_HEADER + meta + vcols + tr + heur + 16384;
     s = (s + 1023) & ~1023ull;
     return (uint32_t)std::min<uint64_t>(s, 0xF0000000ull);
 }
@@ -721,9 +874,16 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         uint64_t budget = (uint64_t)free_b + e->arena_total;
         budget = budget > (4ull << 30) ? budget - (2ull << 30) : budget / 2;
-        while (slots > WARPS_PER_CTA && slots * (uint64_t)arena_size > budget) slots = (slots / 2 / WARPS_PER_CTA) * WARPS_PER_CTA;
-        if (slots * (uint64_t)arena_size > budget) return set_err(APA_ERR_TOO_LARGE, "scratch arena exceeds device memory");
-        size_t need = (size_t)slots * arena_size;
+        // Phase-split path: every pair of the batch keeps its own arena across the three phase kernels. Used when those
+        // arenas fit in HBM (10 000 pairs x 3 MB = 30 GB of 180 GB); otherwise the fused kernel with per-warp arenas runs.
+        bool split = n_work * (uint64_t)arena_size <= budget;
+        if (const char* ev = getenv("APA_SPLIT")) split = split && atoi(ev) != 0;
+        const uint64_t n_arenas = split ? n_work : slots;
+        if (!split) {
+            while (slots > WARPS_PER_CTA && slots * (uint64_t)arena_size > budget) slots = (slots / 2 / WARPS_PER_CTA) * WARPS_PER_CTA;
+            if (slots * (uint64_t)arena_size > budget) return set_err(APA_ERR_TOO_LARGE, "scratch arena exceeds device memory");
+        }
+        size_t need = (size_t)(split ? n_arenas : slots) * arena_size;
         if (e->arena_total < need) {
             if (e->d_arena) CUDA_TRY(cudaFree(e->d_arena));
             e->d_arena = nullptr;
@@ -748,7 +908,23 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         // register variant: 64 registers when the slots fit 8 CTAs per SM
         int regs = slots <= (uint64_t)e->sm_count * 8 * WARPS_PER_CTA ? 64 : (slots <= (uint64_t)e->sm_count * 10 * WARPS_PER_CTA ? 48 : 40);
         if (const char* ev = getenv("APA_REGS")) regs = atoi(ev);
-        if (regs >= 64)
+        bd.q0 = 0;
+        if (split) {
+            CUDA_TRY(cudaMemsetAsync(e->d_queue + 8, 0, 3 * sizeof(unsigned long long), st));
+            const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
+            apa_phase_build_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+            // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
+            // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
+            // done, so the pass / trace kernels are launched after upload_planes() below.
+            if (!streaming) {
+                apa_phase_pass_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                b->stats.kernel_launches++;
+                if (trace) {
+                    apa_phase_trace_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                    b->stats.kernel_launches++;
+                }
+            }
+        } else if (regs >= 64)
             apa_align_kernel_r64<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
         else if (regs >= 48)
             apa_align_kernel_r48<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
@@ -766,6 +942,16 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 cudaStreamSynchronize(e->copy_stream);
                 cudaStreamSynchronize(st);
                 return rc;
+            }
+            if (split) {
+                const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
+                apa_phase_pass_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                b->stats.kernel_launches++;
+                if (trace) {
+                    apa_phase_trace_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                    b->stats.kernel_launches++;
+                }
+                CUDA_TRY(cudaGetLastError());
             }
         }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
