@@ -380,6 +380,7 @@ struct apa_engine {
     uint32_t* h_stage = nullptr;  // pinned staging for the packed planes (grow-only)
     size_t h_stage_cap = 0;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t evp[4] = {};  // phase-split path: before build | after build | after passes | after trace
     // Device-buffer cache: cudaMalloc/cudaFree of multi-GB buffers costs milliseconds each and synchronises the device,
     // so buffers released by a batch are kept for the next one (grow-only, per engine).
     std::unordered_map<void*, size_t> live;
@@ -478,6 +479,7 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     CUDA_TRY(cudaMalloc(&eng->d_ready, 64));
     CUDA_TRY(cudaHostAlloc((void**)&eng->h_ready, 256 * sizeof(uint32_t), cudaHostAllocDefault));
     for (auto& ev : eng->ev) CUDA_TRY(cudaEventCreate(&ev));
+    for (auto& ev : eng->evp) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMalloc(&eng->d_queue, 16 * sizeof(unsigned long long)));
     {   // load every kernel now: lazy first-use loading must never happen while a persistent kernel is spinning
         cudaFuncAttributes fa;
@@ -501,6 +503,8 @@ extern "C" void apa_engine_destroy(apa_engine* e) {
     if (e->d_arena) cudaFree(e->d_arena);
     if (e->d_queue) cudaFree(e->d_queue);
     for (auto& ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->evp)
         if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -818,6 +822,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     b->trace = trace;
     b->stats.kernel_launches = 0;
     b->stats.retries = 0;
+    b->stats.phase_ms[0] = b->stats.phase_ms[1] = b->stats.phase_ms[2] = 0;
     if (b->n_pairs == 0) {
         b->ran = true;
         return APA_OK;
@@ -909,21 +914,29 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         int regs = slots <= (uint64_t)e->sm_count * 8 * WARPS_PER_CTA ? 64 : (slots <= (uint64_t)e->sm_count * 10 * WARPS_PER_CTA ? 48 : 40);
         if (const char* ev = getenv("APA_REGS")) regs = atoi(ev);
         bd.q0 = 0;
+        const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
+        // pass + trace kernels of the phase-split path, with the per-phase events (stats.phase_ms)
+        auto launch_pass_trace = [&]() -> cudaError_t {
+            apa_phase_pass_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+            b->stats.kernel_launches++;
+            cudaError_t ce = cudaEventRecord(e->evp[2], st);
+            if (ce != cudaSuccess) return ce;
+            if (trace) {
+                apa_phase_trace_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                b->stats.kernel_launches++;
+            }
+            ce = cudaEventRecord(e->evp[3], st);
+            return ce != cudaSuccess ? ce : cudaGetLastError();
+        };
         if (split) {
             CUDA_TRY(cudaMemsetAsync(e->d_queue + 8, 0, 3 * sizeof(unsigned long long), st));
-            const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
+            CUDA_TRY(cudaEventRecord(e->evp[0], st));
             apa_phase_build_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+            CUDA_TRY(cudaEventRecord(e->evp[1], st));
             // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
             // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
             // done, so the pass / trace kernels are launched after upload_planes() below.
-            if (!streaming) {
-                apa_phase_pass_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
-                b->stats.kernel_launches++;
-                if (trace) {
-                    apa_phase_trace_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
-                    b->stats.kernel_launches++;
-                }
-            }
+            if (!streaming) CUDA_TRY(launch_pass_trace());
         } else if (regs >= 64)
             apa_align_kernel_r64<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
         else if (regs >= 48)
@@ -943,19 +956,17 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 cudaStreamSynchronize(st);
                 return rc;
             }
-            if (split) {
-                const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
-                apa_phase_pass_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
-                b->stats.kernel_launches++;
-                if (trace) {
-                    apa_phase_trace_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
-                    b->stats.kernel_launches++;
-                }
-                CUDA_TRY(cudaGetLastError());
-            }
+            if (split) CUDA_TRY(launch_pass_trace());
         }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        if (split) {
+            for (int k = 0; k < 3; k++) {
+                float pms = 0;
+                CUDA_TRY(cudaEventElapsedTime(&pms, e->evp[k], e->evp[k + 1]));
+                b->stats.phase_ms[k] += pms;
+            }
+        }
         pending.clear();
         for (uint64_t p = 0; p < b->n_pairs; p++)
             if (b->h_status[p] == ST_OVERFLOW) pending.push_back((uint32_t)p);

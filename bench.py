@@ -10,9 +10,10 @@ n = 100 000, e = 5 %, with CIGAR traceback; --pairs pairs per GPU, weak scaling)
             engine's stream around the kernels of each step).
 `e2e`     : the same metric through the public C-ABI batch call with HOST (pinned) buffers: H2D of the sequences,
             kernels, D2H of costs + CIGAR text, every step.
-`roofline`: dominant kernel = apa_align_kernel (block DP + traceback). HBM: algorithmic bytes = 48 B per
-            64-row x 256-col lane-block x lane-blocks computed / kernel time vs the measured copy
-            peak; the kernel is INT32-ALU bound, so the int32 fraction is reported next to it.
+`roofline`: dominant kernel = the longest of the three phase kernels (build / pass / trace), each timed with CUDA
+            events on the engine's stream. HBM: algorithmic bytes of that kernel (block DP: 48 B per 64-row x
+            256-col lane-block) / its launch duration vs the measured copy peak; the path is integer and
+            latency bound, so the INT32-pipe fraction of the block DP is reported next to it.
 Inputs (2 GB at the default size) are larger than the 126 MB L2, so no explicit flush between iterations.
 """
 import argparse
@@ -102,13 +103,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def traffic_per_launch(args, computed_cells_gpu):
-    """DRAM bytes (read + write) of apa_align_kernel per launch, GB, scaled from the one `ncu --set full` capture of this
-    workload shape (profiles/r1_full_align_kernel_ncu_full.txt: 74.2 GB for 4736 pairs of n=100k, e=5 %, astarpa2_full,
-    i.e. 15.7 MB per pair against ~1.2 KB/pair of algorithmic bytes: scratch-arena data is re-read from DRAM because
-    thousands of concurrent pairs overflow the 126 MB L2). None for shapes that were not captured."""
+KERNELS = ["apa_phase_build_kernel", "apa_phase_pass_kernel", "apa_phase_trace_kernel"]
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from the `ncu --set full` captures of the headline
+# shape (astarpa2_full, n=100k, e=5 %, cost+CIGAR), in MB PER PAIR; scaled by the pairs of a launch. Source files are
+# named next to each figure. None for shapes that were not captured.
+NCU_TRAFFIC_MB_PER_PAIR = {}
+
+
+def traffic_per_launch(args, kernel):
+    """Measured DRAM traffic of `kernel` per launch in GB (from the committed ncu capture), or None."""
     if args.preset == "full" and args.n == 100000 and abs(args.e - 0.05) < 1e-9 and not args.no_trace:
-        return 74.234046 / 4736 * args.pairs
+        mb = NCU_TRAFFIC_MB_PER_PAIR.get(kernel)
+        return None if mb is None else mb * args.pairs / 1e3
     return None
 
 
@@ -214,11 +220,13 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     kernel_ms, launches, st = 0.0, 0, None
+    phase_ms = np.zeros(3)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         batch.run(preset_id, trace)  # synchronises its stream; kernel_ms is CUDA-event time on that stream
         st = batch.stats()
         kernel_ms += st["kernel_ms"]
+        phase_ms += np.array(st["phase_ms"])  # CUDA events around each phase kernel, on the engine's stream
         launches += st["kernel_launches"]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -244,8 +252,9 @@ def main():
     e2e_step = float(np.mean(e2e_ms)) if e2e_ms else float('nan')
 
     # ---- reduce over ranks: max time, sum of work
-    agg = np.array([ms_step, e2e_step], dtype=np.float64)
-    work = np.array([eff_cells, float(st["computed_cells"]), total_bp, float(st["dp_word_steps"])], dtype=np.float64)
+    agg = np.array([ms_step, e2e_step, *(phase_ms / args.steps)], dtype=np.float64)
+    work = np.array([eff_cells, float(st["computed_cells"]), total_bp, float(st["dp_word_steps"]), float(a_off[-1] + b_off[-1])],
+                    dtype=np.float64)
     if dist is not None:
         import torch
         t_agg = torch.tensor(agg, device="cuda")
@@ -258,17 +267,30 @@ def main():
             dist.destroy_process_group()
         return
     ms_step, e2e_step = float(agg[0]), float(agg[1])
-    eff_all, comp_all, bp_all, wsteps_all = work
+    k_ms = [float(x) for x in agg[2:5]]
+    eff_all, comp_all, bp_all, wsteps_all, bases_all = work
     value = eff_all / (ms_step / 1e3) / 1e9
     hbm_peak, peak_src, sm_max = peaks()
-    # algorithmic HBM bytes: 48 B per (64 rows x 256 cols) lane-block = computed_cells * 48 / 16384 (per GPU, per launch)
     comp_gpu = comp_all / world
-    alg_bytes = comp_gpu * 48.0 / 16384.0
-    achieved = alg_bytes / (ms_step / 1e3) / 1e9
-    # int32 ALU view: ~17 ALU-pipe instructions per 32-row word step; pipe peak = 148 SMs x 64 lanes/clk (B300_MICROARCH: rt_SMSP = 2)
     sm_mhz = clocks.get("sm_mhz") or sm_max
+    # Dominant kernel = the longest of the three phase kernels (CUDA events around each launch, live in this run).
+    # Algorithmic HBM bytes per launch:
+    #   pass kernel  (K1 block DP): 48 B per (64 rows x 256 cols) lane-block = computed_cells * 48 / 16384
+    #   build kernel (K2 GCSH)    : 0.7 B per base pair of input (2-bit planes of a and b, seed table, matches)
+    #   trace kernel (K3)         : 2 B per base of a (DT records + V columns re-read) + the CIGAR text written
+    alg = {KERNELS[0]: 0.7 * bases_all / world / 2, KERNELS[1]: comp_gpu * 48.0 / 16384.0,
+           KERNELS[2]: 2.0 * bp_all / world + (d2h_bytes if trace else 0)}
+    if sum(k_ms) <= 0:  # fused single-kernel path (arenas of the whole batch did not fit in HBM)
+        dom, dom_ms = "apa_align_kernel", ms_step
+        alg[dom] = sum(alg.values())
+    else:
+        dom = KERNELS[int(np.argmax(k_ms))]
+        dom_ms = max(k_ms)
+    achieved = alg[dom] / (dom_ms / 1e3) / 1e9
+    # int32 ALU view of the block DP: ~17 ALU-pipe instructions per 32-row word step; pipe peak = 148 SMs x 64 lanes/clk
     int_ops = (wsteps_all / world) * 17.0
     int_peak = 148 * 64 * sm_mhz * 1e6
+    pass_ms = k_ms[1] if k_ms[1] > 0 else ms_step
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-vectors (i32 costs)",
@@ -276,12 +298,15 @@ def main():
         "computed_gcups": comp_all / (ms_step / 1e3) / 1e9, "aligned_bp_per_s": bp_all / (ms_step / 1e3),
         "pairs_per_s": args.pairs * world / (ms_step / 1e3), "wall_ms_per_step": wall_ms / args.steps,
         "passes_per_pair": st["passes"] / args.pairs, "retries": st["retries"],
+        "kernels": [{"name": k, "ms_per_launch": t, "share_of_step": t / ms_step if ms_step else None,
+                     "algorithmic_gb_per_launch": alg[k] / 1e9} for k, t in zip(KERNELS, k_ms)],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic_per_launch(args, comp_gpu), "traffic_unit": "GB per launch (dram read + write)",
-                     "peak_source": peak_src, "kernel": "apa_align_kernel",
-                     "note": "INT32-ALU bound kernel: 0.003 algorithmic B/cell; see int32_* fields",
-                     "int32_ops_per_s": int_ops / (ms_step / 1e3), "int32_peak_ops_per_s": int_peak,
-                     "int32_frac": int_ops / (ms_step / 1e3) / int_peak},
+                     "traffic": traffic_per_launch(args, dom), "traffic_unit": "GB per launch (dram read + write)",
+                     "peak_source": peak_src, "kernel": dom, "kernel_ms_per_launch": dom_ms,
+                     "note": "integer/latency-bound path: ~0.003 algorithmic B/cell in the block DP; the INT32-pipe view of the "
+                             "block DP (apa_phase_pass_kernel) is in the int32_* fields",
+                     "int32_ops_per_s": int_ops / (pass_ms / 1e3), "int32_peak_ops_per_s": int_peak,
+                     "int32_frac": int_ops / (pass_ms / 1e3) / int_peak},
         "e2e": {"value": eff_all / (e2e_step / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": e2e_step},
         "gpu_launches": int(launches), "clocks": clocks,

@@ -1,0 +1,201 @@
+// C++ host mirror of the reference's Rust API for the A*PA2 path, header-only, over the C-ABI of libastarpa_c.so
+// (include/astarpa_b200.h). The image has no Rust toolchain, so this is the compiled-language host layer a C++
+// caller (and tools/pa_bin.cpp) uses instead of the Rust crates:
+//
+//   astarpa2::AstarPa2::simple(trace) / ::full(trace)   AstarPa2Params::{simple,full}().make_aligner(trace)
+//                                                        astarpa2/src/params.rs:70-132
+//   AstarPa2::align(a, b) -> (Cost, optional<Cigar>)    pa_types::Aligner::align as implemented at
+//                                                        astarpa2/src/lib.rs:210-215 (CIGAR iff trace)
+//   AstarPa2::cost(a, b)                                 AstarPa2::cost, astarpa2/src/lib.rs:177-179
+//   astarpa2::astarpa2_simple / astarpa2_full            astarpa2/src/lib.rs:44-53
+//   AstarPa2::align_batch(pairs)                         no reference counterpart: one call carries a whole batch
+//                                                        to the GPU (SURVEY 8b "needed extension")
+//   Cigar::{to_string, parse, verify}                    pa_types::Cigar (external crate; text format pinned by
+//                                                        astarpa-c/example.cpp:16: "=I4=X=", count omitted when 1)
+//
+// Errors: the reference panics (invalid bases, internal assertions); here every failure throws astarpa2::Error
+// carrying apa_last_error(). There is no CPU fallback: without a usable B200 the constructor throws.
+#pragma once
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <utility>
+#include <vector>
+
+#include "astarpa_b200.h"
+
+namespace astarpa2 {
+
+using Cost = int32_t;               // pa_types::Cost
+using Seq = std::string_view;       // pa_types::Seq = &[u8]; bytes over ACGT
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+enum class CigarOp : uint8_t { Match = '=', Sub = 'X', Del = 'D', Ins = 'I' };
+struct CigarElem {
+    CigarOp op;
+    uint32_t cnt;
+    bool operator==(const CigarElem& o) const { return op == o.op && cnt == o.cnt; }
+};
+
+// Run-length CIGAR. I consumes a base of b, D a base of a (astarpa2/src/blocks/trace.rs:176-204).
+struct Cigar {
+    std::vector<CigarElem> ops;
+
+    std::string to_string() const {
+        std::string s;
+        for (const auto& e : ops) {
+            if (e.cnt != 1) s += std::to_string(e.cnt);
+            s += (char)e.op;
+        }
+        return s;
+    }
+    static Cigar parse(std::string_view text) {
+        Cigar c;
+        uint64_t cnt = 0;
+        bool have = false;
+        for (char ch : text) {
+            if (ch >= '0' && ch <= '9') {
+                cnt = cnt * 10 + (uint64_t)(ch - '0');
+                have = true;
+                if (cnt > 0x3fffffffu) throw Error(APA_ERR_BAD_INPUT, "CIGAR count too large");
+            } else if (ch == '=' || ch == 'X' || ch == 'D' || ch == 'I') {
+                if (have && cnt == 0) throw Error(APA_ERR_BAD_INPUT, "CIGAR element with count 0");
+                c.ops.push_back(CigarElem{(CigarOp)ch, have ? (uint32_t)cnt : 1u});
+                cnt = 0;
+                have = false;
+            } else {
+                throw Error(APA_ERR_BAD_INPUT, std::string("unexpected character in CIGAR: ") + ch);
+            }
+        }
+        if (have) throw Error(APA_ERR_BAD_INPUT, "CIGAR ends with a count");
+        return c;
+    }
+    // Cigar::verify: walks the path over (a, b); returns its unit cost, or -1 if it is not a valid alignment of a and b.
+    int64_t verify(Seq a, Seq b) const {
+        size_t i = 0, j = 0;
+        int64_t cost = 0;
+        for (const auto& e : ops) {
+            for (uint32_t t = 0; t < e.cnt; t++) {
+                switch (e.op) {
+                    case CigarOp::Match:
+                        if (i >= a.size() || j >= b.size() || a[i] != b[j]) return -1;
+                        i++, j++;
+                        break;
+                    case CigarOp::Sub:
+                        if (i >= a.size() || j >= b.size() || a[i] == b[j]) return -1;
+                        i++, j++, cost++;
+                        break;
+                    case CigarOp::Del:
+                        if (i >= a.size()) return -1;
+                        i++, cost++;
+                        break;
+                    case CigarOp::Ins:
+                        if (j >= b.size()) return -1;
+                        j++, cost++;
+                        break;
+                }
+            }
+        }
+        return (i == a.size() && j == b.size()) ? cost : -1;
+    }
+};
+
+using Alignment = std::pair<Cost, std::optional<Cigar>>;
+
+struct BatchResult {
+    std::vector<Cost> costs;
+    std::vector<std::string> cigars;  // CIGAR text per pair; empty vector when trace == false
+    apa_batch_stats stats{};
+};
+
+class AstarPa2 {
+  public:
+    enum Preset { Simple = APA_PRESET_SIMPLE, Full = APA_PRESET_FULL };
+
+    AstarPa2(Preset preset, bool trace, int device = 0) : preset_(preset), trace_(trace) {
+        int rc = apa_engine_create(device, &engine_);
+        if (rc != APA_OK) throw Error(rc, std::string("apa_engine_create: ") + apa_last_error());
+    }
+    static AstarPa2 simple(bool trace = true, int device = 0) { return AstarPa2(Simple, trace, device); }
+    static AstarPa2 full(bool trace = true, int device = 0) { return AstarPa2(Full, trace, device); }
+    AstarPa2(const AstarPa2&) = delete;
+    AstarPa2& operator=(const AstarPa2&) = delete;
+    AstarPa2(AstarPa2&& o) noexcept : engine_(o.engine_), preset_(o.preset_), trace_(o.trace_) { o.engine_ = nullptr; }
+    ~AstarPa2() {
+        if (engine_) apa_engine_destroy(engine_);
+    }
+
+    bool trace() const { return trace_; }
+    Preset preset() const { return preset_; }
+
+    // Aligner::align (astarpa2/src/lib.rs:210-215)
+    Alignment align(Seq a, Seq b) {
+        const std::pair<Seq, Seq> one[1] = {{a, b}};
+        BatchResult r = align_batch(one, 1, trace_);
+        if (!trace_) return {r.costs[0], std::nullopt};
+        return {r.costs[0], Cigar::parse(r.cigars[0])};
+    }
+    // AstarPa2::cost (astarpa2/src/lib.rs:177-179)
+    Cost cost(Seq a, Seq b) {
+        const std::pair<Seq, Seq> one[1] = {{a, b}};
+        return align_batch(one, 1, false).costs[0];
+    }
+    BatchResult align_batch(const std::vector<std::pair<Seq, Seq>>& pairs) { return align_batch(pairs.data(), pairs.size(), trace_); }
+
+    // Concatenated form (what the C-ABI takes): pair p is a_all[a_off[p] .. a_off[p+1]) vs b_all[b_off[p] .. b_off[p+1]).
+    BatchResult align_batch_concat(const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all, const int64_t* b_off, size_t n,
+                                   bool trace) {
+        BatchResult r;
+        std::vector<int64_t> costs(n ? n : 1), off(n ? n : 1), len(n ? n : 1);
+        char* pool = nullptr;
+        int rc = apa_align_batch(engine_, (int)preset_, trace ? 1 : 0, n, a_all, a_off, b_all, b_off, costs.data(), &pool, off.data(),
+                                 len.data(), &r.stats);
+        if (rc != APA_OK) throw Error(rc, std::string("apa_align_batch: ") + apa_last_error());
+        r.costs.resize(n);
+        for (size_t p = 0; p < n; p++) r.costs[p] = (Cost)costs[p];
+        if (trace && pool) {
+            r.cigars.resize(n);
+            for (size_t p = 0; p < n; p++) r.cigars[p].assign(pool + off[p], (size_t)len[p]);
+        }
+        apa_free(pool);
+        return r;
+    }
+
+  private:
+    BatchResult align_batch(const std::pair<Seq, Seq>* pairs, size_t n, bool trace) {
+        std::string a_all, b_all;
+        std::vector<int64_t> a_off(n + 1, 0), b_off(n + 1, 0);
+        size_t ta = 0, tb = 0;
+        for (size_t p = 0; p < n; p++) ta += pairs[p].first.size(), tb += pairs[p].second.size();
+        a_all.reserve(ta);
+        b_all.reserve(tb);
+        for (size_t p = 0; p < n; p++) {
+            a_all.append(pairs[p].first);
+            b_all.append(pairs[p].second);
+            a_off[p + 1] = (int64_t)a_all.size();
+            b_off[p + 1] = (int64_t)b_all.size();
+        }
+        return align_batch_concat((const uint8_t*)a_all.data(), a_off.data(), (const uint8_t*)b_all.data(), b_off.data(), n, trace);
+    }
+    apa_engine* engine_ = nullptr;
+    Preset preset_;
+    bool trace_;
+};
+
+// astarpa2::astarpa2_simple / astarpa2_full (astarpa2/src/lib.rs:44-53): a fresh aligner per call, with trace.
+inline std::pair<Cost, Cigar> astarpa2_simple(Seq a, Seq b) {
+    auto r = AstarPa2::simple(true).align(a, b);
+    return {r.first, std::move(*r.second)};
+}
+inline std::pair<Cost, Cigar> astarpa2_full(Seq a, Seq b) {
+    auto r = AstarPa2::full(true).align(a, b);
+    return {r.first, std::move(*r.second)};
+}
+
+}  // namespace astarpa2

@@ -48,6 +48,10 @@ typedef struct apa_batch_stats {
     /* SM-clock cycles summed over warps: [0] heuristic build [1] block DP [2] passes total [3] traceback total
      * [4] DT-trace [5] CIGAR text [6] h() queries [7] match pruning + contour rebuilds */
     uint64_t phase_cycles[8];
+    /* CUDA-event durations of the three phase kernels of the last run: [0] apa_phase_build_kernel (GCSH build)
+     * [1] apa_phase_pass_kernel (band doubling + block DP) [2] apa_phase_trace_kernel (traceback + CIGAR text).
+     * All zero when the fused single-kernel path ran (arenas of the whole batch did not fit in HBM). */
+    double phase_ms[3];
 } apa_batch_stats;
 
 const char* apa_last_error(void);
