@@ -81,7 +81,7 @@ __device__ __forceinline__ BlkView view_of(const PairCtx& cx, const BlkMeta& mt)
 struct GapH {
     I n, m;
     static constexpr bool PRUNE = false;
-    __device__ __forceinline__ Cost h(I i, I j) const {
+    __device__ __forceinline__ Cost h(I i, I j, int = 0) const {
         I d = (n - i) - (m - j);
         return d < 0 ? -d : d;
     }
@@ -143,12 +143,12 @@ __device__ JRange dev_fixed_j_range(const PairCtx& cx, Hh& hh, I i, Cost f_max, 
     I start = prev_fixed.s;
     I end = min(orig_e, cx.m);
     while (start <= end) {
-        Cost f = blk_index(blk, start) + hh.h(i, start);
+        Cost f = blk_index(blk, start) + hh.h(i, start, 1);
         if (f <= f_max) break;
         start += div_ceil_pos(f - f_max, 2);
     }
     while (end >= start) {
-        Cost f = blk_index(blk, end) + hh.h(i, end);
+        Cost f = blk_index(blk, end) + hh.h(i, end, 2);
         if (f <= f_max) break;
         end -= div_ceil_pos(f - f_max, 2);
     }

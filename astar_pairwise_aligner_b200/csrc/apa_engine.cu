@@ -207,7 +207,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
     unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0;
     for (;;) {
         unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(bd.queue + 8 + PHASE, 1ull) + bd.q0;
+        if (lane == 0) q = atomicAdd(bd.queue + 16 + PHASE, 1ull) + bd.q0;
         q = __shfl_sync(FULL, q, 0);
         if (q >= bd.n_order) break;
         if (PHASE <= 1 && bd.ready) {
@@ -313,17 +313,34 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
         atomicAdd(&bd.stats[4], acc_dt);
     }
 }
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_phase_build_kernel(BatchDev bd) {
-    __shared__ WarpSmem smem[WARPS_PER_CTA];
-    apa_phase_body<0>(bd, smem);
+// Each phase kernel exists in three register budgets (CTAs of 128 threads: 10 / 9 / 8 per SM = 48 / 56 / 64 registers);
+// the host picks per phase (APA_BUILD_REGS / APA_PASS_REGS / APA_TRACE_REGS override the defaults).
+#define APA_PHASE_KERNEL(NAME, PHASE, MINB)                                                     \
+    __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) NAME(BatchDev bd) {             \
+        __shared__ WarpSmem smem[WARPS_PER_CTA];                                                \
+        apa_phase_body<PHASE>(bd, smem);                                                        \
+    }
+APA_PHASE_KERNEL(apa_phase_build_kernel, 0, 10)
+APA_PHASE_KERNEL(apa_phase_build_kernel_r56, 0, 9)
+APA_PHASE_KERNEL(apa_phase_build_kernel_r64, 0, 8)
+APA_PHASE_KERNEL(apa_phase_pass_kernel, 1, 10)
+APA_PHASE_KERNEL(apa_phase_pass_kernel_r56, 1, 9)
+APA_PHASE_KERNEL(apa_phase_pass_kernel_r64, 1, 8)
+APA_PHASE_KERNEL(apa_phase_trace_kernel, 2, 10)
+APA_PHASE_KERNEL(apa_phase_trace_kernel_r56, 2, 9)
+APA_PHASE_KERNEL(apa_phase_trace_kernel_r64, 2, 8)
+typedef void (*phase_kernel_t)(BatchDev);
+static phase_kernel_t phase_kernel(int phase, int regs) {
+    static const phase_kernel_t tab[3][3] = {{apa_phase_build_kernel, apa_phase_build_kernel_r56, apa_phase_build_kernel_r64},
+                                             {apa_phase_pass_kernel, apa_phase_pass_kernel_r56, apa_phase_pass_kernel_r64},
+                                             {apa_phase_trace_kernel, apa_phase_trace_kernel_r56, apa_phase_trace_kernel_r64}};
+    return tab[phase][regs >= 64 ? 2 : (regs >= 56 ? 1 : 0)];
 }
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_phase_pass_kernel(BatchDev bd) {
-    __shared__ WarpSmem smem[WARPS_PER_CTA];
-    apa_phase_body<1>(bd, smem);
-}
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_phase_trace_kernel(BatchDev bd) {
-    __shared__ WarpSmem smem[WARPS_PER_CTA];
-    apa_phase_body<2>(bd, smem);
+static int phase_regs(int phase) {  // default register budget per phase, overridable for experiments
+    static const char* names[3] = {"APA_BUILD_REGS", "APA_PASS_REGS", "APA_TRACE_REGS"};
+    static const int defaults[3] = {48, 48, 48};
+    const char* ev = getenv(names[phase]);
+    return ev ? atoi(ev) : defaults[phase];
 }
 
 // Two register budgets of the same kernel: 64 registers (8 CTAs = 32 warps per SM, few spills) and 40 registers
@@ -385,7 +402,7 @@ struct apa_engine {
     // so buffers released by a batch are kept for the next one (grow-only, per engine).
     std::unordered_map<void*, size_t> live;
     std::vector<std::pair<void*, size_t>> free_blocks;
-    unsigned long long* d_queue = nullptr;   // [0] queue head, [1] pool cursor, [2..] stats
+    unsigned long long* d_queue = nullptr;   // [0] queue head, [1] pool cursor, [2..14] stats, [16..18] phase-kernel queue heads
     uint8_t* d_arena = nullptr;
     size_t arena_total = 0;
 };
@@ -480,15 +497,14 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     CUDA_TRY(cudaHostAlloc((void**)&eng->h_ready, 256 * sizeof(uint32_t), cudaHostAllocDefault));
     for (auto& ev : eng->ev) CUDA_TRY(cudaEventCreate(&ev));
     for (auto& ev : eng->evp) CUDA_TRY(cudaEventCreate(&ev));
-    CUDA_TRY(cudaMalloc(&eng->d_queue, 16 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&eng->d_queue, 32 * sizeof(unsigned long long)));
     {   // load every kernel now: lazy first-use loading must never happen while a persistent kernel is spinning
         cudaFuncAttributes fa;
         CUDA_TRY(cudaFuncGetAttributes(&fa, apa_align_kernel_r64));
         CUDA_TRY(cudaFuncGetAttributes(&fa, apa_align_kernel_r48));
         CUDA_TRY(cudaFuncGetAttributes(&fa, apa_align_kernel_r40));
-        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_build_kernel));
-        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_kernel));
-        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_trace_kernel));
+        for (int ph = 0; ph < 3; ph++)
+            for (int regs = 48; regs <= 64; regs += 8) CUDA_TRY(cudaFuncGetAttributes(&fa, phase_kernel(ph, regs)));
         CUDA_TRY(cudaFuncGetAttributes(&fa, apa_block_kernel));
     }
     *out = eng;
@@ -861,7 +877,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     bd.dbg_n = b->d_dbg_n;
 
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
-    CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, 16 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, 32 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(b->d_status, 0, b->n_pairs * 4, st));
     uint32_t arena_size = estimate_arena(b, preset, trace);
     if (const char* ev = getenv("APA_ARENA_BYTES")) arena_size = (uint32_t)std::max<long long>(65536, atoll(ev));  // tests: force the overflow/retry path
@@ -875,19 +891,30 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         uint64_t slots = ((n_work + WARPS_PER_CTA - 1) / WARPS_PER_CTA) * WARPS_PER_CTA;
         slots = std::min<uint64_t>(slots, max_slots);
         if (const char* ev = getenv("APA_SLOTS")) slots = std::max<uint64_t>(WARPS_PER_CTA, ((uint64_t)atoll(ev) / WARPS_PER_CTA) * WARPS_PER_CTA);
-        size_t free_b = 0, total_b = 0;
-        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        uint64_t budget = (uint64_t)free_b + e->arena_total;
-        budget = budget > (4ull << 30) ? budget - (2ull << 30) : budget / 2;
         // Phase-split path: every pair of the batch keeps its own arena across the three phase kernels. Used when those
         // arenas fit in HBM (10 000 pairs x 3 MB = 30 GB of 180 GB); otherwise the fused kernel with per-warp arenas runs.
-        bool split = n_work * (uint64_t)arena_size <= budget;
-        if (const char* ev = getenv("APA_SPLIT")) split = split && atoi(ev) != 0;
-        const uint64_t n_arenas = split ? n_work : slots;
+        // cudaMemGetInfo costs 1-30 ms with tens of GB allocated, so it is only asked when the arena has to grow.
+        uint64_t budget = 0;  // bytes the arena may take; queried lazily
+        auto query_budget = [&]() -> cudaError_t {
+            if (budget) return cudaSuccess;
+            size_t free_b = 0, total_b = 0;
+            cudaError_t ce = cudaMemGetInfo(&free_b, &total_b);
+            budget = (uint64_t)free_b + e->arena_total;
+            budget = budget > (4ull << 30) ? budget - (2ull << 30) : std::max<uint64_t>(budget / 2, 1);
+            return ce;
+        };
+        bool split = n_work * (uint64_t)arena_size <= e->arena_total;
         if (!split) {
+            CUDA_TRY(query_budget());
+            split = n_work * (uint64_t)arena_size <= budget;
+        }
+        if (const char* ev = getenv("APA_SPLIT")) split = split && atoi(ev) != 0;
+        if (!split && slots * (uint64_t)arena_size > e->arena_total) {
+            CUDA_TRY(query_budget());
             while (slots > WARPS_PER_CTA && slots * (uint64_t)arena_size > budget) slots = (slots / 2 / WARPS_PER_CTA) * WARPS_PER_CTA;
             if (slots * (uint64_t)arena_size > budget) return set_err(APA_ERR_TOO_LARGE, "scratch arena exceeds device memory");
         }
+        const uint64_t n_arenas = split ? n_work : slots;
         size_t need = (size_t)(split ? n_arenas : slots) * arena_size;
         if (e->arena_total < need) {
             if (e->d_arena) CUDA_TRY(cudaFree(e->d_arena));
@@ -917,21 +944,21 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
         // pass + trace kernels of the phase-split path, with the per-phase events (stats.phase_ms)
         auto launch_pass_trace = [&]() -> cudaError_t {
-            apa_phase_pass_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+            phase_kernel(1, phase_regs(1))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
             b->stats.kernel_launches++;
             cudaError_t ce = cudaEventRecord(e->evp[2], st);
             if (ce != cudaSuccess) return ce;
             if (trace) {
-                apa_phase_trace_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                phase_kernel(2, phase_regs(2))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
                 b->stats.kernel_launches++;
             }
             ce = cudaEventRecord(e->evp[3], st);
             return ce != cudaSuccess ? ce : cudaGetLastError();
         };
         if (split) {
-            CUDA_TRY(cudaMemsetAsync(e->d_queue + 8, 0, 3 * sizeof(unsigned long long), st));
+            CUDA_TRY(cudaMemsetAsync(e->d_queue + 16, 0, 3 * sizeof(unsigned long long), st));
             CUDA_TRY(cudaEventRecord(e->evp[0], st));
-            apa_phase_build_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+            phase_kernel(0, phase_regs(0))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
             CUDA_TRY(cudaEventRecord(e->evp[1], st));
             // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
             // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
@@ -991,6 +1018,13 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
     b->stats.kernel_ms = ms;
+    if (getenv("APA_DEBUG_TIMING") && b->stats.phase_ms[1] > 0) {
+        float pre = 0, post = 0;
+        cudaEventElapsedTime(&pre, e->ev[2], e->evp[0]);
+        cudaEventElapsedTime(&post, e->evp[3], e->ev[3]);
+        fprintf(stderr, "[batch_run] total %.2f ms: setup %.2f | build %.2f | pass %.2f | trace %.2f | tail %.2f\n", ms, pre,
+                b->stats.phase_ms[0], b->stats.phase_ms[1], b->stats.phase_ms[2], post);
+    }
     b->pool_used = h_q[1];
     b->stats.dp_word_steps = h_q[2];
     b->stats.computed_cells = h_q[3];

@@ -45,7 +45,7 @@ struct GcshH {
     const uint32_t* base;  // [nseeds+1] first match of each seed in by_start order
     uint32_t* before_end;  // ActiveRange.before.end per seed
     uint32_t* after_start; // ActiveRange.after.start per seed (HT_EMPTY = not split yet)
-    int hint;
+    int hint[3];       // last answer of score() per call-site stream (search start only; never changes a result)
     bool dirty;
     unsigned long long h_calls;
     long long t_h;
@@ -66,42 +66,61 @@ struct GcshH {
         return false;
     }
     // HintContours::score (hint_contours.rs:258-272): highest layer containing a point >= q. Layers are monotone
-    // (a point in layer w is dominated by one in layer w-1), so 32 layers are probed per step.
-    __device__ int score(I qx, I qy) {
+    // (a point in layer w is dominated by one in layer w-1), so the warp probes 32 layers per step: first the 32
+    // consecutive layers around the previous answer of the same call site (`slot`: the band code asks in three
+    // streams - band end, fixed-range start, fixed-range end - each of which moves smoothly from block to block),
+    // then, on a miss, strided probes away from that window (stride 1, 16, 256, ...) until the answer is bracketed,
+    // then 32-ary refinement. The result does not depend on the hints.
+    __device__ int score(I qx, I qy, int slot) {
         const int lane = threadIdx.x & 31;
         if (nlayers == 0) return 0;
         int lo = 0;            // known: contained in layer lo (layer 0 holds (MAX, MAX))
         int hi = nlayers + 1;  // known: not contained in layer hi
-        int basew = max(1, min(hint - 15, nlayers - 31));
-        for (;;) {
-            int w = basew + lane;
-            bool c = (w < hi) && (w > lo) && contains(w, qx, qy);
-            unsigned bal = __ballot_sync(FULL, c);
-            // windows are clipped to (lo, hi): lanes outside vote 0
-            int first = max(basew, lo + 1);       // first probed layer
-            int last = min(basew + 31, hi - 1);   // last probed layer
-            if (last < first) break;
-            int cntc = __popc(bal);
-            if (cntc == 0) {
-                hi = first;
+        bool down;
+        {
+            const int basew = max(1, min(hint[slot] - 15, nlayers - 31));
+            const int w = basew + lane;
+            const bool c = (w <= nlayers) && contains(w, qx, qy);
+            const int cnt = __popc(__ballot_sync(FULL, c));
+            const int last = min(basew + 31, nlayers);
+            down = cnt == 0;
+            if (down) {
+                hi = basew;
             } else {
-                lo = first + cntc - 1;
+                lo = basew + cnt - 1;
                 if (lo < last) hi = lo + 1;
             }
-            if (hi - lo <= 1) break;
-            // next window: centred bisection of the remaining interval
-            int mid = lo + (hi - lo) / 2;
-            basew = max(lo + 1, mid - 15);
         }
-        hint = lo;
+        int cap = 1;
+        while (hi - lo > 1) {
+            const int stride = min((hi - lo + 30) >> 5, cap);  // ceil(candidates / 32), capped while galloping
+            cap <<= 4;
+            if (down) {  // probes hi - stride, hi - 2 stride, ...: the contained ones are the far (high-lane) end
+                const int w = hi - (lane + 1) * stride;
+                const bool c = (w <= lo) || contains(w, qx, qy);
+                const unsigned bal = __ballot_sync(FULL, c);
+                const int f = bal ? __ffs(bal) - 1 : 32;  // lanes < f: not contained
+                const int nhi = hi - f * stride;
+                if (f < 32) lo = max(lo, hi - (f + 1) * stride);
+                hi = nhi;
+            } else {  // probes lo + stride, lo + 2 stride, ...: the contained ones are the near (low-lane) end
+                const int w = lo + (lane + 1) * stride;
+                const bool c = (w < hi) && contains(w, qx, qy);
+                const int cnt = __popc(__ballot_sync(FULL, c));
+                const int nlo = lo + cnt * stride;
+                if (cnt < 32) hi = min(hi, lo + (cnt + 1) * stride);
+                lo = nlo;
+            }
+        }
+        hint[slot] = lo;
         return lo;
     }
     // CSHI::h / h_with_hint (csh.rs:341-376): P(u) - layer(T(u)), or max(gap, potential) to the target in layer 0.
-    __device__ Cost h(I i, I j) {
+    __device__ Cost h(I i, I j, int slot = 0) {
         h_calls++;
         long long t0 = APA_TIC();
         Cost p = pot(i);
-        int val = score(i - j - p, j - i - p);
+        int val = score(i - j - p, j - i - p, slot);
         Cost r;
         if (val == 0) {
             I d = (n - i) - (m - j);
@@ -122,12 +141,12 @@ struct GcshH {
         }
         __syncwarp();
         nlayers = 0;
-        hint = 0;
+        hint[0] = 0;
         for (int idx = M - 1; idx >= 0; idx--) {
             if (!active[idx]) continue;
             I ex = px[idx] + 1, ey = py[idx] + 1;  // transform(end): P(end.i) = P(start.i) - 1
             if (!(ex <= ttx && ey <= tty)) continue;
-            int v = score(ex, ey) + 1;
+            int v = score(ex, ey, 0) + 1;
             if (lane == 0) {
                 int4 p = (v > nlayers) ? make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN) : layer_pts[v];
                 if (v > nlayers) layer_head[v] = -1;
@@ -145,68 +164,82 @@ struct GcshH {
                 }
             }
             if (v > nlayers) nlayers = v;
-            hint = v;
+            hint[0] = v;
             __syncwarp();
         }
+        hint[1] = hint[2] = hint[0];
         dirty = false;
     }
     __device__ void update_contours() {
         if (dirty) build_layers();
     }
     // MatchPruner::prune_block (prune.rs:245-292): i_range = is..ie, j_range = js..je used as inclusive bounds.
+    // The seeds of the block (<= 22 for a 256-column block) are independent of each other: one lane per seed.
     __device__ void prune_block(I is, I ie, I js, I je) {
         const int lane = threadIdx.x & 31;
-        I s0 = (is + 1 + GCSH_K - 1) / GCSH_K;  // first seed with col >= is + 1
-        for (I s = s0; s < nseeds && s * GCSH_K <= ie; s++) {
-            uint32_t b_start = base[s], b_end = before_end[s];
-            uint32_t a_start = after_start[s];
-            const uint32_t a_end = base[s + 1];
-            if (a_start == HT_EMPTY) {
-                a_start = b_end;
-                while (a_start >= b_start + 1 && ms_j[a_start - 1] > je) {
-                    b_end -= 1;
-                    a_start -= 1;
+        const I s0 = (is + GCSH_K) / GCSH_K;  // first seed with col >= is + 1
+        bool changed = false;
+        for (I sb = s0; sb < nseeds && sb * GCSH_K <= ie; sb += 32) {
+            const I s = sb + lane;
+            if (s < nseeds && s * GCSH_K <= ie) {
+                const uint32_t b_start = base[s], a_end = base[s + 1];
+                uint32_t b_end = before_end[s];
+                uint32_t a_start = after_start[s];
+                if (a_start == HT_EMPTY) {
+                    a_start = b_end;
+                    while (a_start >= b_start + 1 && ms_j[a_start - 1] > je) {
+                        b_end -= 1;
+                        a_start -= 1;
+                    }
                 }
-            }
-            bool changed = false;
-            while (b_end > b_start && ms_j[b_end - 1] >= js) {
-                if (lane == 0) active[b_end - 1] = 0;
-                b_end -= 1;
-                changed = true;
-            }
-            while (a_start < a_end && ms_j[a_start] <= je) {
-                if (lane == 0) active[a_start] = 0;
-                a_start += 1;
-                changed = true;
-            }
-            if (lane == 0) {
+                while (b_end > b_start && ms_j[b_end - 1] >= js) {
+                    active[b_end - 1] = 0;
+                    b_end -= 1;
+                    changed = true;
+                }
+                while (a_start < a_end && ms_j[a_start] <= je) {
+                    active[a_start] = 0;
+                    a_start += 1;
+                    changed = true;
+                }
                 before_end[s] = b_end;
                 after_start[s] = a_start;
             }
-            if (changed) dirty = true;
         }
+        if (__any_sync(FULL, changed)) dirty = true;
         __syncwarp();
     }
 };
 
 // ------------------------------------------------------------------------------------------------ local pruning
+// Warp-uniform values the build keeps in registers. The compiler otherwise re-derives arena pointers from their
+// allocation arithmetic at every use (10+ instructions each under the 48-register cap); a value that went through a
+// shuffle cannot be rematerialised, so it is kept (or spilled, which costs one load).
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) { return __shfl_sync(FULL, v, 0); }
+template <class T>
+__device__ __forceinline__ T* pin_ptr(T* p) {
+    unsigned long long v = (unsigned long long)p;
+    unsigned lo = __shfl_sync(FULL, (unsigned)v, 0), hi = __shfl_sync(FULL, (unsigned)(v >> 32), 0);
+    return (T*)(((unsigned long long)hi << 32) | lo);
+}
+
 struct NmpdView {  // next_match_per_diag (matches.rs:147-148): diagonal -> start.i of the left-most kept match, default MAX
-    I* v;
+    I* vb;         // biased: vb[d] for dmin <= d <= dmax
     I dmin, dmax;
-    __device__ __forceinline__ I get(I d) const { return (d < dmin || d > dmax) ? INT32_MAX : v[d - dmin]; }
+    __device__ __forceinline__ I get(I d) const { return (d < dmin || d > dmax) ? INT32_MAX : vb[d]; }
 };
 
-// preserve_for_local_pruning (prepruning.rs:95-203) for an exact match starting at (si, sj). Warp-uniform result.
-__device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I si, I sj,
+// preserve_for_local_pruning (prepruning.rs:95-203) for an exact match of seed `seed` starting at (seed * k, sj).
+// Warp-uniform result. Potentials in closed form: P(seed * k) = ns - seed.
+__device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I seed, I sj,
                                                const NmpdView& nm) {
     const int lane = threadIdx.x & 31;
+    const I si = seed * GCSH_K;
     const I ei = si + GCSH_K, ej = sj + GCSH_K;
-    const Cost start_pot = H.pot(si);
-    const I seed_idx = si / GCSH_K;
-    const I last = min(seed_idx + GCSH_P - 1, H.nseeds - 1);
+    const Cost start_pot = H.nseeds - seed;
+    const I last = min(seed + GCSH_P - 1, H.nseeds - 1);
     const I end_i = (last + 1) * GCSH_K;
-    const Cost end_pot = H.pot(end_i);
-    const int pd = start_pot - end_pot;  // <= GCSH_P
+    const int pd = last + 1 - seed;  // start_pot - P(end_i), <= GCSH_P
     // g = 0
     I f0 = ei;
     extend_right_packed(ap, bp, H.m, f0, ej, end_i);
@@ -215,6 +248,7 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __re
     // lanes 0 .. 2*pd hold the front; lane d <-> diagonal e + (d - pd)
     I fr = (lane == pd) ? f0 : INT32_MIN;
     int lo = pd, hi = pd + 1;  // d_range
+    const I dd = ei - ej + (lane - pd);  // this lane's diagonal
     for (Cost g = 1; g < pd; g++) {
         // expand: next[d] = max(fr[d+1], fr[d] + 1, fr[d-1] + 1) over sources inside d_range
         I up = __shfl_down_sync(FULL, fr, 1);  // fr[d+1]
@@ -237,7 +271,6 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __re
         in = lane >= lo && lane < hi;
         bool ok = false;
         if (in) {
-            I dd = ei - ej + (lane - pd);
             I j = fr - dd;
             I old_i = fr;
             extend_right_packed(ap, bp, H.m, fr, j, end_i);
@@ -249,7 +282,8 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __re
     return false;
 }
 
-__device__ __forceinline__ uint32_t kmer_hash(uint32_t key, int log_t) { return (key * 0x9E3779B1u) >> (32 - log_t); }
+constexpr uint32_t KMER_MUL = 0x9E3779B1u;
+constexpr uint32_t STAGE_MULTI = 0x40000000u;  // staged hit whose k-mer occurs in several seeds of a
 
 // CSHI::new (csh.rs:199-308): find matches, filter, sort, build the pruner state and the contours.
 // All scratch comes from the pair's arena; structures that die after the precomputation are placed last so the
@@ -264,14 +298,14 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     H.tty = m - n;
     H.h_calls = 0;
     H.t_h = 0;
-    H.hint = 0;
+    H.hint[0] = H.hint[1] = H.hint[2] = 0;
     H.dirty = false;
     H.nlayers = 0;
     const I ns = H.nseeds;
 
     // capacity for matches scales with the arena (re-run with a larger arena on overflow)
     const uint32_t avail = cx.hi_bot - cx.v_top;
-    int mcap = (int)min((uint32_t)(1u << 30), avail / 180u);
+    int mcap = (int)min((uint32_t)(1u << 30), avail / 192u);
     if (mcap < 64) {
         cx.status = ST_OVERFLOW;
         return false;
@@ -293,38 +327,47 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     int log_t = 5;
     while ((1 << log_t) < 2 * ns) log_t++;
     const uint32_t tsize = 1u << log_t;
+    const int log_bm = log_t + 2;  // k-mer presence filter: 4 bits per table slot = 8..16 bits per seed
+    const uint32_t bm_words = 1u << (log_bm - 5);
     uint32_t off_tab = arena_alloc(cx, tsize * 8u);
+    uint32_t off_bm = arena_alloc(cx, bm_words * 4u);
     const I dmin = (n - m) - ns - (GCSH_P + 2), dmax = (n - m) + ns + (GCSH_P + 2);
     uint32_t off_nm = arena_alloc(cx, (uint32_t)(dmax - dmin + 1) * 4u);
-    uint32_t off_arr_s = arena_alloc(cx, (uint32_t)mcap * 4u);
-    uint32_t off_arr_j = arena_alloc(cx, (uint32_t)mcap * 4u);
-    uint32_t off_arr_r = arena_alloc(cx, (uint32_t)mcap * 4u);
+    uint32_t off_arr = arena_alloc(cx, (uint32_t)mcap * 16u);
+    uint32_t off_stage = arena_alloc(cx, 32u * 32u * 8u);
     if (cx.status != ST_PENDING) return false;
 
-    uint32_t* cnt = (uint32_t*)(cx.arena + off_base);  // counts, then exclusive prefix
+    uint32_t* cnt = pin_ptr((uint32_t*)(cx.arena + off_base));  // counts, then exclusive prefix
     uint32_t* before_end = (uint32_t*)(cx.arena + off_bend);
     uint32_t* after_start = (uint32_t*)(cx.arena + off_astart);
     I* ms_i = (I*)(cx.arena + off_msi);
     I* ms_j = (I*)(cx.arena + off_msj);
-    uint2* tab = (uint2*)(cx.arena + off_tab);
-    NmpdView nm{(I*)(cx.arena + off_nm), dmin, dmax};
-    I* arr_s = (I*)(cx.arena + off_arr_s);
-    I* arr_j = (I*)(cx.arena + off_arr_j);
-    uint32_t* arr_r = (uint32_t*)(cx.arena + off_arr_r);
+    uint2* tab = pin_ptr((uint2*)(cx.arena + off_tab));
+    uint32_t* bm = pin_ptr((uint32_t*)(cx.arena + off_bm));
+    I* nm_v = (I*)(cx.arena + off_nm);
+    NmpdView nm{pin_ptr(nm_v - dmin), dmin, dmax};
+    int4* arr = pin_ptr((int4*)(cx.arena + off_arr));        // kept matches in arrival order: (seed, j, rank within seed, -)
+    uint2* stage = pin_ptr((uint2*)(cx.arena + off_stage));  // per lane: up to 32 staged hits (j, first seed | STAGE_MULTI)
+    const uint2* ap = pin_ptr(cx.aprof);
+    const uint2* bp = pin_ptr(cx.bprof);
 
     for (uint32_t t = lane; t < tsize; t += 32) tab[t] = make_uint2(0u, HT_EMPTY);
-    for (I t = lane; t <= dmax - dmin; t += 32) nm.v[t] = INT32_MAX;
+    for (uint32_t t = lane; t < bm_words; t += 32) bm[t] = 0u;
+    for (I t = lane; t <= dmax - dmin; t += 32) nm_v[t] = INT32_MAX;
     for (I t = lane; t < ns + 2; t += 32) cnt[t] = 0u;
     __syncwarp();
 
     // ---- hash the seeds of a (hash_to_smallvec, exact.rs:48-55). Key: bit t = rank bit0 of char t, bit k+t = rank bit1.
+    const uint32_t kmask = (1u << GCSH_K) - 1u;
     for (I s0 = 0; s0 < ns; s0 += 32) {
         I s = s0 + lane;
         if (s < ns) {
-            const uint2 w = extract32(cx.aprof, s * GCSH_K);  // planes are stored negated
-            const uint32_t km = (1u << GCSH_K) - 1u;
-            const uint32_t key = (~w.x & km) | ((~w.y & km) << GCSH_K);
-            uint32_t slot = kmer_hash(key, log_t);
+            const uint2 w = extract32(ap, s * GCSH_K);  // planes are stored negated
+            const uint32_t key = (~w.x & kmask) | ((~w.y & kmask) << GCSH_K);
+            const uint32_t hsh = key * KMER_MUL;
+            const uint32_t bit = hsh >> (32 - log_bm);
+            atomicOr(&bm[bit >> 5], 1u << (bit & 31));
+            uint32_t slot = hsh >> (32 - log_t);
             unsigned long long want = ((unsigned long long)(uint32_t)s << 32) | key;  // uint2{key, seed}
             for (;;) {
                 unsigned long long old = atomicCAS((unsigned long long*)&tab[slot], ((unsigned long long)HT_EMPTY << 32), want);
@@ -335,15 +378,13 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     }
     __syncwarp();
 
-    // ---- scan all windows of b right to left (b_qgrams_rev, qgrams.rs:81-97), push matches in arrival order
-    int M = 0;
-    // next larger seed with this key after `after` (or the smallest when after < 0); returns count via cnt_out
-    auto probe = [&](uint32_t key, I after, int& cnt_out) -> I {
-        uint32_t slot = kmer_hash(key, log_t);
+    // smallest seed > `after` whose k-mer is `key` (INT32_MAX if none); n_out = number of seeds with that k-mer
+    auto probe = [&](uint32_t key, I after, int& n_out) -> I {
+        uint32_t slot = (key * KMER_MUL) >> (32 - log_t);
         I best = INT32_MAX;
         int c = 0;
         for (;;) {
-            uint2 e = tab[slot];
+            const uint2 e = tab[slot];
             if (e.y == HT_EMPTY) break;
             if (e.x == key) {
                 c++;
@@ -351,54 +392,85 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
             }
             slot = (slot + 1) & (tsize - 1);
         }
-        cnt_out = c;
+        n_out = c;
         return best;
     };
-    const uint32_t kmask = (1u << GCSH_K) - 1u;
-    for (I jt = m - GCSH_K; jt >= 0; jt -= 32) {
-        const I j = jt - lane;
-        uint32_t key = 0;
-        int c = 0;
-        I seed0 = INT32_MAX;
-        if (j >= 0) {
-            const uint2 w = extract32(cx.bprof, j);  // planes are stored negated
-            key = (~w.x & kmask) | ((~w.y & kmask) << GCSH_K);
-            seed0 = probe(key, -1, c);
+
+    // ---- all windows of b, right to left (b_qgrams_rev, qgrams.rs:81-97), 1024 per round: lane l owns the 32 windows
+    // j = jhi, jhi - 1, ... with jhi = jtop - 32 l. (1) every lane tests its windows against the presence filter (one
+    // 4-byte load each, L2-resident), (2) the survivors (~1 in 9 for unrelated windows) are looked up in the hash table and
+    // the hits staged per lane, (3) the hits are pushed in the reference's arrival order - j descending, seeds ascending -
+    // through MatchBuilder::push (matches.rs:205-247), one hit at a time with the lanes on the diagonals of the pruning front.
+    int M = 0;
+    for (I jtop = m - GCSH_K; jtop >= 0; jtop -= 1024) {
+        const I jhi = jtop - 32 * lane;
+        const I wbase = max(jhi - 31, 0);  // bit s of `surv` <-> window j = wbase + s
+        uint32_t surv = 0u;
+        uint32_t w0x = 0u, w0y = 0u, w1x = 0u, w1y = 0u;
+        if (jhi >= 0) {
+            const uint2 lo = extract32(bp, wbase), hi = extract32(bp, wbase + 32);
+            w0x = ~lo.x, w0y = ~lo.y, w1x = ~hi.x, w1y = ~hi.y;
+#pragma unroll 8
+            for (int sft = 0; sft < 32; sft++) {
+                const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GCSH_K);
+                const uint32_t bit = (key * KMER_MUL) >> (32 - log_bm);
+                const uint32_t word = bm[bit >> 5];
+                surv |= ((word >> (bit & 31)) & 1u) << sft;
+            }
+            const int nwin = jhi - wbase + 1;  // windows above jhi belong to the previous lane
+            if (nwin < 32) surv &= (1u << nwin) - 1u;
         }
-        unsigned bal = __ballot_sync(FULL, c > 0);
-        while (bal) {
-            const int l = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const I jj = jt - l;
-            const uint32_t kk = __shfl_sync(FULL, key, l);
-            const int cc = __shfl_sync(FULL, c, l);
-            I seed = __shfl_sync(FULL, seed0, l);
-            for (int t = 0; t < cc; t++) {
-                const I si = seed * GCSH_K;
-                // MatchBuilder::push (matches.rs:205-247)
-                const Cost p = H.pot(si);
-                const bool pass_t = (si - jj - p <= H.ttx) && (jj - si - p <= H.tty);
-                if (pass_t && dev_preserve_for_local_pruning(H, cx.aprof, cx.bprof, si, jj, nm)) {
-                    if (M >= mcap) {
-                        cx.status = ST_OVERFLOW;
-                        return false;
-                    }
-                    const I d = si - jj;
-                    if (d >= dmin && d <= dmax) {
-                        if (lane == 0) nm.v[d - dmin] = si;
-                    }
-                    if (lane == 0) {
-                        arr_s[M] = seed;
-                        arr_j[M] = jj;
-                        arr_r[M] = cnt[seed];
-                        cnt[seed] += 1;
-                    }
-                    M++;
-                    __syncwarp();
+        int nh = 0;
+        while (__any_sync(FULL, surv != 0u)) {
+            if (surv) {
+                const int sft = 31 - __clz(surv);  // highest j first
+                surv &= ~(1u << sft);
+                const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GCSH_K);
+                int c;
+                const I seed0 = probe(key, -1, c);
+                if (c > 0) {
+                    stage[lane * 32 + nh] = make_uint2((uint32_t)(wbase + sft), (uint32_t)seed0 | (c > 1 ? STAGE_MULTI : 0u));
+                    nh++;
                 }
-                if (t + 1 < cc) {
+            }
+        }
+        __syncwarp();
+        unsigned has = __ballot_sync(FULL, nh > 0);
+        while (has) {
+            const int l = __ffs(has) - 1;
+            has &= has - 1;
+            const int cntl = __shfl_sync(FULL, nh, l);
+            for (int hh = 0; hh < cntl; hh++) {
+                const uint2 rec = stage[l * 32 + hh];
+                const I jj = (I)rec.x;
+                I seed = (I)(rec.y & ~STAGE_MULTI);
+                const bool multi = (rec.y & STAGE_MULTI) != 0u;
+                for (;;) {
+                    // MatchBuilder::push (matches.rs:205-247)
+                    const I si = seed * GCSH_K;
+                    const Cost p = ns - seed;  // P(si)
+                    const bool pass_t = (si - jj - p <= H.ttx) && (jj - si - p <= H.tty);
+                    if (pass_t && dev_preserve_for_local_pruning(H, ap, bp, seed, jj, nm)) {
+                        if (M >= mcap) {
+                            cx.status = ST_OVERFLOW;
+                            return false;
+                        }
+                        if (lane == 0) {
+                            const I d = si - jj;
+                            if (d >= dmin && d <= dmax) nm.vb[d] = si;
+                            const uint32_t rank = cnt[seed];
+                            cnt[seed] = rank + 1u;
+                            arr[M] = make_int4(seed, jj, (int)rank, 0);
+                        }
+                        M++;
+                        __syncwarp();
+                    }
+                    if (!multi) break;
+                    const uint2 w = extract32(bp, jj);
+                    const uint32_t kk = (~w.x & kmask) | ((~w.y & kmask) << GCSH_K);
                     int dummy;
                     seed = probe(kk, seed, dummy);
+                    if (seed == INT32_MAX) break;
                 }
             }
         }
@@ -421,11 +493,12 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
         }
         __syncwarp();
         for (int t = lane; t < M; t += 32) {
-            I s = arr_s[t];
+            const int4 a4 = arr[t];
+            const I s = a4.x;
             uint32_t c_s = cnt[s + 1] - cnt[s];
-            uint32_t pos = cnt[s] + (c_s - 1u - arr_r[t]);
+            uint32_t pos = cnt[s] + (c_s - 1u - (uint32_t)a4.z);
             ms_i[pos] = s * GCSH_K;
-            ms_j[pos] = arr_j[t];
+            ms_j[pos] = a4.y;
         }
         __syncwarp();
     }

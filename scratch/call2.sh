@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 5 --warmup 3 --cpu-sample 64 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_full.json'))
+print(d['ms_per_step'], [ (k['name'],round(k['ms_per_launch'],2)) for k in d['kernels']], 'e2e', d['e2e']['ms_per_step'])
+PY
