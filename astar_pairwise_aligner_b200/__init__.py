@@ -33,7 +33,7 @@ class BatchStats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("computed_cells", C.c_uint64),
                 ("dp_word_steps", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("retries", C.c_uint64), ("fill_blocks", C.c_uint64), ("dt_blocks", C.c_uint64),
-                ("phase_cycles", C.c_uint64 * 8), ("phase_ms", C.c_double * 3)]
+                ("phase_cycles", C.c_uint64 * 8), ("phase_ms", C.c_double * 3), ("score_calls", C.c_uint64), ("score_probes", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

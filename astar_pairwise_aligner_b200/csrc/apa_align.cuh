@@ -81,7 +81,7 @@ __device__ __forceinline__ BlkView view_of(const PairCtx& cx, const BlkMeta& mt)
 struct GapH {
     I n, m;
     static constexpr bool PRUNE = false;
-    __device__ __forceinline__ Cost h(I i, I j, int = 0) const {
+    __device__ __forceinline__ Cost h(I i, I j, int = 3) const {
         I d = (n - i) - (m - j);
         return d < 0 ? -d : d;
     }
@@ -107,7 +107,7 @@ __device__ JRange dev_j_range(const PairCtx& cx, Hh& hh, I is, I ie, Cost f_max,
             break;
         }
         I dd = (vi - ui) - (vj - uj);
-        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj);
+        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj, 0);
         if (fv <= f_max) {
             if (vj == cx.m) break;
             vj += 8;
@@ -127,7 +127,7 @@ __device__ JRange dev_j_range(const PairCtx& cx, Hh& hh, I is, I ie, Cost f_max,
             break;
         }
         I dd = (vi - ui) - (vj - uj);
-        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj);
+        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj, 0);
         if (fv <= f_max) break;
         vj -= div_ceil_pos(fv - f_max, 2);
     }

@@ -150,6 +150,8 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
             cw.count = 0;
             cw.pend_cnt = 0;
             cw.pend_op = 0;
+            cw.nbuf = 0;
+            cw.buf = 0;
             long long t0 = APA_TIC();
             bool traced = dev_trace(cx, sm, cw, cost);
             APA_TOC(cx.tphase[3], t0);
@@ -204,10 +206,10 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     WarpSmem& sm = smem[wib];
-    unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0;
+    unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0, acc_h = 0, acc_probe = 0;
     for (;;) {
         unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(bd.queue + 16 + PHASE, 1ull) + bd.q0;
+        if (lane == 0) q = atomicAdd(bd.queue + 24 + PHASE, 1ull) + bd.q0;
         q = __shfl_sync(FULL, q, 0);
         if (q >= bd.n_order) break;
         if (PHASE <= 1 && bd.ready) {
@@ -265,9 +267,12 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
                     if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
                 } else {
                     GcshH hh = ps->hh;
+                    hh.h_calls = hh.probes = 0;
                     Cost h0 = hh.h(0, 0);
                     cost = dev_band_doubling(cx, sm, hh, h0);
                     if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;
+                    acc_h += hh.h_calls;
+                    acc_probe += hh.probes;
                 }
             }
             __syncwarp();
@@ -287,6 +292,8 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
             cw.count = 0;
             cw.pend_cnt = 0;
             cw.pend_op = 0;
+            cw.nbuf = 0;
+            cw.buf = 0;
             if (dev_trace(cx, sm, cw, cost)) {
                 cig_off = emit_cigar_text(cw, bd.pool, bd.pool_cursor, bd.pool_cap, &cig_len);
                 if (cig_off < 0) cx.status = ST_OVERFLOW;
@@ -304,6 +311,10 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
         acc_pass += cx.passes;
         acc_fill += cx.fill_blocks;
         acc_dt += cx.dt_blocks;
+    }
+    if (PHASE == 1 && lane == 0) {
+        atomicAdd(&bd.stats[13], acc_h);
+        atomicAdd(&bd.stats[14], acc_probe);
     }
     if (PHASE >= 1 && lane == 0) {
         atomicAdd(&bd.stats[0], acc_steps);
@@ -402,7 +413,7 @@ struct apa_engine {
     // so buffers released by a batch are kept for the next one (grow-only, per engine).
     std::unordered_map<void*, size_t> live;
     std::vector<std::pair<void*, size_t>> free_blocks;
-    unsigned long long* d_queue = nullptr;   // [0] queue head, [1] pool cursor, [2..14] stats, [16..18] phase-kernel queue heads
+    unsigned long long* d_queue = nullptr;   // [0] queue head, [1] pool cursor, [2..16] stats, [24..26] phase-kernel queue heads
     uint8_t* d_arena = nullptr;
     size_t arena_total = 0;
 };
@@ -956,7 +967,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             return ce != cudaSuccess ? ce : cudaGetLastError();
         };
         if (split) {
-            CUDA_TRY(cudaMemsetAsync(e->d_queue + 16, 0, 3 * sizeof(unsigned long long), st));
+            CUDA_TRY(cudaMemsetAsync(e->d_queue + 24, 0, 3 * sizeof(unsigned long long), st));
             CUDA_TRY(cudaEventRecord(e->evp[0], st));
             phase_kernel(0, phase_regs(0))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
             CUDA_TRY(cudaEventRecord(e->evp[1], st));
@@ -1012,7 +1023,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     }
     if (!pending.empty()) return set_err(APA_ERR_TOO_LARGE, "pairs still overflow after 8 arena enlargements");
     CUDA_TRY(cudaEventRecord(e->ev[3], st));
-    unsigned long long h_q[16];
+    unsigned long long h_q[32];
     CUDA_TRY(cudaMemcpyAsync(h_q, e->d_queue, sizeof h_q, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
@@ -1032,6 +1043,8 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     b->stats.fill_blocks = h_q[5];
     b->stats.dt_blocks = h_q[6];
     for (int t = 0; t < 8; t++) b->stats.phase_cycles[t] = h_q[7 + t];
+    b->stats.score_calls = h_q[15];
+    b->stats.score_probes = h_q[16];
     b->ran = true;
     for (uint64_t p = 0; p < b->n_pairs; p++) {
         if (b->h_status[p] == ST_BAD_INPUT) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT in pair " + std::to_string(p));

@@ -45,9 +45,15 @@ struct GcshH {
     const uint32_t* base;  // [nseeds+1] first match of each seed in by_start order
     uint32_t* before_end;  // ActiveRange.before.end per seed
     uint32_t* after_start; // ActiveRange.after.start per seed (HT_EMPTY = not split yet)
-    int hint[3];       // last answer of score() per call-site stream (search start only; never changes a result)
+    // Search start of score(), per call-site stream (never changes a result): the last answer, the coordinate of the
+    // last query that bound it, and the layers-per-unit density used to extrapolate from one query to the next.
+    // Streams: 0 band end (j_range), 1 fixed-range start, 2 fixed-range end, 3 plain (contour build, h0).
+    int hint[4];
+    int hq[4];
+    int dens;          // nlayers * 256 / nseeds: a layer is one chained match, about one per (1 / match rate) seeds
     bool dirty;
     unsigned long long h_calls;
+    unsigned long long probes;  // 32-layer probe rounds of score() (stats: score_probes / score_calls = rounds per query)
     long long t_h;
 
     // Seeds::potential (seeds.rs:79-81) for fixed-length seeds at 0, k, 2k, ...: number of seeds starting at >= i.
@@ -78,7 +84,17 @@ struct GcshH {
         int hi = nlayers + 1;  // known: not contained in layer hi
         bool down;
         {
-            const int basew = max(1, min(hint[slot] - 15, nlayers - 31));
+            // Along the chain, layer(q) ~ dens * (K - q_bind): the transformed coordinate that binds is y below the
+            // main diagonal (band end) and x above it (band start). Extrapolate from the previous query of the stream.
+            int pred = hint[slot];
+            if (slot != 3) {
+                const int qb = slot == 1 ? qx : qy;
+                const int dq = max(-65536, min(65536, hq[slot] - qb));
+                pred += (dq * dens) >> 8;
+                hq[slot] = qb;
+            }
+            const int basew = max(1, min(pred - 15, nlayers - 31));
+            probes++;
             const int w = basew + lane;
             const bool c = (w <= nlayers) && contains(w, qx, qy);
             const int cnt = __popc(__ballot_sync(FULL, c));
@@ -95,6 +111,7 @@ struct GcshH {
         while (hi - lo > 1) {
             const int stride = min((hi - lo + 30) >> 5, cap);  // ceil(candidates / 32), capped while galloping
             cap <<= 4;
+            probes++;
             if (down) {  // probes hi - stride, hi - 2 stride, ...: the contained ones are the far (high-lane) end
                 const int w = hi - (lane + 1) * stride;
                 const bool c = (w <= lo) || contains(w, qx, qy);
@@ -116,7 +133,7 @@ struct GcshH {
         return lo;
     }
     // CSHI::h / h_with_hint (csh.rs:341-376): P(u) - layer(T(u)), or max(gap, potential) to the target in layer 0.
-    __device__ Cost h(I i, I j, int slot = 0) {
+    __device__ Cost h(I i, I j, int slot = 3) {
         h_calls++;
         long long t0 = APA_TIC();
         Cost p = pot(i);
@@ -141,12 +158,12 @@ struct GcshH {
         }
         __syncwarp();
         nlayers = 0;
-        hint[0] = 0;
+        hint[3] = 0;
         for (int idx = M - 1; idx >= 0; idx--) {
             if (!active[idx]) continue;
             I ex = px[idx] + 1, ey = py[idx] + 1;  // transform(end): P(end.i) = P(start.i) - 1
             if (!(ex <= ttx && ey <= tty)) continue;
-            int v = score(ex, ey, 0) + 1;
+            int v = score(ex, ey, 3) + 1;
             if (lane == 0) {
                 int4 p = (v > nlayers) ? make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN) : layer_pts[v];
                 if (v > nlayers) layer_head[v] = -1;
@@ -164,10 +181,12 @@ struct GcshH {
                 }
             }
             if (v > nlayers) nlayers = v;
-            hint[0] = v;
+            hint[3] = v;
             __syncwarp();
         }
-        hint[1] = hint[2] = hint[0];
+        hint[0] = hint[1] = hint[2] = hint[3];
+        hq[0] = hq[1] = hq[2] = hq[3] = 0;
+        dens = min(256, (int)(((long long)nlayers << 8) / max(1, nseeds)));
         dirty = false;
     }
     __device__ void update_contours() {
@@ -297,8 +316,11 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
     H.ttx = n - m;  // transform(target): P(n) = 0
     H.tty = m - n;
     H.h_calls = 0;
+    H.probes = 0;
     H.t_h = 0;
-    H.hint[0] = H.hint[1] = H.hint[2] = 0;
+    H.hint[0] = H.hint[1] = H.hint[2] = H.hint[3] = 0;
+    H.hq[0] = H.hq[1] = H.hq[2] = H.hq[3] = 0;
+    H.dens = 0;
     H.dirty = false;
     H.nlayers = 0;
     const I ns = H.nseeds;

@@ -16,23 +16,44 @@ constexpr int DT_MAX_G = 40;    // BlockParams.max_g of both presets (params.rs:
 constexpr int DT_FR_DROP = 10;  // BlockParams.fr_drop (params.rs:92,123)
 constexpr int DT_CACHE_ELEMS = (DT_MAX_G + 1) * (DT_MAX_G + 1);
 
+// Shared-memory accesses of the DT fronts through an explicit 32-bit shared address held in a register: under the
+// 48-register cap the compiler otherwise rebuilds the address of the warp's shared block (5 instructions) at every access.
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_i32(uint32_t addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 struct CigarWriter {  // elements are pushed newest-first (the path is walked from the end); see emit_cigar_text.
     uint8_t* arena;
     uint32_t arena_size;
-    uint32_t count;      // elements already stored
+    uint32_t count;      // elements already stored in the arena
     uint32_t pend_op;    // pending (mergeable) element
     uint32_t pend_cnt;   // 0 = none
+    uint32_t nbuf;       // finished elements held in registers: element k of the buffer sits in lane k's `buf`
+    uint32_t buf;
 };
 
-__device__ __forceinline__ void cig_store(PairCtx& cx, CigarWriter& cw, uint32_t op, uint32_t cnt) {
-    uint32_t need = (cw.count + 1) * 4u;
-    if (cx.arena_size - need < cx.v_top) {
+// Write the buffered elements to the arena: element (count + k) goes to arena_end - 4 (count + k + 1), one coalesced store.
+__device__ __forceinline__ void cig_drain(PairCtx& cx, CigarWriter& cw) {
+    if (cw.nbuf == 0) return;
+    const uint32_t need = (cw.count + cw.nbuf) * 4u;
+    if (need > cx.arena_size || cx.arena_size - need < cx.v_top) {
         cx.status = ST_OVERFLOW;
+        cw.nbuf = 0;
         return;
     }
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane < cw.nbuf) *(uint32_t*)(cw.arena + cx.arena_size - 4u * (cw.count + lane + 1u)) = cw.buf;
+    cw.count += cw.nbuf;
+    cw.nbuf = 0;
     cx.hi_bot = cx.arena_size - need;
-    if ((threadIdx.x & 31) == 0) *(uint32_t*)(cw.arena + cx.hi_bot) = cig_pack(op, cnt);
-    cw.count++;
+}
+__device__ __forceinline__ void cig_store(PairCtx& cx, CigarWriter& cw, uint32_t op, uint32_t cnt) {
+    if ((threadIdx.x & 31) == cw.nbuf) cw.buf = cig_pack(op, cnt);
+    cw.nbuf++;
+    if (cw.nbuf == 32) cig_drain(cx, cw);
 }
 // Cigar::push_elem: merge with the previous element when the op is the same.
 __device__ __forceinline__ void cig_push(PairCtx& cx, CigarWriter& cw, uint32_t op, uint32_t cnt) {
@@ -47,6 +68,7 @@ __device__ __forceinline__ void cig_push(PairCtx& cx, CigarWriter& cw, uint32_t 
 __device__ __forceinline__ void cig_flush(PairCtx& cx, CigarWriter& cw) {
     if (cw.pend_cnt != 0) cig_store(cx, cw, cw.pend_op, cw.pend_cnt);
     cw.pend_cnt = 0;
+    cig_drain(cx, cw);
 }
 
 // A column of the dense (re-filled) region or a stored sparse block, as seen by parent().
@@ -117,6 +139,8 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
     auto idx = [](int g, int d) { return g * g + g + d; };
     int8_t* chain = (int8_t*)sm.hrow;  // d of each level on the final path
     constexpr int DOFF = 48;
+    // byte address (shared window) of front element d = 0 of level parity 0; parity 1 is 96 ints further
+    const uint32_t dt0 = __shfl_sync(FULL, (uint32_t)__cvta_generic_to_shared(&sm.dt_i[0][DOFF]), 0);
 
     // reference closure extend_left_simd_and_check (trace.rs:313-329)
     auto reached = [&](I i, I j, Cost target) -> bool {
@@ -131,7 +155,7 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
         I i = si, j = sj;
         I ext = extend_left_packed(cx.aprof, cx.bprof, i, block_start, j);
         if (lane == 0) {
-            sm.dt_i[0][DOFF] = i;
+            sts_i32(dt0, i);
             rec[0] = (ext << 2) | 1;
         }
         __syncwarp();
@@ -139,8 +163,8 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
     }
     while (!found) {
         const int ng = g + 1;
-        const int32_t* cur = sm.dt_i[g & 1];
-        int32_t* nxt = sm.dt_i[ng & 1];
+        const uint32_t cur = dt0 + (uint32_t)(g & 1) * 384u;  // front of level g: element d at cur + 4 d
+        const uint32_t nxt = dt0 + (uint32_t)(ng & 1) * 384u;
         // expand + extend level ng, one diagonal per lane
         I min_fr = INT32_MAX, min_i = INT32_MAX;
         int succ_d = INT32_MAX;
@@ -151,15 +175,15 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
             bool in = d <= d_hi + 1;
             if (in) {
                 if (d - 1 >= d_lo && d - 1 <= d_hi) {  // from d-1: (fr.i, -1) insertion
-                    I y = cur[DOFF + d - 1];
+                    I y = lds_i32(cur + 4 * (d - 1));
                     if (y < best) best = y, pd = -1;
                 }
                 if (d >= d_lo && d <= d_hi) {  // from d: (fr.i - 1, 0) substitution
-                    I y = cur[DOFF + d] - 1;
+                    I y = lds_i32(cur + 4 * d) - 1;
                     if (y < best) best = y, pd = 0;
                 }
                 if (d + 1 >= d_lo && d + 1 <= d_hi) {  // from d+1: (fr.i - 1, +1) deletion
-                    I y = cur[DOFF + d + 1] - 1;
+                    I y = lds_i32(cur + 4 * (d + 1)) - 1;
                     if (y < best) best = y, pd = 1;
                 }
             }
@@ -173,7 +197,7 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
                     min_fr = min(min_fr, (I)(2u * (uint32_t)i - (uint32_t)d));
                     min_i = min(min_i, i);
                 }
-                nxt[DOFF + d] = i;
+                sts_i32(nxt + 4 * d, i);
                 rec[idx(ng, d)] = (ext << 2) | (pd + 1);
             }
             unsigned bal = __ballot_sync(FULL, ok);
@@ -188,24 +212,21 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
             found_d = succ_d;
             break;
         }
-#pragma unroll
-        for (int s = 16; s; s >>= 1) {
-            min_fr = min(min_fr, __shfl_xor_sync(FULL, min_fr, s));
-            min_i = min(min_i, __shfl_xor_sync(FULL, min_i, s));
-        }
+        min_fr = __reduce_min_sync(FULL, min_fr);
+        min_i = __reduce_min_sync(FULL, min_i);
         if (g == DT_MAX_G / 2 && min_i > (block_start + si) / 2) return false;
         if (g == DT_MAX_G) return false;
         // x-drop: shrink diagonals more than fr_drop behind (trace.rs:396-414)
         const I thr = (I)((uint32_t)min_fr + (uint32_t)DT_FR_DROP);
         while (d_lo < d_hi) {
-            I i = nxt[DOFF + d_lo];
+            I i = lds_i32(nxt + 4 * d_lo);
             if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_lo) > thr)
                 d_lo++;
             else
                 break;
         }
         while (d_lo < d_hi) {
-            I i = nxt[DOFF + d_hi];
+            I i = lds_i32(nxt + 4 * d_hi);
             if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_hi) > thr)
                 d_hi--;
             else

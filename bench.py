@@ -298,6 +298,8 @@ def main():
         "computed_gcups": comp_all / (ms_step / 1e3) / 1e9, "aligned_bp_per_s": bp_all / (ms_step / 1e3),
         "pairs_per_s": args.pairs * world / (ms_step / 1e3), "wall_ms_per_step": wall_ms / args.steps,
         "passes_per_pair": st["passes"] / args.pairs, "retries": st["retries"],
+        "h_queries_per_pair": st["score_calls"] / args.pairs,
+        "contour_probe_rounds_per_query": (st["score_probes"] / st["score_calls"]) if st["score_calls"] else None,
         "kernels": [{"name": k, "ms_per_launch": t, "share_of_step": t / ms_step if ms_step else None,
                      "algorithmic_gb_per_launch": alg[k] / 1e9} for k, t in zip(KERNELS, k_ms)],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

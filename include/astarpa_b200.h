@@ -52,6 +52,9 @@ typedef struct apa_batch_stats {
      * [1] apa_phase_pass_kernel (band doubling + block DP) [2] apa_phase_trace_kernel (traceback + CIGAR text).
      * All zero when the fused single-kernel path ran (arenas of the whole batch did not fit in HBM). */
     double phase_ms[3];
+    /* GCSH queries of the pass kernel: h() calls and 32-layer probe rounds of the contour search (rounds / calls ~ 1 when
+     * the per-stream extrapolation of the search start is good). Zero for astarpa2_simple and on the fused path. */
+    uint64_t score_calls, score_probes;
 } apa_batch_stats;
 
 const char* apa_last_error(void);

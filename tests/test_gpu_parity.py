@@ -181,6 +181,29 @@ def test_million_bp_pair_gpu(apa, oracle, preset):
     assert cost == oc and cigar == ocg
 
 
+def test_ten_million_bp_pair_gpu(apa, oracle):
+    # BASELINE configs[4]: one ONT-like pair, n = 10 000 000, e = 5 % (one warp walks the whole pair; replicas only
+    # across GPUs). Cost and CIGAR against the oracle; the CIGAR is also replayed over the pair.
+    a, b = apa.generate_pair(10000000, 0.05, 0, 4242)
+    cost, cigar = apa.AstarPa2(1, True).align(a, b)
+    assert oracle.cigar_verify(cigar, a, b) == cost
+    oc, ocg, _ = oracle.align(a, b, 1, True)
+    assert cost == oc and cigar == ocg
+
+
+def test_config2_cost_only_batch_gpu(apa, oracle):
+    # BASELINE configs[1] shape (n = 10 000, e = 5 %, cost only) on a slice of the batch: costs against the oracle for
+    # both presets, and cost-only == cost of the traced run.
+    pairs = [apa.generate_pair(10000, 0.05, 0, 31415 + s) for s in range(64)]
+    for preset in PRESETS:
+        costs, cigars = apa.AstarPa2(preset, False).align_batch(pairs)
+        assert cigars is None
+        traced, _ = apa.AstarPa2(preset, True).align_batch(pairs)
+        assert (costs == traced).all()
+        for k in range(0, 64, 7):
+            assert int(costs[k]) == oracle.align(pairs[k][0], pairs[k][1], preset, False)[0]
+
+
 def test_bad_input_gpu(apa):
     with pytest.raises(apa.AstarPaError):
         apa.AstarPa2(0, True).align_batch([(b"ACGT", b"ACGT"), (b"ACGN", b"ACGT")])
