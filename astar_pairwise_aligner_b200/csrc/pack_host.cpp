@@ -5,10 +5,35 @@
 #include <immintrin.h>
 #include <stdint.h>
 
-// Packs half-words [hw_begin, hw_end) of `seq` (len bases) into out[2*hw], out[2*hw+1]. Half-words past the end of the
+// AVX2 (and AVX-512BW when the CPU has it, chosen at run time). Packs half-words [hw_begin, hw_end) of `seq` (len bases) into out[2*hw], out[2*hw+1]. Half-words past the end of the
 // sequence are zero (padding). Returns 0, or 1 if a byte outside ACGT was seen.
+// AVX-512BW body for whole 64-base groups (two half-words per iteration): rank bits straight into mask registers.
+// Returns the first half-word it did not pack.
+__attribute__((target("avx512f,avx512bw"))) static int64_t pack_planes_avx512(const uint8_t* seq, int64_t len, int64_t hw_begin,
+                                                                             int64_t hw_end, uint32_t* out, int* bad) {
+    int64_t hw = hw_begin;
+    if (hw & 1) return hw;  // callers start on even half-words except for tails
+    const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'), cT = _mm512_set1_epi8('T');
+    const __m512i b1 = _mm512_set1_epi8(2), b2 = _mm512_set1_epi8(4);
+    __mmask64 all_ok = ~0ull;
+    for (; hw + 2 <= hw_end && (hw + 2) * 32 <= len; hw += 2) {
+        const __m512i v = _mm512_loadu_si512(seq + hw * 32);
+        const uint64_t c1 = _mm512_test_epi8_mask(v, b1), c2 = _mm512_test_epi8_mask(v, b2);  // c.bit1, c.bit2 per base
+        const uint64_t p0 = ~(c1 ^ c2), p1 = ~c2;  // negated rank bits: rank.bit0 = c.bit1 ^ c.bit2, rank.bit1 = c.bit2
+        out[2 * hw] = (uint32_t)p0;
+        out[2 * hw + 1] = (uint32_t)p1;
+        out[2 * hw + 2] = (uint32_t)(p0 >> 32);
+        out[2 * hw + 3] = (uint32_t)(p1 >> 32);
+        all_ok &= _mm512_cmpeq_epi8_mask(v, cA) | _mm512_cmpeq_epi8_mask(v, cC) | _mm512_cmpeq_epi8_mask(v, cG) | _mm512_cmpeq_epi8_mask(v, cT);
+    }
+    if (all_ok != ~0ull) *bad = 1;
+    return hw;
+}
+
 extern "C" int apa_pack_planes_host(const uint8_t* seq, int64_t len, int64_t hw_begin, int64_t hw_end, uint32_t* out) {
     int bad = 0;
+    static const bool has512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f");
+    if (has512) hw_begin = pack_planes_avx512(seq, len, hw_begin, hw_end, out, &bad);
     const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
     for (int64_t hw = hw_begin; hw < hw_end; hw++) {
         const int64_t j0 = hw * 32;

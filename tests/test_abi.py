@@ -47,3 +47,34 @@ def test_generator_is_deterministic(apa):
     assert (a1, b1) == (a2, b2) and len(a1) == 1000 and set(a1 + b1) <= set(b"ACGT")
     aa, ao, bb, bo = apa.generate_batch(3, 1000, 0.05, 0, 31415, threads=2)
     assert aa[:1000].tobytes() == a1 and bb[bo[0]:bo[1]].tobytes() == b1
+
+
+def test_host_packer_matches_layout(apa):
+    """apa_pack_planes_host (K0, BitProfile::build layout, pa-bitpacking/src/profile.rs:112-133): negated rank-bit planes per
+    32 bases, zero padding, ACGT validation — AVX2 / AVX-512 bodies against a scalar restatement, for ragged lengths and
+    segment starts (the engine packs long sequences in segments)."""
+    import numpy as np
+    L = apa.load_library()
+    L.apa_pack_planes_host.restype = ctypes.c_int
+    L.apa_pack_planes_host.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+    rng = np.random.default_rng(5)
+    rank = {65: 0, 67: 1, 71: 2, 84: 3}
+    for n in [0, 1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000, 4097]:
+        seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n).astype(np.uint8)
+        nhw = ((n + 63) // 64) * 2 + 2
+        ref = np.zeros(2 * nhw, dtype=np.uint32)
+        for i, c in enumerate(seq):
+            r = rank[int(c)]
+            ref[2 * (i // 32)] |= np.uint32(((r & 1) ^ 1) << (i % 32))
+            ref[2 * (i // 32) + 1] |= np.uint32(((r >> 1) ^ 1) << (i % 32))
+        buf = np.ascontiguousarray(np.concatenate([seq, np.zeros(64, np.uint8)]))
+        for h0 in (0, 1, 2, 3):
+            if h0 >= nhw:
+                continue
+            out = ref.copy()
+            out[2 * h0:] = 0xDEADBEEF
+            assert L.apa_pack_planes_host(buf.ctypes.data, n, h0, nhw, out.ctypes.data) == 0
+            assert (out == ref).all(), (n, h0)
+        if n > 40:
+            buf[37] = ord("N")
+            assert L.apa_pack_planes_host(buf.ctypes.data, n, 0, nhw, ref.ctypes.data) == 1

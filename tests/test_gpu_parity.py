@@ -204,6 +204,19 @@ def test_config2_cost_only_batch_gpu(apa, oracle):
             assert int(costs[k]) == oracle.align(pairs[k][0], pairs[k][1], preset, False)[0]
 
 
+@pytest.mark.parametrize("preset", PRESETS)
+def test_fused_kernel_path_gpu(apa, oracle, preset, monkeypatch):
+    # Batches whose per-pair arenas do not fit in HBM run the fused single-kernel path (per-warp arenas, apa_align_kernel_*);
+    # APA_SPLIT=0 forces it. Same bit-exact contract; every register variant.
+    monkeypatch.setenv("APA_SPLIT", "0")
+    rng = np.random.default_rng(23)
+    pairs = [apa.generate_pair(int(rng.integers(0, 9000)), float(rng.choice([0.02, 0.05, 0.15])), int(rng.integers(0, 4)),
+                               int(rng.integers(1 << 40))) for _ in range(96)]
+    for regs in ("64", "48", "40"):
+        monkeypatch.setenv("APA_REGS", regs)
+        _check_pairs(apa, oracle, pairs, preset)
+
+
 def test_bad_input_gpu(apa):
     with pytest.raises(apa.AstarPaError):
         apa.AstarPa2(0, True).align_batch([(b"ACGT", b"ACGT"), (b"ACGN", b"ACGT")])
