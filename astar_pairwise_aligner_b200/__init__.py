@@ -43,7 +43,8 @@ class BatchStats(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libastarpa_c.so")
+    # APA_LIB: an alternative build of the same library (A/B measurements of kernel variants, see csrc/Makefile `ab`)
+    return os.environ.get("APA_LIB") or os.path.join(_HERE, "libastarpa_c.so")
 
 
 def load_library():

@@ -13,36 +13,82 @@
 
 namespace apa {
 
+// APA_DP_V2 (default): the per-column equality word comes from a per-lane table in shared memory (4 words: this lane's 32
+// rows of b against A, C, G, T) indexed by the column's base - one byte load, one IMAD for the address, one word load -
+// instead of an a-mask load and 2 LOP3: the ALU pipe is the one the block DP saturates (profiles/README.md), the FMA pipe
+// and the shared-memory pipe have room. Measured on B200: pass kernel of astarpa2_simple 150.1 -> 137.2 ms per 2 000 pairs,
+// astarpa2_full 47.5 -> 47.1 ms per 10 000 pairs. APA_DP_V2=0 keeps the first formulation (make ab) for A/B measurements.
+#ifndef APA_DP_V2
+#define APA_DP_V2 1
+#endif
+
 struct WarpSmem {
+#if APA_DP_V2
+    uint32_t etab[4 * 32];   // etab[c * 32 + lane]: BitProfile::eq of base c against the 32 rows of b this lane owns
+    uint8_t achar[BLOCK_W + 4];  // per column of the current block: rank of a[i] (A0 C1 G2 T3, profile.rs:113); +4: zero
+                                 // padding, the steady loop of dp_chunk fetches one column ahead
+#else
     uint2 amask[BLOCK_W];   // per column of the current block: (0 - rank bit0, 0 - rank bit1) of a[i]  (profile.rs:117-121)
+#endif
     uint8_t hrow[BLOCK_W];  // bottom horizontal deltas of the previous chunk: bit0 = +1, bit1 = -1
-    int32_t dt_i[2][96];    // DT-trace fronts of the current and previous level: column reached on diagonal d at [d + 48]
+    alignas(8) int32_t dt_i[2][96];  // (8-byte aligned: the build kernel keeps its uint2 plane windows here) DT-trace fronts of the current and previous level: column reached on diagonal d at [d + 48]
 };
 
-// The constant 2 as an operand the assembler cannot fold: (h << 1) | carry is issued as IMAD h, c[2], carry on the FMA
-// pipe instead of a funnel shift on the ALU pipe, which is the saturated pipe of the block DP (profiles/README.md).
+// Constants as operands the assembler cannot fold: (h << 1) | carry is issued as IMAD h, c[2], carry and the table
+// address as IMAD c, c[128], base on the FMA pipe instead of shifts / LEAs on the ALU pipe.
 __constant__ uint32_t c_two = 2u;
+__constant__ uint32_t c_128 = 128u;
 
-// One 32-row x 1-column Myers step (myers.rs:27-55 on a 32-bit word).
+// One 32-row x 1-column Myers step (myers.rs:27-55 on a 32-bit word) for a given equality word.
 // cp_in/cm_in: the horizontal delta entering this lane's top row, as 0/1 flags (+1 / -1), i.e. bit 31 of the hp/hm
 // words of the lane above. cp_out/cm_out: the same for the delta leaving at the bottom.
-__device__ __forceinline__ void myers_step(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t& vp, uint32_t& vm,
-                                           uint32_t cp_in, uint32_t cm_in, uint32_t& cp_out, uint32_t& cm_out) {
-    uint32_t eq = (a0 ^ b0) & (a1 ^ b1);  // BitProfile::eq, profile.rs:141-144 (b planes are stored negated)
+__device__ __forceinline__ void myers_step_eq(uint32_t eq, uint32_t& vp, uint32_t& vm, uint32_t cp_in, uint32_t cm_in,
+                                              uint32_t& cp_out, uint32_t& cm_out) {
     uint32_t vx = eq | vm;
     uint32_t eq2 = eq | cm_in;            // `eq |= h0.m`: the input delta may be -1 (myers.rs:31-32)
     uint32_t hx = (((eq2 & vp) + vp) ^ vp) | eq2;
     uint32_t hp = vm | ~(hx | vp);
     uint32_t hm = vp & hx;
+    uint32_t hps, hms;  // (hp << 1) | h0.p, (hm << 1) | h0.m
+    // Carry out = bit 31: a shift on the ALU pipe. Measured alternatives on B200 (profiles/README.md, r1c): IMAD.HI
+    // (h * 2 >> 32) and IMAD.WIDE are slower than the shift they replace (multi-pass on the FMA pipe).
     cp_out = hp >> 31;
     cm_out = hm >> 31;
-    uint32_t hps, hms;  // (hp << 1) | h0.p, (hm << 1) | h0.m
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hps) : "r"(hp), "r"(c_two), "r"(cp_in));
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hms) : "r"(hm), "r"(c_two), "r"(cm_in));
     vp = hms | ~(vx | hps);
     vm = hps & vx;
 }
 
+#if APA_DP_V2
+// Stage the bases of columns [col_s, col_s + ncols) into shared memory from the packed planes of a (col_s is a multiple
+// of 256, so the block starts on a half-word boundary; stored planes are negated rank bits). One lane per 4 columns:
+// the 4 bits of each plane are spread to the low bits of 4 bytes with a multiply.
+__device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restrict__ aprof, I col_s, int ncols, int lane) {
+    const int hw0 = col_s >> 5;
+    const int nw = (ncols >> 2) + 1;  // one word past the last column: the steady loop of dp_chunk fetches one column ahead
+    for (int w = lane; w < nw; w += 32) {
+        uint32_t word = 0u;
+        if (4 * w < ncols) {
+            const uint2 pl = aprof[hw0 + (w >> 3)];
+            const int sh = (w & 7) * 4;
+            const uint32_t n0 = (~pl.x >> sh) & 15u, n1 = (~pl.y >> sh) & 15u;
+            word = ((n0 * 0x00204081u) & 0x01010101u) | (((n1 * 0x00204081u) & 0x01010101u) << 1);
+        }
+        ((uint32_t*)sm.achar)[w] = word;
+    }
+    __syncwarp();
+}
+// The equality words of this lane's rows (negated planes b0, b1 of 32 rows of b) against the four bases:
+// eq = (a0 ^ b0) & (a1 ^ b1) with a0 / a1 = all-ones where the rank bit of a's base is set (profile.rs:141-144).
+// Each lane reads back only what it wrote, so no synchronisation is needed.
+__device__ __forceinline__ void stage_etab(WarpSmem& sm, uint32_t b0, uint32_t b1, int lane) {
+    sm.etab[0 * 32 + lane] = b0 & b1;
+    sm.etab[1 * 32 + lane] = ~b0 & b1;
+    sm.etab[2 * 32 + lane] = b0 & ~b1;
+    sm.etab[3 * 32 + lane] = ~b0 & ~b1;
+}
+#else
 // Stage the a-masks of columns [col_s, col_s + ncols) into shared memory from the packed planes of a
 // (col_s is a multiple of 256, so the block starts on a half-word boundary). Stored planes are negated rank bits:
 // mask = 0 - rank_bit = stored_bit - 1.
@@ -54,6 +100,7 @@ __device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restric
     }
     __syncwarp();
 }
+#endif
 
 // One chunk of the wavefront: `nact` lanes take part, lane l working on column t - l at step t.
 // FIRST (the chunk touches the top edge of the band, where +1 deltas enter): lane 0 is a FEEDER, not a row. Its state
@@ -72,35 +119,65 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
     const bool is_bot = lane == nact - 1;
     const int r = act_lane ? lane : 0;  // idle lanes shadow lane 0 on valid addresses; their results are never stored
     uint32_t cp_o = FIRST ? 1u : 0u, cm_o = 0u;  // the feeder's constant output (idle lanes carry it too, unused)
-    auto step = [&](int t, bool guarded) {
-        uint32_t cpi = __shfl_up_sync(FULL, cp_o, 1);
-        uint32_t cmi = __shfl_up_sync(FULL, cm_o, 1);
+#if APA_DP_V2
+    stage_etab(sm, b0, b1, lane);
+    __syncwarp();
+    const uint32_t etab_lane = (uint32_t)__cvta_generic_to_shared(&sm.etab[lane]);
+    // eq word of this lane's rows against column `col`: etab[achar[col] * 32 + lane]; the address is one IMAD
+    auto load_eq = [&](int col) -> uint32_t {
+        uint32_t eaddr;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(eaddr) : "r"((uint32_t)sm.achar[col]), "r"(c_128), "r"(etab_lane));
+        return *(const uint32_t*)__cvta_shared_to_generic(eaddr);
+    };
+#else
+    auto load_eq = [&](int col) -> uint32_t {
+        uint2 am = sm.amask[col];
+        return (am.x ^ b0) & (am.y ^ b1);  // BitProfile::eq, profile.rs:141-144 (b planes are stored negated)
+    };
+#endif
+    auto carries_in = [&](int t, uint32_t& cpi, uint32_t& cmi) {
+        cpi = __shfl_up_sync(FULL, cp_o, 1);
+        cmi = __shfl_up_sync(FULL, cm_o, 1);
         if (!FIRST) {
             uint32_t x = sm.hrow[min(t, ncols - 1)];
             cpi = is_top ? (x & 1u) : cpi;
             cmi = is_top ? (x >> 1) : cmi;
         }
-        const int col = t - r;
-        if (!guarded || (unsigned)col < (unsigned)ncols) {
-            uint2 am = sm.amask[col];
-            myers_step(am.x, am.y, b0, b1, vp, vm, cpi, cmi, cp_o, cm_o);
-            if (HAND_OFF) {
-                if (is_bot) sm.hrow[col] = (uint8_t)(cp_o | (cm_o << 1));
-            }
-            if (FILL) {
-                if (is_row) fillcol[(size_t)col * nhw] = make_uint2(vp, vm);
-            }
+    };
+    auto step_core = [&](int col, uint32_t eq, uint32_t cpi, uint32_t cmi) {
+        myers_step_eq(eq, vp, vm, cpi, cmi, cp_o, cm_o);
+        if (HAND_OFF) {
+            if (is_bot) sm.hrow[col] = (uint8_t)(cp_o | (cm_o << 1));
         }
+        if (FILL) {
+            if (is_row) fillcol[(size_t)col * nhw] = make_uint2(vp, vm);
+        }
+    };
+    // ramp-up / ramp-down step: lanes whose column is outside the block only take part in the shuffles
+    auto step_guarded = [&](int t) {
+        uint32_t cpi, cmi;
+        carries_in(t, cpi, cmi);
+        const int col = t - r;
+        if ((unsigned)col < (unsigned)ncols) step_core(col, load_eq(col), cpi, cmi);
     };
     int t = 0;
     const int t_steady = min(nact - 1, ncols);  // first step at which every active lane has a valid column
-    for (; t < t_steady; t++) step(t, true);
+    for (; t < t_steady; t++) step_guarded(t);
     if (nact - 1 < ncols) {
+        // steady state: every lane has a valid column; the eq word of the next step is fetched one step ahead
+        // (achar is padded, so the fetch past the last column of lane 0 stays in bounds)
+        uint32_t eq_next = load_eq(t - r);
 #pragma unroll 4
-        for (; t < ncols; t++) step(t, false);
+        for (; t < ncols; t++) {
+            const uint32_t eq = eq_next;
+            eq_next = load_eq(t + 1 - r);
+            uint32_t cpi, cmi;
+            carries_in(t, cpi, cmi);
+            step_core(t - r, eq, cpi, cmi);
+        }
     }
     const int T = ncols + nact - 1;
-    for (; t < T; t++) step(t, true);
+    for (; t < T; t++) step_guarded(t);
 }
 
 // Compute the right-edge column of a block.

@@ -131,7 +131,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
             } else {
                 GcshH hh;
                 long long t0 = APA_TIC();
-                bool built = gcsh_build(cx, hh);
+                bool built = gcsh_build(cx, sm, hh);
                 APA_TOC(cx.tphase[0], t0);
                 if (built) {
                     Cost h0 = hh.h(0, 0);
@@ -246,7 +246,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
             cx.dbg_n = 0;
             if (cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
             GcshH hh;
-            if (cx.status == ST_PENDING && bd.preset == APA_PRESET_FULL) gcsh_build(cx, hh);
+            if (cx.status == ST_PENDING && bd.preset == APA_PRESET_FULL) gcsh_build(cx, sm, hh);
             __syncwarp();
             if (lane == 0) {
                 ps->cx = cx;

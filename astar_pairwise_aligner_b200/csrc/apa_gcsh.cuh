@@ -248,10 +248,105 @@ struct NmpdView {  // next_match_per_diag (matches.rs:147-148): diagonal -> star
     __device__ __forceinline__ I get(I d) const { return (d < dmin || d > dmax) ? INT32_MAX : vb[d]; }
 };
 
+#ifndef APA_PRUNE_WIN  // 1: stage the plane windows of a local-pruning check in shared memory (measured slower: the
+#define APA_PRUNE_WIN 0  // direct loads hit L1, 83 % hit rate in the build kernel, and the staging adds two warp syncs per hit)
+#endif
+#if APA_PRUNE_WIN
+// Windows of the packed planes staged in shared memory for one local-pruning check: the check only ever looks at
+// a[ei, end_i) (<= 13 seeds = 156 bases) and b[ej, ej + 156 + 14), so one coalesced load per sequence replaces the two
+// dependent global loads every diagonal extension would otherwise issue (the build kernel is latency-bound).
+struct PruneWin {
+    uint2 a[8];   // plane words (ei >> 5) + 0..7 of a
+    uint2 b[10];  // plane words (ej >> 5) + 0..8 of b
+};
+static_assert(sizeof(PruneWin) <= sizeof(((WarpSmem*)0)->dt_i), "PruneWin lives in the DT-front area of WarpSmem");
+__device__ __forceinline__ uint2 extract32_win(const uint2* w, int hw0, I pos) {
+    const int hw = (pos >> 5) - hw0, sh = pos & 31;
+    const uint2 lo = w[hw], hi = w[hw + 1];
+    return make_uint2(__funnelshift_r(lo.x, hi.x, sh), __funnelshift_r(lo.y, hi.y, sh));
+}
+// extend_right (prepruning.rs:25-32) on the staged windows.
+__device__ __forceinline__ void extend_right_win(const PruneWin& w, int ahw0, int bhw0, I m, I& i, I j, I end_i) {
+    for (;;) {
+        int len = min(32, min(end_i - i, m - j));
+        if (len <= 0) return;
+        uint2 A = extract32_win(w.a, ahw0, i), B = extract32_win(w.b, bhw0, j);
+        uint32_t mm = (A.x ^ B.x) | (A.y ^ B.y);
+        if (len < 32) mm |= 0xffffffffu << len;
+        int run = mm ? __ffs(mm) - 1 : 32;
+        i += run;
+        j += run;
+        if (run < 32) return;
+    }
+}
+
 // preserve_for_local_pruning (prepruning.rs:95-203) for an exact match of seed `seed` starting at (seed * k, sj).
 // Warp-uniform result. Potentials in closed form: P(seed * k) = ns - seed.
-__device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I seed, I sj,
-                                               const NmpdView& nm) {
+__device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin& win, const uint2* __restrict__ ap, const uint2* __restrict__ bp,
+                                               I seed, I sj, const NmpdView& nm) {
+    const int lane = threadIdx.x & 31;
+    const I si = seed * GCSH_K;
+    const I ei = si + GCSH_K, ej = sj + GCSH_K;
+    const Cost start_pot = H.nseeds - seed;
+    const I last = min(seed + GCSH_P - 1, H.nseeds - 1);
+    const I end_i = (last + 1) * GCSH_K;
+    const int pd = last + 1 - seed;  // start_pot - P(end_i), <= GCSH_P
+    // lanes 0 .. 2*pd hold the front; lane d <-> diagonal e + (d - pd)
+    const I dd = ei - ej + (lane - pd);  // this lane's diagonal
+    // One round trip: the plane windows (lanes 0..7: a, 8..17: b) and this lane's next_match_per_diag entry.
+    const int ahw0 = ei >> 5, bhw0 = ej >> 5;
+    __syncwarp();  // the previous check's readers are done
+    if (lane < 8)
+        win.a[lane] = ap[min(ahw0 + lane, ((H.n + 63) >> 6) * 2 + 1)];
+    else if (lane < 18)
+        win.b[lane - 8] = bp[min(bhw0 + lane - 8, ((H.m + 63) >> 6) * 2 + 1)];
+    const I nmv = nm.get(dd);
+    __syncwarp();
+    // g = 0
+    I f0 = ei;
+    extend_right_win(win, ahw0, bhw0, H.m, f0, ej, end_i);
+    if (f0 >= end_i) return true;
+    if (__shfl_sync(FULL, nmv, pd) <= f0) return true;
+    I fr = (lane == pd) ? f0 : INT32_MIN;
+    int lo = pd, hi = pd + 1;  // d_range
+    for (Cost g = 1; g < pd; g++) {
+        // expand: next[d] = max(fr[d+1], fr[d] + 1, fr[d-1] + 1) over sources inside d_range
+        I up = __shfl_down_sync(FULL, fr, 1);  // fr[d+1]
+        I dn = __shfl_up_sync(FULL, fr, 1);    // fr[d-1]
+        I nx = INT32_MIN;
+        if (lane + 1 >= lo && lane + 1 < hi) nx = max(nx, up);
+        if (lane >= lo && lane < hi) nx = max(nx, fr + 1);
+        if (lane - 1 >= lo && lane - 1 < hi) nx = max(nx, dn + 1);
+        fr = nx;
+        lo -= 1;
+        hi += 1;
+        // check & shrink
+        bool in = lane >= lo && lane < hi;
+        bool dead = in && (g + H.pot(fr) >= start_pot);
+        unsigned alive = __ballot_sync(FULL, in && !dead);
+        if (alive == 0) return false;
+        lo = __ffs(alive) - 1;
+        hi = 32 - __clz(alive);
+        // extend
+        in = lane >= lo && lane < hi;
+        bool ok = false;
+        if (in) {
+            I j = fr - dd;
+            I old_i = fr;
+            extend_right_win(win, ahw0, bhw0, H.m, fr, j, end_i);
+            ok = (fr >= end_i) || (old_i <= nmv && nmv <= fr);
+        }
+        if (__any_sync(FULL, ok)) return true;
+    }
+    return false;
+}
+
+#else
+struct PruneWin {};
+// preserve_for_local_pruning (prepruning.rs:95-203) for an exact match of seed `seed` starting at (seed * k, sj).
+// Warp-uniform result. Potentials in closed form: P(seed * k) = ns - seed.
+__device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin&, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I seed,
+                                               I sj, const NmpdView& nm) {
     const int lane = threadIdx.x & 31;
     const I si = seed * GCSH_K;
     const I ei = si + GCSH_K, ej = sj + GCSH_K;
@@ -301,13 +396,16 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, const uint2* __re
     return false;
 }
 
+#endif
+
 constexpr uint32_t KMER_MUL = 0x9E3779B1u;
 constexpr uint32_t STAGE_MULTI = 0x40000000u;  // staged hit whose k-mer occurs in several seeds of a
 
 // CSHI::new (csh.rs:199-308): find matches, filter, sort, build the pruner state and the contours.
 // All scratch comes from the pair's arena; structures that die after the precomputation are placed last so the
 // block store can reuse their space. Returns false on arena overflow (cx.status set).
-__device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
+__device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
+    PruneWin& win = *(PruneWin*)sm.dt_i;
     const int lane = threadIdx.x & 31;
     const I n = cx.n, m = cx.m;
     H.n = n;
@@ -443,6 +541,7 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
             if (nwin < 32) surv &= (1u << nwin) - 1u;
         }
         int nh = 0;
+        uint2 st0 = make_uint2(0u, 0u), st1 = make_uint2(0u, 0u);
         while (__any_sync(FULL, surv != 0u)) {
             if (surv) {
                 const int sft = 31 - __clz(surv);  // highest j first
@@ -450,8 +549,14 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
                 const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GCSH_K);
                 int c;
                 const I seed0 = probe(key, -1, c);
-                if (c > 0) {
-                    stage[lane * 32 + nh] = make_uint2((uint32_t)(wbase + sft), (uint32_t)seed0 | (c > 1 ? STAGE_MULTI : 0u));
+                if (c > 0) {  // the first two hits of a lane stay in registers (1.7 hits per lane and round on average)
+                    const uint2 rec = make_uint2((uint32_t)(wbase + sft), (uint32_t)seed0 | (c > 1 ? STAGE_MULTI : 0u));
+                    if (nh == 0)
+                        st0 = rec;
+                    else if (nh == 1)
+                        st1 = rec;
+                    else
+                        stage[lane * 32 + nh] = rec;
                     nh++;
                 }
             }
@@ -463,7 +568,13 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
             has &= has - 1;
             const int cntl = __shfl_sync(FULL, nh, l);
             for (int hh = 0; hh < cntl; hh++) {
-                const uint2 rec = stage[l * 32 + hh];
+                uint2 rec;
+                if (hh < 2) {
+                    rec.x = __shfl_sync(FULL, hh == 0 ? st0.x : st1.x, l);
+                    rec.y = __shfl_sync(FULL, hh == 0 ? st0.y : st1.y, l);
+                } else {
+                    rec = stage[l * 32 + hh];
+                }
                 const I jj = (I)rec.x;
                 I seed = (I)(rec.y & ~STAGE_MULTI);
                 const bool multi = (rec.y & STAGE_MULTI) != 0u;
@@ -472,7 +583,7 @@ __device__ bool gcsh_build(PairCtx& cx, GcshH& H) {
                     const I si = seed * GCSH_K;
                     const Cost p = ns - seed;  // P(si)
                     const bool pass_t = (si - jj - p <= H.ttx) && (jj - si - p <= H.tty);
-                    if (pass_t && dev_preserve_for_local_pruning(H, ap, bp, seed, jj, nm)) {
+                    if (pass_t && dev_preserve_for_local_pruning(H, win, ap, bp, seed, jj, nm)) {
                         if (M >= mcap) {
                             cx.status = ST_OVERFLOW;
                             return false;
