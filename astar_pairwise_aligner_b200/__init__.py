@@ -16,8 +16,8 @@ import os
 
 import numpy as np
 
-__all__ = ["AstarPa2", "AstarPaError", "Engine", "astarpa2_simple", "astarpa2_full", "generate_pair", "generate_batch",
-           "PRESET_SIMPLE", "PRESET_FULL", "lib_path", "load_library"]
+__all__ = ["AstarPa2", "AstarPa2Params", "AstarPaError", "Engine", "astarpa2_simple", "astarpa2_full", "generate_pair",
+           "generate_batch", "PRESET_SIMPLE", "PRESET_FULL", "lib_path", "load_library"]
 
 PRESET_SIMPLE, PRESET_FULL = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -40,6 +40,52 @@ class BatchStats(C.Structure):
         d["phase_cycles"] = list(d["phase_cycles"])
         d["phase_ms"] = list(d["phase_ms"])
         return d
+
+
+class AstarPa2Params(C.Structure):
+    """``apa_params`` (include/astarpa_b200.h): the flat AstarPa2Params of the reference (astarpa2/src/params.rs:8-42).
+
+    ``AstarPa2Params.simple()`` / ``.full()`` are the presets; ``.nw()`` is the full n*m alignment (params.rs:46-68);
+    other configurations are built by setting fields, e.g. the reference's test matrix (astarpa2/src/tests.rs:19-119)."""
+    DOMAIN = {"full": 0, "gap_start": 1, "gap_gap": 2, "astar": 3}
+    HEURISTIC = {"none": 0, "gap": 1, "gcsh": 2}
+    DOUBLING = {"none": 0, "band_doubling": 1, "linear_search": 2}
+    START = {"zero": 0, "gap": 1, "h0": 2}
+    _fields_ = [("domain", C.c_int32), ("heuristic", C.c_int32), ("k", C.c_int32), ("r", C.c_int32), ("p", C.c_int32),
+                ("doubling", C.c_int32), ("doubling_start", C.c_int32), ("factor", C.c_float), ("delta", C.c_int32),
+                ("block_width", C.c_int32), ("sparse", C.c_int32), ("incremental_doubling", C.c_int32), ("dt_trace", C.c_int32),
+                ("max_g", C.c_int32), ("fr_drop", C.c_int32), ("sparse_h", C.c_int32), ("prune", C.c_int32)]
+
+    @classmethod
+    def _preset(cls, preset):
+        q = cls()
+        _check(load_library().apa_params_preset(preset, C.byref(q)))
+        return q
+
+    @classmethod
+    def simple(cls):
+        return cls._preset(PRESET_SIMPLE)
+
+    @classmethod
+    def full(cls):
+        return cls._preset(PRESET_FULL)
+
+    @classmethod
+    def nw(cls):
+        """AstarPa2Params::nw() (params.rs:46-68): Domain::Full, no doubling, no dt_trace."""
+        q = cls._preset(PRESET_SIMPLE)
+        q.domain, q.heuristic, q.doubling, q.dt_trace, q.sparse_h, q.prune = 0, 0, 0, 0, 0, 0
+        return q
+
+    def replace(self, **kw):
+        """Copy with fields replaced; domain / heuristic / doubling / doubling_start also accept their names."""
+        q = type(self).from_buffer_copy(self)
+        names = {"domain": self.DOMAIN, "heuristic": self.HEURISTIC, "doubling": self.DOUBLING, "doubling_start": self.START}
+        for k, v in kw.items():
+            if isinstance(v, str):
+                v = names[k][v]
+            setattr(q, k, v)
+        return q
 
 
 def lib_path():
@@ -69,6 +115,13 @@ def load_library():
     L.apa_batch_free.argtypes = [C.c_void_p, C.c_void_p]
     L.apa_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(C.c_void_p), vp, vp,
                                   C.POINTER(BatchStats)]
+    pp = C.POINTER(AstarPa2Params)
+    L.apa_params_preset.argtypes = [C.c_int, pp]
+    L.apa_batch_run_params.argtypes = [C.c_void_p, C.c_void_p, pp, C.c_int]
+    L.apa_align_batch_params.argtypes = [C.c_void_p, pp, C.c_int, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(C.c_void_p), vp, vp,
+                                         C.POINTER(BatchStats)]
+    L.apa_debug_band_log_params.restype = C.c_int64
+    L.apa_debug_band_log_params.argtypes = [C.c_void_p, pp, C.c_int, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64]
     L.apa_free.argtypes = [C.c_void_p]
     L.apa_pinned_alloc.restype = C.c_void_p
     L.apa_pinned_alloc.argtypes = [C.c_uint64]
@@ -182,8 +235,12 @@ class Engine:
         st = BatchStats()
         ap = a_all.ctypes.data if a_all.size else None
         bp = b_all.ctypes.data if b_all.size else None
-        _check(self._L.apa_align_batch(self._h, preset, int(trace), n, ap, a_off.ctypes.data, bp, b_off.ctypes.data, costs.ctypes.data,
-                                       C.byref(pool), off.ctypes.data, ln.ctypes.data, C.byref(st)))
+        if isinstance(preset, AstarPa2Params):  # explicit parameters: the general kernel
+            _check(self._L.apa_align_batch_params(self._h, C.byref(preset), int(trace), n, ap, a_off.ctypes.data, bp, b_off.ctypes.data,
+                                                  costs.ctypes.data, C.byref(pool), off.ctypes.data, ln.ctypes.data, C.byref(st)))
+        else:
+            _check(self._L.apa_align_batch(self._h, preset, int(trace), n, ap, a_off.ctypes.data, bp, b_off.ctypes.data,
+                                           costs.ctypes.data, C.byref(pool), off.ctypes.data, ln.ctypes.data, C.byref(st)))
         return costs[:n], pool, off[:n], ln[:n], st.as_dict()
 
     def free_pool(self, pool):
@@ -227,7 +284,10 @@ class Batch:
         self._h = h
 
     def run(self, preset=PRESET_FULL, trace=True):
-        _check(self._L.apa_batch_run(self._eng._h, self._h, preset, int(trace)))
+        if isinstance(preset, AstarPa2Params):
+            _check(self._L.apa_batch_run_params(self._eng._h, self._h, C.byref(preset), int(trace)))
+        else:
+            _check(self._L.apa_batch_run(self._eng._h, self._h, preset, int(trace)))
         return self
 
     def download(self, cigars=True):
@@ -300,10 +360,11 @@ def _engine(device=0):
 
 
 class AstarPa2:
-    """Mirror of ``AstarPa2Params::{simple,full}().make_aligner(trace)`` (astarpa2/src/params.rs:70-132)."""
+    """Mirror of ``AstarPa2Params::{simple,full}().make_aligner(trace)`` (astarpa2/src/params.rs:70-132), or of
+    ``params.make_aligner(trace)`` for an explicit ``AstarPa2Params`` (served by the general kernel)."""
 
     def __init__(self, preset="full", trace=True, device=0):
-        self.preset = {"simple": PRESET_SIMPLE, "full": PRESET_FULL, 0: 0, 1: 1}[preset]
+        self.preset = preset if isinstance(preset, AstarPa2Params) else {"simple": PRESET_SIMPLE, "full": PRESET_FULL, 0: 0, 1: 1}[preset]
         self.trace = trace
         self.device = device
 

@@ -7,9 +7,10 @@
 // both give the same V column (blocks.rs:471-543), and the oracle's differential check confirms it. The
 // reuse *decision* is still tracked because it keeps the old original_j_range (domain.rs:451-455, blocks.rs:190-197).
 #pragma once
+#include "apa_batch.cuh"
 #include "apa_blockdp.cuh"
 
-namespace apa {
+namespace APA_NS {
 
 // Everything one warp needs to know about its pair.
 struct PairCtx {
@@ -21,6 +22,7 @@ struct PairCtx {
     BlkMeta* meta;       // nblk + 1 entries (entry 0 = column 0)
     int nblk;            // number of 256-column blocks
     int nblk_alloc;      // blocks.len() of the reference: entries [0, nblk_alloc) hold ranges of an earlier pass
+    int last_idx;        // Blocks.last_block_idx: survives from one pass to the next (see dev_pass, column 0)
     uint32_t v_base;     // start of the V region in the arena (bytes)
     uint32_t v_top;      // bump pointer
     uint32_t hi_bot;     // lowest byte used by the downward-growing region at the arena end (CIGAR elements)
@@ -35,7 +37,33 @@ struct PairCtx {
     // optional band log (apa_debug_band_log): records of 7 ints {pass, f_max, block, j_s, j_e, fixed_s, fixed_e}
     int32_t* dbg;
     uint32_t dbg_cap, dbg_n;
+#if APA_GENERAL
+    RunParams par;
+#endif
 };
+
+// Parameters of the search: compile-time constants of the two presets (params.rs:70-128), or RunParams in the general build.
+enum : int { DOM_FULL = 0, DOM_GAPSTART = 1, DOM_GAPGAP = 2, DOM_ASTAR = 3 };
+constexpr Cost F_MAX_NONE = -1;  // align_for_bounded_dist(f_max = None): DoublingType::None (lib.rs:126-130)
+#if APA_GENERAL
+#define P_BW(cx) ((cx).par.block_width)
+#define P_ASTAR(cx) ((cx).par.domain == DOM_ASTAR)
+#define P_SPARSE_H(cx) ((cx).par.sparse_h != 0)
+#define P_PRUNE(cx) ((cx).par.prune != 0)
+#define P_DT_TRACE(cx) ((cx).par.dt_trace != 0)
+#define P_FR_DROP(cx) ((cx).par.fr_drop)
+#define P_MAX_G(cx) ((cx).par.max_g)
+#else
+#define P_BW(cx) BLOCK_W
+#define P_ASTAR(cx) true
+#define P_SPARSE_H(cx) true
+#define P_PRUNE(cx) true
+#define P_DT_TRACE(cx) true
+#define P_FR_DROP(cx) DT_FR_DROP
+#define P_MAX_G(cx) DT_MAX_G
+#endif
+constexpr int DT_MAX_G = 40;    // BlockParams.max_g of both presets and of BlockParams::default() (params.rs:91,122, blocks.rs:66)
+constexpr int DT_FR_DROP = 10;  // BlockParams.fr_drop of the presets (params.rs:92,123)
 
 __device__ __forceinline__ void dbg_log(PairCtx& cx, Cost f_max, int t, JRange jr, JRange fx) {
     if (!cx.dbg) return;
@@ -89,47 +117,88 @@ struct GapH {
     __device__ __forceinline__ void update_contours() {}
 };
 
+// NoCost (pa-heuristic/src/heuristic/distances.rs): h = 0, Dijkstra; also the placeholder of the non-A* domains.
+struct NoneH {
+    static constexpr bool PRUNE = false;
+    __device__ __forceinline__ Cost h(I, I, int = 3) const { return 0; }
+    __device__ __forceinline__ void prune_block(I, I, I, I) {}
+    __device__ __forceinline__ void update_contours() {}
+};
+
 // ---------------------------------------------------------------------------------------------- band selection
 // AstarPa2Instance::j_range for Domain::Astar with sparse_h (domain.rs:77-246). prev_fixed is the fixed range of
 // the previous column, gu the value at its end (0 for the virtual column -1).
 template <class Hh>
 __device__ JRange dev_j_range(const PairCtx& cx, Hh& hh, I is, I ie, Cost f_max, JRange prev_fixed, const BlkView* prev,
                               bool has_old, JRange old_range) {
+#if APA_GENERAL
+    if (f_max == F_MAX_NONE) return JRange{0, cx.m};  // domain.rs:84-86
+    if (!P_ASTAR(cx)) {  // domain.rs:93-112
+        JRange range{0, cx.m};
+        if (cx.par.domain == DOM_GAPSTART) {
+            range = JRange{is + 1 - f_max, ie + f_max};
+        } else if (cx.par.domain == DOM_GAPGAP) {
+            const I d = cx.m - cx.n;
+            const Cost s = f_max - (d < 0 ? -d : d);
+            const I extra = s / 2;  // Rust '/' truncates toward zero, like C
+            range = JRange{is + 1 + min(d, 0) - extra, ie + max(d, 0) + extra};
+        }
+        if (has_old) range = jr_union(range, old_range);
+        return jr_inter(range, JRange{0, cx.m});
+    }
+#endif
     I fixed_start = prev_fixed.s, fixed_end = prev_fixed.e;
     I ui = is, uj = fixed_end;
     Cost gu = is < 0 ? 0 : blk_index(*prev, fixed_end);
     I vi = ui + 1, vj = uj + 1;
-    vj += BLOCK_W;
-    vj = min(vj, cx.m);
-    for (;;) {
-        if (vj < vi - ui + uj) {
-            vj = vi - ui + uj;
-            break;
-        }
-        I dd = (vi - ui) - (vj - uj);
-        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj, 0);
-        if (fv <= f_max) {
-            if (vj == cx.m) break;
-            vj += 8;
-            if (vj >= cx.m) vj = cx.m;
-        } else {
-            vi += div_ceil_pos(fv - f_max, 2);
-            if (vi > ie) {
-                vi = ie;
+    if (P_SPARSE_H(cx)) {
+        vj += P_BW(cx);
+        vj = min(vj, cx.m);
+        for (;;) {
+            if (vj < vi - ui + uj) {
+                vj = vi - ui + uj;
                 break;
             }
+            I dd = (vi - ui) - (vj - uj);
+            Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj, 0);
+            if (fv <= f_max) {
+                if (vj == cx.m) break;
+                vj += 8;
+                if (vj >= cx.m) vj = cx.m;
+            } else {
+                vi += div_ceil_pos(fv - f_max, 2);
+                if (vi > ie) {
+                    vi = ie;
+                    break;
+                }
+            }
         }
-    }
-    vi = ie;
-    for (;;) {
-        if (vj < vi - ui + uj) {
-            vj = vi - ui + uj;
-            break;
+        vi = ie;
+        for (;;) {
+            if (vj < vi - ui + uj) {
+                vj = vi - ui + uj;
+                break;
+            }
+            I dd = (vi - ui) - (vj - uj);
+            Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj, 0);
+            if (fv <= f_max) break;
+            vj -= div_ceil_pos(fv - f_max, 2);
         }
-        I dd = (vi - ui) - (vj - uj);
-        Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj, 0);
-        if (fv <= f_max) break;
-        vj -= div_ceil_pos(fv - f_max, 2);
+    } else {  // domain.rs:150-176: walk down the diagonal one column at a time, extending while f <= f_max
+        vi = ui;
+        vj = uj;
+        while (vi < ie) {
+            vi += 1;
+            vj += 2;
+            for (;;) {
+                if (vj > cx.m) break;
+                I dd = (vi - ui) - (vj - uj);
+                Cost fv = gu + (dd < 0 ? -dd : dd) + hh.h(vi, vj, 0);
+                if (fv > f_max) break;
+                vj += 1;
+            }
+            vj -= 1;
+        }
     }
     JRange range{fixed_start, vj};
     if (has_old) range = jr_union(range, old_range);
@@ -145,12 +214,12 @@ __device__ JRange dev_fixed_j_range(const PairCtx& cx, Hh& hh, I i, Cost f_max, 
     while (start <= end) {
         Cost f = blk_index(blk, start) + hh.h(i, start, 1);
         if (f <= f_max) break;
-        start += div_ceil_pos(f - f_max, 2);
+        start += P_SPARSE_H(cx) ? div_ceil_pos(f - f_max, 2) : 1;
     }
     while (end >= start) {
         Cost f = blk_index(blk, end) + hh.h(i, end, 2);
         if (f <= f_max) break;
-        end -= div_ceil_pos(f - f_max, 2);
+        end -= P_SPARSE_H(cx) ? div_ceil_pos(f - f_max, 2) : 1;
     }
     JRange fixed{start, end};
     if (has_old_fixed) {
@@ -170,7 +239,7 @@ template <class Hh>
 __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
     const int lane = threadIdx.x & 31;
     cx.passes++;
-    if (Hh::PRUNE) {
+    if (Hh::PRUNE && P_PRUNE(cx)) {
         long long t_u0 = APA_TIC();
         hh.update_contours();
         APA_TOC(cx.tphase[7], t_u0);
@@ -181,7 +250,12 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
     BlkMeta* meta = cx.meta;
     BlkMeta m0 = meta[0];
     bool had0 = cx.nblk_alloc > 0;
-    JRange jr0 = dev_j_range(cx, hh, -1, 0, f_max, JRange{-1, -1}, nullptr, had0, JRange{m0.js, m0.je});
+    // The old range handed to j_range for column 0 is next_block_j_range() = blocks[last_block_idx + 1] with
+    // last_block_idx still where the PREVIOUS pass stopped (domain.rs:386-393 runs before Blocks::init resets it): it only
+    // exists when that pass ended before an earlier one did. Blocks::init then unions with blocks[0] (blocks.rs:152-155).
+    const bool had_next = cx.last_idx + 1 < cx.nblk_alloc;
+    const BlkMeta mnext = had_next ? meta[cx.last_idx + 1] : BlkMeta{};
+    JRange jr0 = dev_j_range(cx, hh, -1, 0, f_max, JRange{-1, -1}, nullptr, had_next, JRange{mnext.js, mnext.je});
     if (jr_empty(jr0) || jr0.s > 0) return PASS_NONE;
     {
         JRange init = jr0;
@@ -205,12 +279,13 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         if (lane == 0) meta[0] = nm;
         __syncwarp();
         if (cx.nblk_alloc < 1) cx.nblk_alloc = 1;
+        cx.last_idx = 0;
         dbg_log(cx, f_max, 0, jr0, jr0);
     }
     bool all_reused = true;
     for (int t = 1; t <= cx.nblk; t++) {
-        const I is = (t - 1) * BLOCK_W;
-        const I ie = min(is + BLOCK_W, cx.n);
+        const I is = (t - 1) * P_BW(cx);
+        const I ie = min(is + P_BW(cx), cx.n);
         const BlkMeta pm = meta[t - 1];
         const BlkView prev = view_of(cx, pm);
         const bool existed = t < cx.nblk_alloc;
@@ -257,27 +332,35 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         cur.ones = 0;
 
         const bool has_old_fixed = existed && old.has_fixed;
-        JRange next_fixed = dev_fixed_j_range(cx, hh, ie, f_max, prev_fixed, cur, nm.orig_e, has_old_fixed, JRange{old.fs, old.fe});
-        // The block is stored (with its previous fixed range) even when the pass aborts right after it.
-        JRange stored = next_fixed;
-        bool store_fixed = true;
-        if (jr_empty(next_fixed)) {
-            stored = JRange{old.fs, old.fe};
-            store_fixed = has_old_fixed;
-        } else if (has_old_fixed) {
-            stored = jr_union(JRange{old.fs, old.fe}, next_fixed);  // set_last_block_fixed_j_range, blocks.rs:556-563
+        JRange next_fixed{0, -1};
+        if (P_ASTAR(cx) && f_max != F_MAX_NONE) {
+            next_fixed = dev_fixed_j_range(cx, hh, ie, f_max, prev_fixed, cur, nm.orig_e, has_old_fixed, JRange{old.fs, old.fe});
+            // The block is stored (with its previous fixed range) even when the pass aborts right after it.
+            JRange stored = next_fixed;
+            bool store_fixed = true;
+            if (jr_empty(next_fixed)) {
+                stored = JRange{old.fs, old.fe};
+                store_fixed = has_old_fixed;
+            } else if (has_old_fixed) {
+                stored = jr_union(JRange{old.fs, old.fe}, next_fixed);  // set_last_block_fixed_j_range, blocks.rs:556-563
+            }
+            nm.fs = stored.s;
+            nm.fe = stored.e;
+            nm.has_fixed = store_fixed ? 1 : 0;
+        } else {  // fixed_j_range is None outside Domain::Astar (domain.rs:258-261): the stored range is cleared
+            nm.fs = 0;
+            nm.fe = -1;
+            nm.has_fixed = 0;
         }
-        nm.fs = stored.s;
-        nm.fe = stored.e;
-        nm.has_fixed = store_fixed ? 1 : 0;
         __syncwarp();
         if (lane == 0) meta[t] = nm;
         __syncwarp();
         if (cx.nblk_alloc < t + 1) cx.nblk_alloc = t + 1;
-        if (jr_empty(next_fixed)) return PASS_NONE;
-        dbg_log(cx, f_max, t, jr, stored);
+        cx.last_idx = t;
+        if (P_ASTAR(cx) && f_max != F_MAX_NONE && jr_empty(next_fixed)) return PASS_NONE;
+        dbg_log(cx, f_max, t, jr, JRange{nm.fs, nm.fe});
 
-        if (Hh::PRUNE) {
+        if (Hh::PRUNE && P_PRUNE(cx)) {
             long long t_p0 = APA_TIC();
             JRange inter = jr_inter(prev_fixed, next_fixed);
             if (!jr_empty(inter)) hh.prune_block(is, ie, inter.s, inter.e);
@@ -291,13 +374,35 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
     return blk_index(last, cx.m);
 }
 
-// band::exponential_search driven by cost_or_align (band.rs:100-141, lib.rs:140-159): offset = h0,
-// s0 = max(1, block_width) = 256, factor 2.0. Returns the cost; the blocks of the final pass stay in the arena.
+// band::exponential_search / linear_search driven by cost_or_align (band.rs:100-190, lib.rs:122-175). The presets use
+// BandDoubling{start: H0, factor: 2}: offset = h0, s0 = max(1, block_width) = 256. Returns the cost; the blocks of the
+// final pass stay in the arena.
 template <class Hh>
 __device__ Cost dev_band_doubling(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost h0) {
     Cost offset = h0;
+    Cost s0 = BLOCK_W;
+    float factor = 2.0f;
+    bool linear = false;
+    Cost delta = 0;
+#if APA_GENERAL
+    if (cx.par.doubling == 0) {  // DoublingType::None: one pass without a bound (lib.rs:126-130)
+        Cost cost = dev_pass(cx, sm, hh, F_MAX_NONE);
+        if (cx.status == ST_PENDING && cost == PASS_NONE) cx.status = ST_ASSERT;  // .unwrap()
+        return cost;
+    }
+    {
+        const I gap = cx.n > cx.m ? cx.n - cx.m : cx.m - cx.n;  // DoublingStart::initial_values (band.rs:13-23)
+        Cost start_f = cx.par.start == 0 ? 0 : (cx.par.start == 1 ? gap : h0);
+        Cost start_inc = cx.par.start == 1 ? gap : 1;
+        offset = start_f;
+        s0 = max(start_inc, (Cost)cx.par.block_width);
+        factor = cx.par.factor;
+        linear = cx.par.doubling == 2;
+        delta = cx.par.delta;
+    }
+#endif
     Cost last_s = -1;
-    Cost s = offset + BLOCK_W;
+    Cost s = linear ? offset : offset + s0;
     Cost maxs = INT32_MAX;
     for (;;) {
         Cost cost = dev_pass(cx, sm, hh, s);
@@ -320,10 +425,14 @@ __device__ Cost dev_band_doubling(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost h0) {
             return -1;
         }
         last_s = s;
-        float grown = ceilf(2.0f * (float)(s - offset));
-        s = max((Cost)grown, 1) + offset;
-        s = min(s, maxs);
+        if (linear) {
+            s = min(s + delta, maxs);
+        } else {
+            float grown = ceilf(factor * (float)(s - offset));
+            s = max((Cost)grown, 1) + offset;
+            s = min(s, maxs);
+        }
     }
 }
 
-}  // namespace apa
+}  // namespace APA_NS

@@ -11,7 +11,7 @@
 #pragma once
 #include "apa_common.cuh"
 
-namespace apa {
+namespace APA_NS {
 
 // APA_DP_V2 (default): the per-column equality word comes from a per-lane table in shared memory (4 words: this lane's 32
 // rows of b against A, C, G, T) indexed by the column's base - one byte load, one IMAD for the address, one word load -
@@ -70,8 +70,14 @@ __device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restric
     for (int w = lane; w < nw; w += 32) {
         uint32_t word = 0u;
         if (4 * w < ncols) {
+#if APA_GENERAL  // block widths below 32: the block may start anywhere inside a half-word
+            const uint2 pl = extract32(aprof, col_s + 4 * w);
+            const int sh = 0;
+            (void)hw0;
+#else
             const uint2 pl = aprof[hw0 + (w >> 3)];
             const int sh = (w & 7) * 4;
+#endif
             const uint32_t n0 = (~pl.x >> sh) & 15u, n1 = (~pl.y >> sh) & 15u;
             word = ((n0 * 0x00204081u) & 0x01010101u) | (((n1 * 0x00204081u) & 0x01010101u) << 1);
         }
@@ -249,4 +255,4 @@ __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const Bl
     return running;
 }
 
-}  // namespace apa
+}  // namespace APA_NS

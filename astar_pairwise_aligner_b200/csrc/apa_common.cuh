@@ -20,7 +20,20 @@
 #define APA_TOC(acc, t0) ((void)(t0))
 #endif
 
-namespace apa {
+// The device code is compiled twice: with APA_GENERAL=0 (namespace apa, apa_engine.cu) every AstarPa2 parameter is the
+// compile-time constant of the two presets, which is what the hot path is tuned for; with APA_GENERAL=1 (namespace
+// apa_gen, apa_general.cu) the same code reads them from RunParams at run time (other domains, heuristics, doubling
+// types, block widths: astarpa2/src/params.rs, the configurations of astarpa2/src/tests.rs:19-119).
+#ifndef APA_GENERAL
+#define APA_GENERAL 0
+#endif
+#if APA_GENERAL
+#define APA_NS apa_gen
+#else
+#define APA_NS apa
+#endif
+
+namespace APA_NS {
 
 typedef int32_t I;
 typedef int32_t Cost;
@@ -163,4 +176,4 @@ __device__ __forceinline__ I extend_left_packed(const uint2* __restrict__ ap, co
 enum CigOp : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3 };
 __device__ __forceinline__ uint32_t cig_pack(uint32_t op, uint32_t cnt) { return (op << 30) | cnt; }
 
-}  // namespace apa
+}  // namespace APA_NS

@@ -38,37 +38,8 @@ static int set_err(int code, const std::string& msg) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ kernels
-struct BatchDev {
-    uint64_t n_pairs;
-    const int64_t* a_off;
-    const int64_t* b_off;
-    const int64_t* bp_off;  // per pair offset into bprof, in 32-row half-words (two padding half-words per pair)
-    uint2* bprof;
-    const int64_t* ap_off;  // the same for a
-    uint2* aprof;
-    int32_t* status;  // per pair
-    int32_t* cost;    // per pair
-    int64_t* cig_off;
-    int64_t* cig_len;
-    const uint32_t* order;  // work order (largest first)
-    uint32_t n_order;
-    unsigned long long* queue;  // work-queue head
-    uint8_t* arena;             // n_slots * arena_size
-    uint32_t arena_size;
-    char* pool;
-    unsigned long long* pool_cursor;
-    unsigned long long pool_cap;
-    unsigned long long* stats;  // [0] word_steps [1] computed_cells [2] passes [3] fill_blocks [4] dt_blocks [5..12] phase cycles
-    int preset;
-    int trace;
-    uint32_t q0;        // phase-split path: first work-order position of this wave (arena slot = q - q0)
-    const volatile uint32_t* ready;  // streaming upload: number of pairs (in work order) whose bases are in HBM; nullptr = all
-    int32_t* dbg;  // band log of the (single) pair, or nullptr
-    uint32_t dbg_cap;
-    uint32_t* dbg_n;
-};
+#include "apa_batch.cuh"
 
-constexpr int WARPS_PER_CTA = 4;
 
 // K1+K3 fused per pair: a persistent warp pulls pairs from the device work queue and runs the band-doubling
 // search, the traceback and the CIGAR text emission for each.
@@ -103,6 +74,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.arena_size = bd.arena_size;
         cx.nblk = (cx.n + BLOCK_W - 1) / BLOCK_W;
         cx.nblk_alloc = 0;
+        cx.last_idx = 0;
         cx.meta = (BlkMeta*)arena;
         uint32_t meta_bytes = ((uint32_t)(cx.nblk + 1) * (uint32_t)sizeof(BlkMeta) + 15u) & ~15u;
         cx.v_base = meta_bytes;
@@ -231,6 +203,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
             cx.arena_size = bd.arena_size;
             cx.nblk = (cx.n + BLOCK_W - 1) / BLOCK_W;
             cx.nblk_alloc = 0;
+        cx.last_idx = 0;
             cx.meta = (BlkMeta*)(arena + ARENA_HEADER);
             uint32_t meta_bytes = ((uint32_t)(cx.nblk + 1) * (uint32_t)sizeof(BlkMeta) + 15u) & ~15u;
             cx.v_base = ARENA_HEADER + meta_bytes;
@@ -826,24 +799,89 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
     return batch_prepare(e, n_pairs, a_all, a_off, b_all, b_off, false, out);
 }
 
-static uint32_t estimate_arena(const apa_batch* b, int preset, int trace) {
+static uint32_t estimate_arena(const apa_batch* b, int preset, int trace, const RunParams* gp) {
     // meta + V columns of one pass + traceback scratch + CIGAR elements. Deliberately modest: pairs that do
     // not fit are re-run with a larger arena (ST_OVERFLOW).
-    uint64_t nblk = (uint64_t)(b->max_n + BLOCK_W - 1) / BLOCK_W + 1;
+    const uint64_t bw = gp ? (uint64_t)gp->block_width : BLOCK_W;
+    const bool gcsh = gp ? (gp->domain == DOM_ASTAR && gp->heuristic == APA_HEURISTIC_GCSH) : preset == APA_PRESET_FULL;
+    uint64_t nblk = (uint64_t)(b->max_n + bw - 1) / bw + 1;
     uint64_t meta = nblk * sizeof(BlkMeta);
-    uint64_t band_rows = preset == APA_PRESET_SIMPLE ? std::min<uint64_t>((uint64_t)b->max_m + 64, std::max<uint64_t>(2048, (uint64_t)b->max_n / 8))
-                                                     : std::min<uint64_t>((uint64_t)b->max_m + 64, 2048);
+    uint64_t band_rows = !gcsh ? std::min<uint64_t>((uint64_t)b->max_m + 64, std::max<uint64_t>(2048, (uint64_t)b->max_n / 8))
+                               : std::min<uint64_t>((uint64_t)b->max_m + 64, 2048);
+    if (gp && gp->domain == APA_DOMAIN_FULL) band_rows = (uint64_t)b->max_m + 64;
     uint64_t vcols = nblk * (band_rows / 32 * 12 + 16);
     uint64_t tr = trace ? (DT_CACHE_ELEMS * 8 + 256 * (band_rows / 32) * 8 / 4 + (uint64_t)(b->max_n + b->max_m) / 4 * 4 + 65536) : 0;
-    uint64_t heur = preset == APA_PRESET_FULL ? 24ull * (uint64_t)b->max_n + 65536 : 0;  // k-mer table, matches, contours
+    uint64_t heur = gcsh ? 24ull * (uint64_t)b->max_n + 65536 : 0;  // k-mer table, matches, contours
     uint64_t s = ARENA_HEADER + meta + vcols + tr + heur + 16384;
     s = (s + 1023) & ~1023ull;
     return (uint32_t)std::min<uint64_t>(s, 0xF0000000ull);
 }
 
-static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool stream_data) {
+static int validate_params(const apa_params* q, RunParams* out) {
+    if (!q) return set_err(APA_ERR_BAD_INPUT, "null params");
+    auto bad = [](const char* what) { return set_err(APA_ERR_BAD_INPUT, std::string("unsupported AstarPa2Params: ") + what); };
+    if (q->domain < APA_DOMAIN_FULL || q->domain > APA_DOMAIN_ASTAR) return bad("domain");
+    if (q->domain == APA_DOMAIN_ASTAR) {
+        if (q->heuristic < APA_HEURISTIC_NONE || q->heuristic > APA_HEURISTIC_GCSH) return bad("heuristic (NoCost, GapCost and GCSH are built)");
+        if (q->heuristic == APA_HEURISTIC_GCSH) {
+            if (q->r != 1) return bad("r (exact matches only)");
+            if (q->k < 4 || q->k > 16) return bad("k must be 4..16");
+            if (q->p < 0 || q->p > 15) return bad("p must be 0..15");
+        }
+    }
+    if (q->doubling < APA_DOUBLING_NONE || q->doubling > APA_DOUBLING_LINEAR) return bad("doubling");
+    if (q->doubling == APA_DOUBLING_NONE && q->domain != APA_DOMAIN_FULL) return bad("DoublingType::None requires Domain::Full (lib.rs:128)");
+    if (q->doubling != APA_DOUBLING_NONE && (q->doubling_start < APA_START_ZERO || q->doubling_start > APA_START_H0)) return bad("doubling_start");
+    if (q->doubling == APA_DOUBLING_BAND && !(q->factor > 1.0f)) return bad("factor must be > 1");
+    if (q->doubling == APA_DOUBLING_LINEAR && q->delta < 1) return bad("delta must be >= 1");
+    if (q->block_width < 1 || q->block_width > BLOCK_W) return bad("block_width must be 1..256");
+    if (!q->sparse) return bad("sparse = false");
+    if (q->max_g < 1 || q->max_g > DT_MAX_G) return bad("max_g must be 1..40");
+    if (q->fr_drop < 0) return bad("fr_drop");
+    out->domain = q->domain;
+    out->heuristic = q->domain == APA_DOMAIN_ASTAR ? q->heuristic : APA_HEURISTIC_NONE;
+    out->k = q->k;
+    out->p = q->p;
+    out->doubling = q->doubling;
+    out->start = q->doubling_start;
+    out->factor = q->factor;
+    out->delta = q->delta;
+    out->block_width = q->block_width;
+    out->dt_trace = q->dt_trace != 0;
+    out->max_g = q->max_g;
+    out->fr_drop = q->fr_drop;
+    out->sparse_h = q->sparse_h != 0;
+    out->prune = q->prune != 0;
+    return APA_OK;
+}
+
+extern "C" int apa_params_preset(int preset, apa_params* out) {
+    if (!out || (preset != APA_PRESET_SIMPLE && preset != APA_PRESET_FULL)) return set_err(APA_ERR_BAD_INPUT, "unknown preset");
+    apa_params q{};
+    q.domain = APA_DOMAIN_ASTAR;
+    q.heuristic = preset == APA_PRESET_FULL ? APA_HEURISTIC_GCSH : APA_HEURISTIC_GAP;
+    q.k = 12;  // params.rs:103-105
+    q.r = 1;
+    q.p = 14;
+    q.doubling = APA_DOUBLING_BAND;
+    q.doubling_start = APA_START_H0;
+    q.factor = 2.0f;
+    q.delta = 1;
+    q.block_width = 256;
+    q.sparse = 1;
+    q.incremental_doubling = preset == APA_PRESET_FULL;
+    q.dt_trace = 1;
+    q.max_g = 40;
+    q.fr_drop = 10;
+    q.sparse_h = 1;
+    q.prune = preset == APA_PRESET_FULL;
+    *out = q;
+    return APA_OK;
+}
+
+static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool stream_data, const RunParams* gp = nullptr) {
     if (!e || !b) return set_err(APA_ERR_NO_DEVICE, "null engine/batch");
-    if (preset != APA_PRESET_SIMPLE && preset != APA_PRESET_FULL) return set_err(APA_ERR_BAD_INPUT, "unknown preset");
+    if (!gp && preset != APA_PRESET_SIMPLE && preset != APA_PRESET_FULL) return set_err(APA_ERR_BAD_INPUT, "unknown preset");
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
     b->trace = trace;
@@ -890,7 +928,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
     CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, 32 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(b->d_status, 0, b->n_pairs * 4, st));
-    uint32_t arena_size = estimate_arena(b, preset, trace);
+    uint32_t arena_size = estimate_arena(b, preset, trace, gp);
     if (const char* ev = getenv("APA_ARENA_BYTES")) arena_size = (uint32_t)std::max<long long>(65536, atoll(ev));  // tests: force the overflow/retry path
     std::vector<uint32_t> pending;  // empty = all pairs in the uploaded order
     b->h_status.assign(b->n_pairs, 0);
@@ -898,7 +936,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         // Slots (resident warps). Measured on B200 (profiles/README.md): throughput grows with resident warps up to
         // ~40 per SM even though the last wave is then only partly full; equalising the waves was slower.
         uint64_t n_work = attempt == 0 ? b->n_pairs : pending.size();
-        const uint64_t max_slots = (uint64_t)e->sm_count * 10 * WARPS_PER_CTA;
+        const uint64_t max_slots = (uint64_t)e->sm_count * (gp ? 6 : 10) * WARPS_PER_CTA;  // the general kernel runs 6 CTAs per SM
         uint64_t slots = ((n_work + WARPS_PER_CTA - 1) / WARPS_PER_CTA) * WARPS_PER_CTA;
         slots = std::min<uint64_t>(slots, max_slots);
         if (const char* ev = getenv("APA_SLOTS")) slots = std::max<uint64_t>(WARPS_PER_CTA, ((uint64_t)atoll(ev) / WARPS_PER_CTA) * WARPS_PER_CTA);
@@ -920,6 +958,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             split = n_work * (uint64_t)arena_size <= budget;
         }
         if (const char* ev = getenv("APA_SPLIT")) split = split && atoi(ev) != 0;
+        if (gp) split = false;  // the general kernel is fused (per-warp arenas)
         if (!split && slots * (uint64_t)arena_size > e->arena_total) {
             CUDA_TRY(query_budget());
             while (slots > WARPS_PER_CTA && slots * (uint64_t)arena_size > budget) slots = (slots / 2 / WARPS_PER_CTA) * WARPS_PER_CTA;
@@ -942,7 +981,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             bd.order = b->d_order + b->n_pairs;
             CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(unsigned long long), st));
         }
-        const bool streaming = stream_data && attempt == 0 && !b->chunk_pair_end.empty();
+        const bool streaming = stream_data && attempt == 0 && !b->chunk_pair_end.empty() && !gp;
         bd.ready = streaming ? e->d_ready : nullptr;
         if (streaming) {
             CUDA_TRY(cudaMemsetAsync(e->d_ready, 0, 4, st));
@@ -975,6 +1014,8 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
             // done, so the pass / trace kernels are launched after upload_planes() below.
             if (!streaming) CUDA_TRY(launch_pass_trace());
+        } else if (gp) {
+            CUDA_TRY(apa_general_launch(bd, *gp, (unsigned)(slots / WARPS_PER_CTA), st));
         } else if (regs >= 64)
             apa_align_kernel_r64<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
         else if (regs >= 48)
@@ -1115,21 +1156,54 @@ extern "C" int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_
     return rc;
 }
 
+extern "C" int apa_batch_run_params(apa_engine* e, apa_batch* b, const apa_params* params, int trace) {
+    RunParams rp;
+    int rc = validate_params(params, &rp);
+    if (rc != APA_OK) return rc;
+    return batch_run(e, b, -1, trace, false, &rp);
+}
+
+extern "C" int apa_align_batch_params(apa_engine* e, const apa_params* params, int trace, uint64_t n_pairs, const uint8_t* a_all,
+                                      const int64_t* a_off, const uint8_t* b_all, const int64_t* b_off, int64_t* costs,
+                                      char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len, apa_batch_stats* stats) {
+    RunParams rp;
+    int rc = validate_params(params, &rp);
+    if (rc != APA_OK) return rc;
+    apa_batch* b = nullptr;
+    rc = apa_batch_upload(e, n_pairs, a_all, a_off, b_all, b_off, &b);
+    if (rc == APA_OK) rc = batch_run(e, b, -1, trace, false, &rp);
+    if (rc == APA_OK) rc = apa_batch_download(e, b, costs, cigar_pool, cigar_off, cigar_len);
+    if (rc == APA_OK && stats) *stats = b->stats;
+    apa_batch_free(e, b);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------ band log (tests)
+static int64_t band_log_impl(apa_engine* e, int preset, const apa_params* params, int trace, const uint8_t* a, uint64_t n, const uint8_t* b,
+                             uint64_t m, int32_t* out, uint64_t cap);
 extern "C" int64_t apa_debug_band_log(apa_engine* e, int preset, int trace, const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m,
                                       int32_t* out, uint64_t cap) {
+    return band_log_impl(e, preset, nullptr, trace, a, n, b, m, out, cap);
+}
+extern "C" int64_t apa_debug_band_log_params(apa_engine* e, const apa_params* params, int trace, const uint8_t* a, uint64_t n,
+                                             const uint8_t* b, uint64_t m, int32_t* out, uint64_t cap) {
+    if (!params) return set_err(APA_ERR_BAD_INPUT, "null params");
+    return band_log_impl(e, -1, params, trace, a, n, b, m, out, cap);
+}
+static int64_t band_log_impl(apa_engine* e, int preset, const apa_params* params, int trace, const uint8_t* a, uint64_t n, const uint8_t* b,
+                             uint64_t m, int32_t* out, uint64_t cap) {
     int64_t a_off[2] = {0, (int64_t)n}, b_off[2] = {0, (int64_t)m};
     apa_batch* bt = nullptr;
     int rc = apa_batch_upload(e, 1, a, a_off, b, b_off, &bt);
     if (rc != APA_OK) return rc;
-    const uint32_t rec_cap = 7u * 64u * (uint32_t)(n / BLOCK_W + 2);
+    const uint32_t rec_cap = 7u * 64u * (uint32_t)(n / (params ? std::max(1, params->block_width) : BLOCK_W) + 2);
     std::vector<int32_t> rec(rec_cap);
     uint32_t nrec = 0;
     cudaError_t ce = cudaMalloc(&bt->d_dbg, rec_cap * 4);
     if (ce == cudaSuccess) ce = cudaMalloc(&bt->d_dbg_n, 4);
     if (ce == cudaSuccess) ce = cudaMemset(bt->d_dbg_n, 0, 4);
     bt->dbg_cap = rec_cap;
-    if (ce == cudaSuccess) rc = apa_batch_run(e, bt, preset, trace);
+    if (ce == cudaSuccess) rc = params ? apa_batch_run_params(e, bt, params, trace) : apa_batch_run(e, bt, preset, trace);
     if (ce == cudaSuccess && rc == APA_OK) ce = cudaMemcpy(&nrec, bt->d_dbg_n, 4, cudaMemcpyDeviceToHost);
     if (ce == cudaSuccess && rc == APA_OK) ce = cudaMemcpy(rec.data(), bt->d_dbg, std::min(nrec, rec_cap) * 4, cudaMemcpyDeviceToHost);
     cudaFree(bt->d_dbg);

@@ -20,7 +20,7 @@
 #pragma once
 #include "apa_align.cuh"
 
-namespace apa {
+namespace APA_NS {
 
 constexpr int GCSH_K = 12;        // seed length (params.rs:103)
 constexpr int GCSH_P = 14;        // local-pruning look-ahead in seeds (params.rs:105)
@@ -28,6 +28,14 @@ constexpr uint32_t HT_EMPTY = 0xffffffffu;
 
 struct GcshH {
     static constexpr bool PRUNE = true;
+#if APA_GENERAL
+    int k_, p_;  // MatchConfig.length / local_pruning (pa-heuristic/src/matches.rs:388-423)
+    __device__ __forceinline__ int K() const { return k_; }
+    __device__ __forceinline__ int P() const { return p_; }
+#else
+    static __device__ __forceinline__ constexpr int K() { return GCSH_K; }
+    static __device__ __forceinline__ constexpr int P() { return GCSH_P; }
+#endif
     I n, m;
     I nseeds;
     I ttx, tty;  // transform(target)
@@ -58,7 +66,7 @@ struct GcshH {
 
     // Seeds::potential (seeds.rs:79-81) for fixed-length seeds at 0, k, 2k, ...: number of seeds starting at >= i.
     __device__ __forceinline__ Cost pot(I i) const {
-        I c = (i + GCSH_K - 1) / GCSH_K;
+        I c = (i + K() - 1) / K();
         return c >= nseeds ? 0 : nseeds - c;
     }
     // RotateToFrontContour::contains on layer w (rotate_to_front.rs:32-44), without the rotation.
@@ -196,11 +204,11 @@ struct GcshH {
     // The seeds of the block (<= 22 for a 256-column block) are independent of each other: one lane per seed.
     __device__ void prune_block(I is, I ie, I js, I je) {
         const int lane = threadIdx.x & 31;
-        const I s0 = (is + GCSH_K) / GCSH_K;  // first seed with col >= is + 1
+        const I s0 = (is + K()) / K();  // first seed with col >= is + 1
         bool changed = false;
-        for (I sb = s0; sb < nseeds && sb * GCSH_K <= ie; sb += 32) {
+        for (I sb = s0; sb < nseeds && sb * K() <= ie; sb += 32) {
             const I s = sb + lane;
-            if (s < nseeds && s * GCSH_K <= ie) {
+            if (s < nseeds && s * K() <= ie) {
                 const uint32_t b_start = base[s], a_end = base[s + 1];
                 uint32_t b_end = before_end[s];
                 uint32_t a_start = after_start[s];
@@ -285,11 +293,11 @@ __device__ __forceinline__ void extend_right_win(const PruneWin& w, int ahw0, in
 __device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin& win, const uint2* __restrict__ ap, const uint2* __restrict__ bp,
                                                I seed, I sj, const NmpdView& nm) {
     const int lane = threadIdx.x & 31;
-    const I si = seed * GCSH_K;
-    const I ei = si + GCSH_K, ej = sj + GCSH_K;
+    const I si = seed * H.K();
+    const I ei = si + H.K(), ej = sj + H.K();
     const Cost start_pot = H.nseeds - seed;
-    const I last = min(seed + GCSH_P - 1, H.nseeds - 1);
-    const I end_i = (last + 1) * GCSH_K;
+    const I last = min(seed + H.P() - 1, H.nseeds - 1);
+    const I end_i = (last + 1) * H.K();
     const int pd = last + 1 - seed;  // start_pot - P(end_i), <= GCSH_P
     // lanes 0 .. 2*pd hold the front; lane d <-> diagonal e + (d - pd)
     const I dd = ei - ej + (lane - pd);  // this lane's diagonal
@@ -348,11 +356,11 @@ struct PruneWin {};
 __device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin&, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I seed,
                                                I sj, const NmpdView& nm) {
     const int lane = threadIdx.x & 31;
-    const I si = seed * GCSH_K;
-    const I ei = si + GCSH_K, ej = sj + GCSH_K;
+    const I si = seed * H.K();
+    const I ei = si + H.K(), ej = sj + H.K();
     const Cost start_pot = H.nseeds - seed;
-    const I last = min(seed + GCSH_P - 1, H.nseeds - 1);
-    const I end_i = (last + 1) * GCSH_K;
+    const I last = min(seed + H.P() - 1, H.nseeds - 1);
+    const I end_i = (last + 1) * H.K();
     const int pd = last + 1 - seed;  // start_pot - P(end_i), <= GCSH_P
     // g = 0
     I f0 = ei;
@@ -410,7 +418,8 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     const I n = cx.n, m = cx.m;
     H.n = n;
     H.m = m;
-    H.nseeds = n >= GCSH_K ? (n - GCSH_K) / GCSH_K + 1 : 0;  // fixed_length_seeds, qgrams.rs:99-109
+    const int GK = H.K(), GP = H.P();
+    H.nseeds = n >= GK ? (n - GK) / GK + 1 : 0;  // fixed_length_seeds, qgrams.rs:99-109
     H.ttx = n - m;  // transform(target): P(n) = 0
     H.tty = m - n;
     H.h_calls = 0;
@@ -451,7 +460,7 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     const uint32_t bm_words = 1u << (log_bm - 5);
     uint32_t off_tab = arena_alloc(cx, tsize * 8u);
     uint32_t off_bm = arena_alloc(cx, bm_words * 4u);
-    const I dmin = (n - m) - ns - (GCSH_P + 2), dmax = (n - m) + ns + (GCSH_P + 2);
+    const I dmin = (n - m) - ns - (GP + 2), dmax = (n - m) + ns + (GP + 2);
     uint32_t off_nm = arena_alloc(cx, (uint32_t)(dmax - dmin + 1) * 4u);
     uint32_t off_arr = arena_alloc(cx, (uint32_t)mcap * 16u);
     uint32_t off_stage = arena_alloc(cx, 32u * 32u * 8u);
@@ -478,12 +487,12 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     __syncwarp();
 
     // ---- hash the seeds of a (hash_to_smallvec, exact.rs:48-55). Key: bit t = rank bit0 of char t, bit k+t = rank bit1.
-    const uint32_t kmask = (1u << GCSH_K) - 1u;
+    const uint32_t kmask = (1u << GK) - 1u;
     for (I s0 = 0; s0 < ns; s0 += 32) {
         I s = s0 + lane;
         if (s < ns) {
-            const uint2 w = extract32(ap, s * GCSH_K);  // planes are stored negated
-            const uint32_t key = (~w.x & kmask) | ((~w.y & kmask) << GCSH_K);
+            const uint2 w = extract32(ap, s * GK);  // planes are stored negated
+            const uint32_t key = (~w.x & kmask) | ((~w.y & kmask) << GK);
             const uint32_t hsh = key * KMER_MUL;
             const uint32_t bit = hsh >> (32 - log_bm);
             atomicOr(&bm[bit >> 5], 1u << (bit & 31));
@@ -522,7 +531,7 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     // the hits staged per lane, (3) the hits are pushed in the reference's arrival order - j descending, seeds ascending -
     // through MatchBuilder::push (matches.rs:205-247), one hit at a time with the lanes on the diagonals of the pruning front.
     int M = 0;
-    for (I jtop = m - GCSH_K; jtop >= 0; jtop -= 1024) {
+    for (I jtop = m - GK; jtop >= 0; jtop -= 1024) {
         const I jhi = jtop - 32 * lane;
         const I wbase = max(jhi - 31, 0);  // bit s of `surv` <-> window j = wbase + s
         uint32_t surv = 0u;
@@ -532,7 +541,7 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
             w0x = ~lo.x, w0y = ~lo.y, w1x = ~hi.x, w1y = ~hi.y;
 #pragma unroll 8
             for (int sft = 0; sft < 32; sft++) {
-                const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GCSH_K);
+                const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GK);
                 const uint32_t bit = (key * KMER_MUL) >> (32 - log_bm);
                 const uint32_t word = bm[bit >> 5];
                 surv |= ((word >> (bit & 31)) & 1u) << sft;
@@ -546,7 +555,7 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
             if (surv) {
                 const int sft = 31 - __clz(surv);  // highest j first
                 surv &= ~(1u << sft);
-                const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GCSH_K);
+                const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GK);
                 int c;
                 const I seed0 = probe(key, -1, c);
                 if (c > 0) {  // the first two hits of a lane stay in registers (1.7 hits per lane and round on average)
@@ -580,10 +589,10 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
                 const bool multi = (rec.y & STAGE_MULTI) != 0u;
                 for (;;) {
                     // MatchBuilder::push (matches.rs:205-247)
-                    const I si = seed * GCSH_K;
+                    const I si = seed * GK;
                     const Cost p = ns - seed;  // P(si)
                     const bool pass_t = (si - jj - p <= H.ttx) && (jj - si - p <= H.tty);
-                    if (pass_t && dev_preserve_for_local_pruning(H, win, ap, bp, seed, jj, nm)) {
+                    if (pass_t && (GP == 0 || dev_preserve_for_local_pruning(H, win, ap, bp, seed, jj, nm))) {  // local_pruning = 0: keep all (matches.rs:213)
                         if (M >= mcap) {
                             cx.status = ST_OVERFLOW;
                             return false;
@@ -600,7 +609,7 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
                     }
                     if (!multi) break;
                     const uint2 w = extract32(bp, jj);
-                    const uint32_t kk = (~w.x & kmask) | ((~w.y & kmask) << GCSH_K);
+                    const uint32_t kk = (~w.x & kmask) | ((~w.y & kmask) << GK);
                     int dummy;
                     seed = probe(kk, seed, dummy);
                     if (seed == INT32_MAX) break;
@@ -630,7 +639,7 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
             const I s = a4.x;
             uint32_t c_s = cnt[s + 1] - cnt[s];
             uint32_t pos = cnt[s] + (c_s - 1u - (uint32_t)a4.z);
-            ms_i[pos] = s * GCSH_K;
+            ms_i[pos] = s * GK;
             ms_j[pos] = a4.y;
         }
         __syncwarp();
@@ -672,4 +681,4 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     return true;
 }
 
-}  // namespace apa
+}  // namespace APA_NS

@@ -10,10 +10,8 @@
 #pragma once
 #include "apa_align.cuh"
 
-namespace apa {
+namespace APA_NS {
 
-constexpr int DT_MAX_G = 40;    // BlockParams.max_g of both presets (params.rs:91,122)
-constexpr int DT_FR_DROP = 10;  // BlockParams.fr_drop (params.rs:92,123)
 constexpr int DT_CACHE_ELEMS = (DT_MAX_G + 1) * (DT_MAX_G + 1);
 
 // Shared-memory accesses of the DT fronts through an explicit 32-bit shared address held in a register: under the
@@ -214,23 +212,25 @@ __device__ bool dev_dt_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, TraceSt
         }
         min_fr = __reduce_min_sync(FULL, min_fr);
         min_i = __reduce_min_sync(FULL, min_i);
-        if (g == DT_MAX_G / 2 && min_i > (block_start + si) / 2) return false;
-        if (g == DT_MAX_G) return false;
+        if (g == P_MAX_G(cx) / 2 && min_i > (block_start + si) / 2) return false;
+        if (g == P_MAX_G(cx)) return false;
         // x-drop: shrink diagonals more than fr_drop behind (trace.rs:396-414)
-        const I thr = (I)((uint32_t)min_fr + (uint32_t)DT_FR_DROP);
-        while (d_lo < d_hi) {
-            I i = lds_i32(nxt + 4 * d_lo);
-            if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_lo) > thr)
-                d_lo++;
-            else
-                break;
-        }
-        while (d_lo < d_hi) {
-            I i = lds_i32(nxt + 4 * d_hi);
-            if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_hi) > thr)
-                d_hi--;
-            else
-                break;
+        if (P_FR_DROP(cx) > 0) {
+            const I thr = (I)((uint32_t)min_fr + (uint32_t)P_FR_DROP(cx));
+            while (d_lo < d_hi) {
+                I i = lds_i32(nxt + 4 * d_lo);
+                if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_lo) > thr)
+                    d_lo++;
+                else
+                    break;
+            }
+            while (d_lo < d_hi) {
+                I i = lds_i32(nxt + 4 * d_hi);
+                if (i <= block_start || (I)(2u * (uint32_t)i - (uint32_t)d_hi) > thr)
+                    d_hi--;
+                else
+                    break;
+            }
         }
         if (d_lo > d_hi) return false;
     }
@@ -300,7 +300,7 @@ __device__ bool dev_trace(PairCtx& cx, WarpSmem& sm, CigarWriter& cw, Cost cost)
             while (ts.top > 0 && cx.meta[ts.top].col_s >= ts.ti) ts.top--;
         }
         // DT trace first (trace.rs:50-65).
-        if (ts.ti > 0 && !ts.fill) {
+        if (P_DT_TRACE(cx) && ts.ti > 0 && !ts.fill) {
             const BlkMeta pm = cx.meta[ts.top - 1];
             if (pm.col_e < ts.ti - 1) {
                 const BlkView prev = view_of(cx, pm);
@@ -495,4 +495,4 @@ __device__ long long emit_cigar_text(const CigarWriter& cw, char* pool, unsigned
     return (long long)off;
 }
 
-}  // namespace apa
+}  // namespace APA_NS

@@ -85,6 +85,54 @@ int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, cons
                     const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool, int64_t* cigar_off,
                     int64_t* cigar_len, apa_batch_stats* stats);
 
+/* ---------------------------------------------------------------- general parameters
+ * AstarPa2Params (astarpa2/src/params.rs:8-42) beyond the two presets: the other Domains and DoublingTypes, block widths,
+ * heuristics and BlockParams knobs of the reference's own test matrix (astarpa2/src/tests.rs:19-119). Served by a second,
+ * general kernel (same device code, parameters read at run time); results are bit-exact against the oracle like the presets.
+ * Not supported (APA_ERR_BAD_INPUT): the SH / CSH heuristics, inexact matches (r = 2), sparse = false, LocalDoubling
+ * (ignored as broken in the reference, tests.rs:121-130), viz. */
+#define APA_DOMAIN_FULL 0      /* Domain::Full: the whole rectangle (params.rs:232) */
+#define APA_DOMAIN_GAP_START 1 /* states with gap(s, u) <= f (params.rs:234) */
+#define APA_DOMAIN_GAP_GAP 2   /* gap(s, u) + gap(u, t) <= f, Edlib-like (params.rs:236) */
+#define APA_DOMAIN_ASTAR 3     /* g(u) + h(u) <= f (params.rs:240) */
+#define APA_HEURISTIC_NONE 0   /* NoCost: Dijkstra */
+#define APA_HEURISTIC_GAP 1    /* GapCost (pa-heuristic/src/heuristic/distances.rs:130-169) */
+#define APA_HEURISTIC_GCSH 2   /* GCSH with exact matches of length k, Prune::Start (pa-heuristic/src/heuristic/csh.rs) */
+#define APA_DOUBLING_NONE 0    /* one unbounded pass; requires APA_DOMAIN_FULL (lib.rs:126-130) */
+#define APA_DOUBLING_BAND 1    /* DoublingType::BandDoubling{start, factor} (band.rs:100-141) */
+#define APA_DOUBLING_LINEAR 2  /* DoublingType::LinearSearch{start, delta} (band.rs:142-190) */
+#define APA_START_ZERO 0       /* DoublingStart (band.rs:4-23) */
+#define APA_START_GAP 1
+#define APA_START_H0 2
+typedef struct apa_params {
+    int32_t domain;
+    int32_t heuristic;    /* read when domain == APA_DOMAIN_ASTAR */
+    int32_t k;            /* GCSH seed length, 4..16 (HeuristicParams.k) */
+    int32_t r;            /* must be 1 (exact matches) */
+    int32_t p;            /* GCSH local-pruning look-ahead in seeds, 0 (off) ..15 (HeuristicParams.p) */
+    int32_t doubling;
+    int32_t doubling_start;
+    float factor;         /* BandDoubling */
+    int32_t delta;        /* LinearSearch */
+    int32_t block_width;  /* 1..256 */
+    int32_t sparse;       /* BlockParams.sparse: must be 1 */
+    int32_t incremental_doubling; /* accepted; blocks are always recomputed, which the reference asserts is identical (blocks.rs:471-543) */
+    int32_t dt_trace;
+    int32_t max_g;        /* 1..40 */
+    int32_t fr_drop;      /* 0 disables the x-drop */
+    int32_t sparse_h;
+    int32_t prune;
+} apa_params;
+/* Fills *out with AstarPa2Params::simple() / ::full() (params.rs:70-128). */
+int apa_params_preset(int preset, apa_params* out);
+/* apa_batch_run / apa_align_batch / apa_debug_band_log with explicit parameters (always the general kernel). */
+int apa_batch_run_params(apa_engine* e, apa_batch* b, const apa_params* params, int trace);
+int apa_align_batch_params(apa_engine* e, const apa_params* params, int trace, uint64_t n_pairs, const uint8_t* a_all,
+                           const int64_t* a_off, const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool,
+                           int64_t* cigar_off, int64_t* cigar_len, apa_batch_stats* stats);
+int64_t apa_debug_band_log_params(apa_engine* e, const apa_params* params, int trace, const uint8_t* a, uint64_t n,
+                                  const uint8_t* b, uint64_t m, int32_t* out, uint64_t cap);
+
 /* Debug/test introspection: per-pass band log of one pair in the oracle's layout
  * (passes, then per pass: f_max, nblocks, nblocks x (j_s, j_e, fixed_s, fixed_e)). Returns int32 count or <0. */
 int64_t apa_debug_band_log(apa_engine* e, int preset, int trace, const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m,

@@ -648,6 +648,9 @@ struct AstarPa2Params {  // params.rs:8-42 (subset reachable from the presets + 
     size_t p = 14;
     bool doubling = true;  // BandDoubling{start: H0 | Gap, factor}
     bool doubling_start_gap = false;
+    bool doubling_start_zero = false;  // DoublingStart::Zero (band.rs:16)
+    bool linear = false;               // DoublingType::LinearSearch{start, delta} (band.rs:34-37, 142-190)
+    Cost delta = 1;
     float factor = 2.0f;
     I block_width = 256;
     BlockParams front;
@@ -930,6 +933,9 @@ inline AlignResult cost_or_align(const uint8_t* a, size_t n, const uint8_t* b, s
         Cost start_f, start_increment;
         if (params.doubling_start_gap) {  // DoublingStart::Gap
             start_f = start_increment = GapCostI::gap(Pos{0, 0}, Pos{(I)n, (I)m});
+        } else if (params.doubling_start_zero) {  // DoublingStart::Zero
+            start_f = 0;
+            start_increment = 1;
         } else {  // DoublingStart::H0
             start_f = h0;
             start_increment = 1;
@@ -940,7 +946,7 @@ inline AlignResult cost_or_align(const uint8_t* a, size_t n, const uint8_t* b, s
         // exponential_search(offset = start_f, s0 = start_increment, factor)
         Cost offset = start_f;
         Cost last_s = -1;
-        Cost s = offset + start_increment;
+        Cost s = params.linear ? start_f : offset + start_increment;  // linear_search(s0 = start_f, delta), lib.rs:131-139
         Cost maxs = I_MAX;
         for (;;) {
             auto r = nw.align_for_bounded_dist(s, trace, &blocks);
@@ -961,6 +967,10 @@ inline AlignResult cost_or_align(const uint8_t* a, size_t n, const uint8_t* b, s
                 ORACLE_ASSERT(maxs == I_MAX, "A solution was found for a previous s but not for current s");
             }
             last_s = s;
+            if (params.linear) {  // band.rs:186
+                s = std::min(s + params.delta, maxs);
+                continue;
+            }
             float grown = std::ceil(params.factor * (float)(s - offset));
             s = std::max((Cost)grown, 1) + offset;
             s = std::min(s, maxs);

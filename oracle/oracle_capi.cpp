@@ -97,6 +97,63 @@ static AstarPa2Params preset_params(int preset) {
             q.prune = true;
             return q;
         }
+        // Further configurations the parameter space allows (astarpa2/src/params.rs, band.rs), used to pin the general GPU kernel.
+        case 10: {  // Domain::GapStart, bw = 64, BandDoubling{Gap, 2}
+            AstarPa2Params q = AstarPa2Params::simple();
+            q.domain = DomainKind::GapStart;
+            q.doubling_start_gap = true;
+            q.block_width = 64;
+            q.front = BlockParams{};
+            q.front.dt_trace = true;
+            return q;
+        }
+        case 11: {  // GapCost with LinearSearch{start: Gap, delta: 48}, bw = 32
+            AstarPa2Params q = AstarPa2Params::simple();
+            q.doubling_start_gap = true;
+            q.linear = true;
+            q.delta = 48;
+            q.block_width = 32;
+            return q;
+        }
+        case 12: {  // GCSH k = 12, p = 14 like astarpa2_full, but dense h (sparse_h = false), bw = 32, start Zero, factor 1.5, fr_drop 20
+            AstarPa2Params q = AstarPa2Params::full();
+            q.sparse_h = false;
+            q.block_width = 32;
+            q.doubling_start_zero = true;
+            q.factor = 1.5f;
+            q.front.fr_drop = 20;
+            return q;
+        }
+        case 13: {  // AstarPa2Params::nw() (params.rs:46-68): Domain::Full, no doubling, bw = 256, no dt_trace
+            AstarPa2Params q = AstarPa2Params::simple();
+            q.domain = DomainKind::Full;
+            q.doubling = false;
+            q.block_width = 256;
+            q.front = BlockParams{true, true, false, false, false, 40, 20};
+            q.sparse_h = false;
+            q.prune = false;
+            return q;
+        }
+        case 14: {  // Dijkstra (NoCost) with bw = 1 and dt_trace, GCSH-free pruning flag on
+            AstarPa2Params q = AstarPa2Params::simple();
+            q.heuristic = HeuristicKind::None;
+            q.doubling_start_gap = true;
+            q.block_width = 1;
+            q.front = BlockParams{};
+            q.front.dt_trace = true;
+            q.prune = true;
+            return q;
+        }
+        case 15: {  // GCSH k = 8, p = 3, prune off, bw = 100 (not a multiple of 32), LinearSearch{H0, 200}
+            AstarPa2Params q = AstarPa2Params::full();
+            q.k = 8;
+            q.p = 3;
+            q.prune = false;
+            q.block_width = 100;
+            q.linear = true;
+            q.delta = 200;
+            return q;
+        }
     }
     throw RefPanic("unknown preset");
 }

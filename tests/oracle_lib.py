@@ -84,7 +84,7 @@ def align(a: bytes, b: bytes, preset=PRESET_FULL, trace=True, self_check=False):
 
 def band_log(a: bytes, b: bytes, preset=PRESET_FULL, trace=True):
     L = lib()
-    cap = 16 + 8 * (len(a) // 64 + 4) * 40
+    cap = 16 + 8 * (len(a) // (64 if preset < 2 else 1) + 4) * 40  # configurations >= 2 may use block_width 1
     buf = np.zeros(cap, dtype=np.int32)
     w = L.oracle_align_log(preset, int(trace), a, len(a), b, len(b), buf.ctypes.data, cap)
     if w < 0:

@@ -233,3 +233,75 @@ def test_full_size_properties_gpu(apa, oracle):
     c2, cg2 = al.align(b, a)
     assert c1 == c2
     assert oracle.cigar_verify(cg1, a, b) == c1 and oracle.cigar_verify(cg2, b, a) == c2
+
+
+# ---------------------------------------------------------------------------------------------- general parameters
+# the other Domains / DoublingTypes / block widths / heuristics of AstarPa2Params, served by the general
+# kernel (apa_general.cu). Same bit-exact contract as the presets: cost, CIGAR text and the per-pass band log against the
+# oracle configured identically (tests/params_matrix.py mirrors oracle/oracle_capi.cpp preset_params).
+from params_matrix import GENERAL_PRESETS, params_for  # noqa: E402
+
+
+def _gpu_band_log_params(apa, a, b, params, trace=True):
+    eng = apa._engine(0)
+    L = apa.load_library()
+    cap = 16 + 8 * (len(a) + 4) * 40
+    buf = np.zeros(cap, dtype=np.int32)
+    w = L.apa_debug_band_log_params(eng._h, C.byref(params), int(trace), a, len(a), b, len(b), buf.ctypes.data, cap)
+    assert 0 <= w <= cap, (w, L.apa_last_error())
+    return buf[:w]
+
+
+def _check_pairs_params(apa, oracle, pairs, preset, trace=True):
+    params = params_for(apa, preset)
+    costs, cigars = apa.AstarPa2(params, trace).align_batch(pairs)
+    for k, (a, b) in enumerate(pairs):
+        oc, ocg, _ = oracle.align(a, b, preset, trace)
+        assert int(costs[k]) == oc, (preset, k, len(a), len(b), int(costs[k]), oc)
+        if trace and cigars[k] != ocg:
+            gl = oracle.parse_band_log(_gpu_band_log_params(apa, a, b, params))
+            ol = oracle.band_log(a, b, preset, True)
+            first = next((i for i, (x, y) in enumerate(zip(gl, ol)) if x != y), None)
+            raise AssertionError(f"CIGAR differs: config {preset} pair {k} n={len(a)} m={len(b)} cost {oc}; "
+                                 f"band logs equal: {gl == ol}; first differing pass {first}")
+
+
+@pytest.mark.parametrize("preset", GENERAL_PRESETS)
+def test_general_params_grid_gpu(apa, oracle, preset):
+    # the pa-test grid (pa-test/src/lib.rs:24-63), thinned per configuration; golden pairs first
+    pairs = [(p["a"].encode(), p["b"].encode()) for p in GOLD["pairs"]]
+    pairs += [apa.generate_pair(n, e, model, 31415 + 1000 * n + model)
+              for n in NS for e in ES[preset % 3::3] for model in ((preset + n) % 4,)]
+    _check_pairs_params(apa, oracle, pairs, preset)
+    _check_pairs_params(apa, oracle, pairs[::5], preset, trace=False)
+
+
+@pytest.mark.parametrize("preset", GENERAL_PRESETS)
+def test_general_params_band_log_gpu(apa, oracle, preset):
+    big = preset in (9, 13)  # Domain::Full computes n * m cells
+    for n, e in [(700, 0.1), (3000, 0.08)] if big else [(700, 0.1), (5000, 0.08), (12000, 0.05)]:
+        a, b = apa.generate_pair(n, e, 0, 7 + preset)
+        params = params_for(apa, preset)
+        assert oracle.parse_band_log(_gpu_band_log_params(apa, a, b, params)) == oracle.band_log(a, b, preset, True), (preset, n)
+        cost, cigar = apa.AstarPa2(params, True).align(a, b)
+        oc, ocg, _ = oracle.align(a, b, preset, True)
+        assert (cost, cigar) == (oc, ocg), (preset, n)
+
+
+def test_general_kernel_equals_preset_kernels_gpu(apa):
+    # the presets through the general kernel give what the tuned kernels give
+    rng = np.random.default_rng(11)
+    pairs = [apa.generate_pair(int(rng.integers(0, 20000)), float(rng.choice([0.02, 0.05, 0.15])), int(rng.integers(0, 4)),
+                               int(rng.integers(1 << 40))) for _ in range(200)]
+    for preset, params in ((0, apa.AstarPa2Params.simple()), (1, apa.AstarPa2Params.full())):
+        c0, g0 = apa.AstarPa2(preset, True).align_batch(pairs)
+        c1, g1 = apa.AstarPa2(params, True).align_batch(pairs)
+        assert (c0 == c1).all() and g0 == g1
+
+
+def test_general_params_rejects_unsupported_gpu(apa):
+    P = apa.AstarPa2Params
+    for bad in (P.full().replace(r=2), P.full().replace(k=20), P.simple().replace(block_width=512), P.simple().replace(sparse=0),
+                P.simple().replace(doubling="none"), P.simple().replace(max_g=100)):
+        with pytest.raises(apa.AstarPaError):
+            apa.AstarPa2(bad, True).align(b"ACGT", b"ACGT")

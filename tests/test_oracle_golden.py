@@ -9,7 +9,8 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
-PRESETS = list(range(10))  # 0 simple, 1 full, 2..9: configurations of astarpa2/src/tests.rs:19-119
+PRESETS = list(range(16))  # 0 simple, 1 full, 2..9: configurations of astarpa2/src/tests.rs:19-119, 10..15: further
+# points of the parameter space (other domain / LinearSearch / dense h / nw() / bw = 1 / k = 8), see oracle/oracle_capi.cpp
 
 
 @pytest.mark.parametrize("idx", range(len(GOLD["pairs"])))
