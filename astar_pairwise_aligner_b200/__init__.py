@@ -42,6 +42,12 @@ class BatchStats(C.Structure):
         return d
 
 
+class PairStats(C.Structure):
+    """``apa_pair_stats``: per-pair counters (AstarPa2Stats / TraceStats of the reference, see include/astarpa_b200.h)."""
+    _fields_ = [(k, C.c_int64) for k in ("f_max_tries", "h0", "num_matches", "h_calls", "computed_cells", "dt_trace_success",
+                                         "fill_tries", "reserved")]
+
+
 class AstarPa2Params(C.Structure):
     """``apa_params`` (include/astarpa_b200.h): the flat AstarPa2Params of the reference (astarpa2/src/params.rs:8-42).
 
@@ -122,6 +128,7 @@ def load_library():
                                          C.POINTER(BatchStats)]
     L.apa_debug_band_log_params.restype = C.c_int64
     L.apa_debug_band_log_params.argtypes = [C.c_void_p, pp, C.c_int, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64]
+    L.apa_batch_download_pair_stats.argtypes = [C.c_void_p, C.c_void_p, vp]
     L.apa_free.argtypes = [C.c_void_p]
     L.apa_pinned_alloc.restype = C.c_void_p
     L.apa_pinned_alloc.argtypes = [C.c_uint64]
@@ -322,6 +329,13 @@ class Batch:
         if pool and pool.value:
             self._L.apa_free(pool)
 
+    def pair_stats(self):
+        """Per-pair counters of the last run: list of dicts (apa_pair_stats)."""
+        arr = (PairStats * max(self.n_pairs, 1))()
+        _check(self._L.apa_batch_download_pair_stats(self._eng._h, self._h, C.cast(arr, C.c_void_p)))
+        keys = [k for k, _ in PairStats._fields_ if k != "reserved"]
+        return [{k: getattr(arr[p], k) for k in keys} for p in range(self.n_pairs)]
+
     def stats(self):
         st = BatchStats()
         _check(self._L.apa_batch_get_stats(self._h, C.byref(st)))
@@ -382,6 +396,21 @@ class AstarPa2:
         """Aligner::align (astarpa2/src/lib.rs:210-215): (cost, cigar or None)."""
         costs, cigs = self.align_batch([(a, b)])
         return int(costs[0]), (cigs[0] if cigs is not None else None)
+
+    def align_with_stats(self, a: bytes, b: bytes):
+        """AstarPa2StatsAligner::align_with_stats (astarpa2/src/lib.rs:200-208): ((cost, cigar or None), stats dict)."""
+        out = self.align_batch_with_stats([(a, b)])
+        return (int(out[0][0]), out[1][0] if out[1] is not None else None), out[2][0]
+
+    def align_batch_with_stats(self, pairs):
+        """(costs, cigars or None, per-pair stats dicts) through an HBM-resident batch."""
+        batch = _engine(self.device).upload(*_concat(pairs))
+        try:
+            batch.run(self.preset, self.trace)
+            costs, cigars = batch.download(cigars=self.trace)
+            return costs, cigars, batch.pair_stats()
+        finally:
+            batch.free()
 
     def cost(self, a: bytes, b: bytes):
         """AstarPa2::cost (astarpa2/src/lib.rs:177-179)."""

@@ -235,8 +235,16 @@ constexpr Cost PASS_NONE = -1;
 
 // One pass for a given f_max: AstarPa2Instance::align_for_bounded_dist (domain.rs:356-541), without the trace.
 // Returns the distance found in the last column, or PASS_NONE.
-template <class Hh>
-__device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
+// Right-edge column of the next block on one warp: stage the bases of the block's columns, then sweep (see run_block_dp in
+// apa_coop.cuh for the variant where the warps of a CTA share the chunks of a tall band).
+__device__ __forceinline__ Cost run_block_dp(WarpSmem& sm, PairCtx& cx, const BlkView& prev, I is, int ncols, I njs, I nje,
+                                             uint2* vout, int32_t* cumout, Cost top_val) {
+    stage_amask(sm, cx.aprof, is, ncols, threadIdx.x & 31);
+    return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.word_steps);
+}
+
+template <class Hh, class SM>
+__device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
     const int lane = threadIdx.x & 31;
     cx.passes++;
     if (Hh::PRUNE && P_PRUNE(cx)) {
@@ -302,12 +310,10 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
         uint32_t off = arena_alloc(cx, (uint32_t)nhw * 8u + (uint32_t)(nhw + 1) * 4u);
         if (cx.status != ST_PENDING) return PASS_NONE;
         Cost top_val = blk_index(prev, rounded.s) + (ie - is);
-        stage_amask(sm, cx.aprof, is, ie - is, lane);
         uint2* vout = (uint2*)(cx.arena + off);
         int32_t* cumout = (int32_t*)(cx.arena + off + (size_t)nhw * 8);
         long long t_dp0 = APA_TIC();
-        Cost bot_val = block_dp<false>(sm, cx.bprof, prev, ie - is, rounded.s, rounded.e, vout, cumout, top_val, nullptr,
-                                       cx.word_steps);
+        Cost bot_val = run_block_dp(sm, cx, prev, is, ie - is, rounded.s, rounded.e, vout, cumout, top_val);
         APA_TOC(cx.tphase[1], t_dp0);
         cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
 
@@ -377,8 +383,8 @@ __device__ Cost dev_pass(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost f_max) {
 // band::exponential_search / linear_search driven by cost_or_align (band.rs:100-190, lib.rs:122-175). The presets use
 // BandDoubling{start: H0, factor: 2}: offset = h0, s0 = max(1, block_width) = 256. Returns the cost; the blocks of the
 // final pass stay in the arena.
-template <class Hh>
-__device__ Cost dev_band_doubling(PairCtx& cx, WarpSmem& sm, Hh& hh, Cost h0) {
+template <class Hh, class SM>
+__device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
     Cost offset = h0;
     Cost s0 = BLOCK_W;
     float factor = 2.0f;

@@ -19,6 +19,7 @@
 #include "../../include/astarpa_b200.h"
 #include "apa_gcsh.cuh"
 #include "apa_trace.cuh"
+#include "apa_coop.cuh"
 
 using namespace apa;
 
@@ -92,10 +93,12 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
 
         Cost cost = -1;
         long long cig_off = -1, cig_len = 0;
+        long long st_h0 = 0, st_matches = 0, st_hcalls = 0;
         if (cx.status == ST_PENDING) {
             if (bd.preset == APA_PRESET_SIMPLE) {
                 GapH hh{cx.n, cx.m};
                 Cost h0 = hh.h(0, 0);
+                st_h0 = h0;
                 long long t0 = APA_TIC();
                 cost = dev_band_doubling(cx, sm, hh, h0);
                 APA_TOC(cx.tphase[2], t0);
@@ -111,6 +114,9 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
                     cost = dev_band_doubling(cx, sm, hh, h0);
                     APA_TOC(cx.tphase[2], t0);
                     cx.tphase[6] += hh.t_h;
+                    st_h0 = h0;
+                    st_matches = hh.M;
+                    st_hcalls = (long long)hh.h_calls + 1;  // + the h(0,0) inside CSHI::new (csh.rs:296), not needed here
                     if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
                 }
             }
@@ -139,6 +145,11 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
             bd.cost[p] = cost;
             bd.cig_off[p] = cig_off;
             bd.cig_len[p] = cig_len;
+        }
+        if (lane == 0) {
+            long long* ps = bd.pair_stats + 8ull * p;
+            ps[0] = cx.passes, ps[1] = st_h0, ps[2] = st_matches, ps[3] = st_hcalls, ps[4] = (long long)cx.computed_cells;
+            ps[5] = cx.dt_blocks, ps[6] = cx.fill_blocks, ps[7] = 0;
         }
         if (bd.dbg_n && lane == 0) *bd.dbg_n = cx.dbg_n;
         acc_steps += cx.word_steps;
@@ -173,11 +184,9 @@ struct PairState {
 constexpr uint32_t ARENA_HEADER = 512;
 static_assert(sizeof(PairState) <= ARENA_HEADER, "PairState must fit the arena header");
 
-template <int PHASE>
-__device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* smem) {
+template <int PHASE, class SM>
+__device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    WarpSmem& sm = smem[wib];
     unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0, acc_h = 0, acc_probe = 0;
     for (;;) {
         unsigned long long q = 0;
@@ -194,7 +203,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
         uint8_t* arena = bd.arena + (size_t)(q - bd.q0) * bd.arena_size;
         PairState* ps = (PairState*)arena;
         PairCtx cx;
-        if (PHASE == 0) {
+        if constexpr (PHASE == 0) {
             cx.n = (I)(bd.a_off[p + 1] - bd.a_off[p]);
             cx.m = (I)(bd.b_off[p + 1] - bd.b_off[p]);
             cx.bprof = bd.bprof + bd.bp_off[p];
@@ -231,13 +240,15 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
         }
         cx = ps->cx;
         Cost cost = ps->cost;
-        if (PHASE == 1) {
+        if constexpr (PHASE == 1) {
             if (cx.status == ST_PENDING) {
+                long long* pst = bd.pair_stats + 8ull * p;
                 if (bd.preset == APA_PRESET_SIMPLE) {
                     GapH hh{cx.n, cx.m};
                     Cost h0 = hh.h(0, 0);
                     cost = dev_band_doubling(cx, sm, hh, h0);
                     if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
+                    if (lane == 0) pst[1] = h0, pst[2] = 0, pst[3] = 0;
                 } else {
                     GcshH hh = ps->hh;
                     hh.h_calls = hh.probes = 0;
@@ -246,6 +257,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
                     if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;
                     acc_h += hh.h_calls;
                     acc_probe += hh.probes;
+                    if (lane == 0) pst[1] = h0, pst[2] = hh.M, pst[3] = (long long)hh.h_calls + 1;  // + CSHI::new's own h(0,0) (csh.rs:296)
                 }
             }
             __syncwarp();
@@ -258,7 +270,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
         }
         // PHASE 2, or PHASE 1 of a cost-only run: finish the pair
         long long cig_off = -1, cig_len = 0;
-        if (PHASE == 2 && cx.status == ST_PENDING && bd.trace) {
+        if constexpr (PHASE == 2) if (cx.status == ST_PENDING && bd.trace) {
             CigarWriter cw;
             cw.arena = arena;
             cw.arena_size = bd.arena_size;
@@ -277,6 +289,8 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
             bd.cost[p] = cost;
             bd.cig_off[p] = cig_off;
             bd.cig_len[p] = cig_len;
+            long long* pst = bd.pair_stats + 8ull * p;
+            pst[0] = cx.passes, pst[4] = (long long)cx.computed_cells, pst[5] = cx.dt_blocks, pst[6] = cx.fill_blocks, pst[7] = 0;
         }
         if (bd.dbg_n && lane == 0) *bd.dbg_n = cx.dbg_n;
         acc_steps += cx.word_steps;
@@ -302,7 +316,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, WarpSmem* sme
 #define APA_PHASE_KERNEL(NAME, PHASE, MINB)                                                     \
     __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) NAME(BatchDev bd) {             \
         __shared__ WarpSmem smem[WARPS_PER_CTA];                                                \
-        apa_phase_body<PHASE>(bd, smem);                                                        \
+        apa_phase_body<PHASE>(bd, smem[threadIdx.x >> 5]);                                      \
     }
 APA_PHASE_KERNEL(apa_phase_build_kernel, 0, 10)
 APA_PHASE_KERNEL(apa_phase_build_kernel_r56, 0, 9)
@@ -313,6 +327,18 @@ APA_PHASE_KERNEL(apa_phase_pass_kernel_r64, 1, 8)
 APA_PHASE_KERNEL(apa_phase_trace_kernel, 2, 10)
 APA_PHASE_KERNEL(apa_phase_trace_kernel_r56, 2, 9)
 APA_PHASE_KERNEL(apa_phase_trace_kernel_r64, 2, 8)
+// Pass kernel with the W warps of a CTA on one pair (apa_coop.cuh): warp 0 runs the pair, the others serve its tall blocks.
+template <int W>
+__global__ void __launch_bounds__(W * 32, 32 / W) apa_phase_pass_coop_kernel(BatchDev bd) {
+    __shared__ CoopSmem<W> cs;
+    const int wid = threadIdx.x >> 5;
+    if (wid == 0) {
+        apa_phase_body<1>(bd, cs);
+        coop_release_workers<W>(cs);
+    } else {
+        coop_worker_loop<W>(cs, wid);
+    }
+}
 typedef void (*phase_kernel_t)(BatchDev);
 static phase_kernel_t phase_kernel(int phase, int regs) {
     static const phase_kernel_t tab[3][3] = {{apa_phase_build_kernel, apa_phase_build_kernel_r56, apa_phase_build_kernel_r64},
@@ -400,6 +426,7 @@ struct apa_batch {
     uint2 *d_bprof = nullptr, *d_aprof = nullptr;
     int32_t *d_status = nullptr, *d_cost = nullptr;
     int64_t *d_cig_off = nullptr, *d_cig_len = nullptr;
+    long long* d_pair_stats = nullptr;  // 8 per pair (apa_pair_stats)
     uint32_t* d_order = nullptr;
     char* d_pool = nullptr;
     uint64_t pool_cap = 0;
@@ -581,6 +608,7 @@ extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     eng_release(e, b->d_cost);
     eng_release(e, b->d_cig_off);
     eng_release(e, b->d_cig_len);
+    eng_release(e, b->d_pair_stats);
     eng_release(e, b->d_order);
     eng_release(e, b->d_pool);
     delete b;
@@ -714,6 +742,7 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     CUDA_TRY(eng_alloc(e, (void**)&b->d_cost, std::max<uint64_t>(n_pairs, 1) * 4));
     CUDA_TRY(eng_alloc(e, (void**)&b->d_cig_off, std::max<uint64_t>(n_pairs, 1) * 8));
     CUDA_TRY(eng_alloc(e, (void**)&b->d_cig_len, std::max<uint64_t>(n_pairs, 1) * 8));
+    CUDA_TRY(eng_alloc(e, (void**)&b->d_pair_stats, std::max<uint64_t>(n_pairs, 1) * 64));
     CUDA_TRY(eng_alloc(e, (void**)&b->d_order, std::max<uint64_t>(n_pairs, 1) * 8));  // [0,n): work order, [n,2n): retry list
     // pinned staging for the packed planes: [aprof | bprof]
     const size_t stage_words = (size_t)(hwa + hw) * 2 + 16;
@@ -912,6 +941,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     bd.cost = b->d_cost;
     bd.cig_off = b->d_cig_off;
     bd.cig_len = b->d_cig_len;
+    bd.pair_stats = b->d_pair_stats;
     bd.order = b->d_order;
     bd.n_order = (uint32_t)b->n_pairs;
     bd.queue = e->d_queue;
@@ -950,21 +980,45 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             cudaError_t ce = cudaMemGetInfo(&free_b, &total_b);
             budget = (uint64_t)free_b + e->arena_total;
             budget = budget > (4ull << 30) ? budget - (2ull << 30) : std::max<uint64_t>(budget / 2, 1);
+            if (const char* ev = getenv("APA_BUDGET_BYTES")) budget = std::max<long long>(1 << 20, atoll(ev));  // tests: force the wave path
             return ce;
         };
-        bool split = n_work * (uint64_t)arena_size <= e->arena_total;
+        uint64_t have = e->arena_total;  // an arena this large is already allocated
+        if (const char* ev = getenv("APA_BUDGET_BYTES")) have = std::min<uint64_t>(have, (uint64_t)std::max<long long>(1 << 20, atoll(ev)));
+        bool split = n_work * (uint64_t)arena_size <= have;
         if (!split) {
             CUDA_TRY(query_budget());
             split = n_work * (uint64_t)arena_size <= budget;
         }
-        if (const char* ev = getenv("APA_SPLIT")) split = split && atoi(ev) != 0;
-        if (gp) split = false;  // the general kernel is fused (per-warp arenas)
+        const bool split_allowed = !gp && !(getenv("APA_SPLIT") && atoi(getenv("APA_SPLIT")) == 0);  // the general kernel is fused
+        split = split && split_allowed;
+        // Memory-limited work lists (long, divergent pairs: BASELINE configs[3]): when only a few hundred per-pair arenas fit at
+        // once, the phase-split path runs in waves of that many pairs, each pair on a whole CTA (apa_coop.cuh), instead of
+        // the fused kernel with one warp per pair on a mostly empty GPU.
+        uint64_t wave_n = n_work;
+        if (!split && split_allowed) {
+            CUDA_TRY(query_budget());
+            const uint64_t fit = budget / arena_size;
+            if (fit >= 1 && fit <= (uint64_t)e->sm_count * 8) {
+                split = true;
+                wave_n = std::min<uint64_t>(fit, n_work);
+            }
+        }
+        // Warps per pair in the pass kernel: a whole CTA when the wave has fewer pairs than the GPU has CTA slots.
+        int coop_w = 1;
+        if (split) {
+            if (wave_n <= (uint64_t)e->sm_count * 4)
+                coop_w = 8;
+            else if (wave_n <= (uint64_t)e->sm_count * 8)
+                coop_w = 4;
+            if (const char* ev = getenv("APA_COOP")) coop_w = atoi(ev) >= 8 ? 8 : (atoi(ev) >= 4 ? 4 : 1);
+        }
         if (!split && slots * (uint64_t)arena_size > e->arena_total) {
             CUDA_TRY(query_budget());
             while (slots > WARPS_PER_CTA && slots * (uint64_t)arena_size > budget) slots = (slots / 2 / WARPS_PER_CTA) * WARPS_PER_CTA;
             if (slots * (uint64_t)arena_size > budget) return set_err(APA_ERR_TOO_LARGE, "scratch arena exceeds device memory");
         }
-        const uint64_t n_arenas = split ? n_work : slots;
+        const uint64_t n_arenas = split ? wave_n : slots;
         size_t need = (size_t)(split ? n_arenas : slots) * arena_size;
         if (e->arena_total < need) {
             if (e->d_arena) CUDA_TRY(cudaFree(e->d_arena));
@@ -981,7 +1035,12 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             bd.order = b->d_order + b->n_pairs;
             CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(unsigned long long), st));
         }
-        const bool streaming = stream_data && attempt == 0 && !b->chunk_pair_end.empty() && !gp;
+        bool streaming = stream_data && attempt == 0 && !b->chunk_pair_end.empty() && !gp;
+        if (streaming && split && wave_n < n_work) {  // waves: plain upload first, the waves then find their bases in HBM
+            int rc = upload_planes(e, b, /*streaming=*/false);
+            if (rc != APA_OK) return rc;
+            streaming = false;
+        }
         bd.ready = streaming ? e->d_ready : nullptr;
         if (streaming) {
             CUDA_TRY(cudaMemsetAsync(e->d_ready, 0, 4, st));
@@ -994,7 +1053,13 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
         // pass + trace kernels of the phase-split path, with the per-phase events (stats.phase_ms)
         auto launch_pass_trace = [&]() -> cudaError_t {
-            phase_kernel(1, phase_regs(1))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+            const unsigned wave_pairs = (unsigned)(bd.n_order - bd.q0);
+            if (coop_w == 8)
+                apa_phase_pass_coop_kernel<8><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 4), 256, 0, st>>>(bd);
+            else if (coop_w == 4)
+                apa_phase_pass_coop_kernel<4><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 8), 128, 0, st>>>(bd);
+            else
+                phase_kernel(1, phase_regs(1))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
             b->stats.kernel_launches++;
             cudaError_t ce = cudaEventRecord(e->evp[2], st);
             if (ce != cudaSuccess) return ce;
@@ -1005,15 +1070,33 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             ce = cudaEventRecord(e->evp[3], st);
             return ce != cudaSuccess ? ce : cudaGetLastError();
         };
+        auto add_phase_ms = [&]() -> cudaError_t {
+            for (int k = 0; k < 3; k++) {
+                float pms = 0;
+                cudaError_t ce = cudaEventElapsedTime(&pms, e->evp[k], e->evp[k + 1]);
+                if (ce != cudaSuccess) return ce;
+                b->stats.phase_ms[k] += pms;
+            }
+            return cudaSuccess;
+        };
         if (split) {
-            CUDA_TRY(cudaMemsetAsync(e->d_queue + 24, 0, 3 * sizeof(unsigned long long), st));
-            CUDA_TRY(cudaEventRecord(e->evp[0], st));
-            phase_kernel(0, phase_regs(0))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
-            CUDA_TRY(cudaEventRecord(e->evp[1], st));
-            // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
-            // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
-            // done, so the pass / trace kernels are launched after upload_planes() below.
-            if (!streaming) CUDA_TRY(launch_pass_trace());
+            for (uint64_t w0 = 0; w0 < n_work; w0 += wave_n) {
+                bd.q0 = (uint32_t)w0;
+                bd.n_order = (uint32_t)std::min<uint64_t>(w0 + wave_n, n_work);
+                CUDA_TRY(cudaMemsetAsync(e->d_queue + 24, 0, 3 * sizeof(unsigned long long), st));
+                CUDA_TRY(cudaEventRecord(e->evp[0], st));
+                phase_kernel(0, phase_regs(0))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                b->stats.kernel_launches++;
+                CUDA_TRY(cudaEventRecord(e->evp[1], st));
+                // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
+                // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
+                // done, so the pass / trace kernels are launched after upload_planes() below.
+                if (!streaming) CUDA_TRY(launch_pass_trace());
+                if (w0 + wave_n < n_work) {  // more waves follow: the arenas are reused
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    CUDA_TRY(add_phase_ms());
+                }
+            }
         } else if (gp) {
             CUDA_TRY(apa_general_launch(bd, *gp, (unsigned)(slots / WARPS_PER_CTA), st));
         } else if (regs >= 64)
@@ -1022,7 +1105,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             apa_align_kernel_r48<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
         else
             apa_align_kernel_r40<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
-        b->stats.kernel_launches++;
+        if (!split) b->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
         if (streaming) {
             // host threads pack the bases while the persistent kernel already consumes the chunks that have landed
@@ -1039,13 +1122,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (split) {
-            for (int k = 0; k < 3; k++) {
-                float pms = 0;
-                CUDA_TRY(cudaEventElapsedTime(&pms, e->evp[k], e->evp[k + 1]));
-                b->stats.phase_ms[k] += pms;
-            }
-        }
+        if (split) CUDA_TRY(add_phase_ms());
         pending.clear();
         for (uint64_t p = 0; p < b->n_pairs; p++)
             if (b->h_status[p] == ST_OVERFLOW) pending.push_back((uint32_t)p);
@@ -1124,6 +1201,16 @@ extern "C" int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, c
     CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]));
     b->stats.d2h_ms = ms;
     b->stats.d2h_bytes = bytes;
+    return APA_OK;
+}
+
+extern "C" int apa_batch_download_pair_stats(apa_engine* e, apa_batch* b, apa_pair_stats* out) {
+    if (!e || !b || !b->ran || !out) return set_err(APA_ERR_BAD_INPUT, "batch has not been run");
+    static_assert(sizeof(apa_pair_stats) == 64, "apa_pair_stats layout");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (b->n_pairs == 0) return APA_OK;
+    CUDA_TRY(cudaMemcpyAsync(out, b->d_pair_stats, b->n_pairs * 64, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
     return APA_OK;
 }
 

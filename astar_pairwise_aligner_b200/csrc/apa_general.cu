@@ -60,6 +60,7 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
         if (cx.status == ST_PENDING) {
             // AstarPa2::build + cost_or_align (lib.rs:87-175): h0 = h(0, 0) for Domain::Astar, 0 otherwise.
             Cost h0 = 0;
+            long long st_matches = 0, st_hcalls = 0;
             if (par.domain != DOM_ASTAR || par.heuristic == 0) {
                 NoneH hh;
                 cost = dev_band_doubling(cx, sm, hh, 0);
@@ -76,7 +77,13 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
                     cost = dev_band_doubling(cx, sm, hh, h0);
                     acc_h += hh.h_calls;
                     acc_probe += hh.probes;
+                    st_matches = hh.M;
+                    st_hcalls = (long long)hh.h_calls + 1;  // + the h(0,0) inside CSHI::new (csh.rs:296)
                 }
+            }
+            if (lane == 0) {
+                long long* ps = bd.pair_stats + 8ull * p;
+                ps[1] = h0, ps[2] = st_matches, ps[3] = st_hcalls;
             }
             if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
         }
@@ -99,6 +106,8 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
             bd.cost[p] = cost;
             bd.cig_off[p] = cig_off;
             bd.cig_len[p] = cig_len;
+            long long* ps = bd.pair_stats + 8ull * p;
+            ps[0] = cx.passes, ps[4] = (long long)cx.computed_cells, ps[5] = cx.dt_blocks, ps[6] = cx.fill_blocks, ps[7] = 0;
         }
         if (bd.dbg_n && lane == 0) *bd.dbg_n = cx.dbg_n;
         acc_steps += cx.word_steps;

@@ -8,6 +8,9 @@
 //                                                        astarpa2/src/lib.rs:210-215 (CIGAR iff trace)
 //   AstarPa2::cost(a, b)                                 AstarPa2::cost, astarpa2/src/lib.rs:177-179
 //   astarpa2::astarpa2_simple / astarpa2_full            astarpa2/src/lib.rs:44-53
+//   astarpa2::AstarPa2Params{...}.make_aligner(trace)    AstarPa2Params::make_aligner (params.rs:132-226): other domains,
+//                                                        heuristics, doubling types, block widths (general kernel)
+//   AstarPa2::align_with_stats(a, b)                     AstarPa2StatsAligner::align_with_stats, astarpa2/src/lib.rs:200-208
 //   AstarPa2::align_batch(pairs)                         no reference counterpart: one call carries a whole batch
 //                                                        to the GPU (SURVEY 8b "needed extension")
 //   Cigar::{to_string, parse, verify}                    pa_types::Cigar (external crate; text format pinned by
@@ -112,6 +115,29 @@ struct BatchResult {
     std::vector<Cost> costs;
     std::vector<std::string> cigars;  // CIGAR text per pair; empty vector when trace == false
     apa_batch_stats stats{};
+    std::vector<apa_pair_stats> pair_stats;  // filled by align_batch_with_stats only
+};
+
+class AstarPa2;
+// Flat parameters (astarpa2/src/params.rs:8-42) = the C-ABI struct; simple() / full() / nw() as in params.rs:46-128.
+struct AstarPa2Params : apa_params {
+    static AstarPa2Params preset(int which) {
+        AstarPa2Params q;
+        int rc = apa_params_preset(which, &q);
+        if (rc != APA_OK) throw Error(rc, std::string("apa_params_preset: ") + apa_last_error());
+        return q;
+    }
+    static AstarPa2Params simple() { return preset(APA_PRESET_SIMPLE); }
+    static AstarPa2Params full() { return preset(APA_PRESET_FULL); }
+    static AstarPa2Params nw() {  // params.rs:46-68
+        AstarPa2Params q = simple();
+        q.domain = APA_DOMAIN_FULL;
+        q.heuristic = APA_HEURISTIC_NONE;
+        q.doubling = APA_DOUBLING_NONE;
+        q.dt_trace = q.sparse_h = q.prune = 0;
+        return q;
+    }
+    inline AstarPa2 make_aligner(bool trace, int device = 0) const;
 };
 
 class AstarPa2 {
@@ -122,11 +148,18 @@ class AstarPa2 {
         int rc = apa_engine_create(device, &engine_);
         if (rc != APA_OK) throw Error(rc, std::string("apa_engine_create: ") + apa_last_error());
     }
+    // Explicit parameters: served by the general kernel (apa_align_batch_params).
+    AstarPa2(const apa_params& params, bool trace, int device = 0) : preset_(Full), trace_(trace), params_(params), has_params_(true) {
+        int rc = apa_engine_create(device, &engine_);
+        if (rc != APA_OK) throw Error(rc, std::string("apa_engine_create: ") + apa_last_error());
+    }
     static AstarPa2 simple(bool trace = true, int device = 0) { return AstarPa2(Simple, trace, device); }
     static AstarPa2 full(bool trace = true, int device = 0) { return AstarPa2(Full, trace, device); }
     AstarPa2(const AstarPa2&) = delete;
     AstarPa2& operator=(const AstarPa2&) = delete;
-    AstarPa2(AstarPa2&& o) noexcept : engine_(o.engine_), preset_(o.preset_), trace_(o.trace_) { o.engine_ = nullptr; }
+    AstarPa2(AstarPa2&& o) noexcept : engine_(o.engine_), preset_(o.preset_), trace_(o.trace_), params_(o.params_), has_params_(o.has_params_) {
+        o.engine_ = nullptr;
+    }
     ~AstarPa2() {
         if (engine_) apa_engine_destroy(engine_);
     }
@@ -148,14 +181,65 @@ class AstarPa2 {
     }
     BatchResult align_batch(const std::vector<std::pair<Seq, Seq>>& pairs) { return align_batch(pairs.data(), pairs.size(), trace_); }
 
+    // AstarPa2StatsAligner::align_with_stats (astarpa2/src/lib.rs:200-208): the alignment plus the per-pair counters.
+    std::pair<Alignment, apa_pair_stats> align_with_stats(Seq a, Seq b) {
+        BatchResult r = align_batch_with_stats({{a, b}});
+        Alignment al{r.costs[0], std::nullopt};
+        if (trace_) al.second = Cigar::parse(r.cigars[0]);
+        return {std::move(al), r.pair_stats[0]};
+    }
+    // Through an HBM-resident batch (upload / run / download), which is where the per-pair counters live.
+    BatchResult align_batch_with_stats(const std::vector<std::pair<Seq, Seq>>& pairs) {
+        const size_t n = pairs.size();
+        std::string a_all, b_all;
+        std::vector<int64_t> a_off(n + 1, 0), b_off(n + 1, 0);
+        for (size_t p = 0; p < n; p++) {
+            a_all.append(pairs[p].first);
+            b_all.append(pairs[p].second);
+            a_off[p + 1] = (int64_t)a_all.size();
+            b_off[p + 1] = (int64_t)b_all.size();
+        }
+        apa_batch* bt = nullptr;
+        auto check = [&](int rc, const char* what) {
+            if (rc == APA_OK) return;
+            std::string msg = std::string(what) + ": " + apa_last_error();
+            if (bt) apa_batch_free(engine_, bt);
+            throw Error(rc, msg);
+        };
+        check(apa_batch_upload(engine_, n, (const uint8_t*)a_all.data(), a_off.data(), (const uint8_t*)b_all.data(), b_off.data(), &bt),
+              "apa_batch_upload");
+        check(has_params_ ? apa_batch_run_params(engine_, bt, &params_, trace_ ? 1 : 0) : apa_batch_run(engine_, bt, (int)preset_, trace_ ? 1 : 0),
+              "apa_batch_run");
+        BatchResult r;
+        std::vector<int64_t> costs(n ? n : 1), off(n ? n : 1), len(n ? n : 1);
+        char* pool = nullptr;
+        check(trace_ ? apa_batch_download(engine_, bt, costs.data(), &pool, off.data(), len.data())
+                     : apa_batch_download(engine_, bt, costs.data(), nullptr, nullptr, nullptr),
+              "apa_batch_download");
+        r.costs.assign(costs.begin(), costs.begin() + n);
+        if (trace_ && pool) {
+            r.cigars.resize(n);
+            for (size_t p = 0; p < n; p++) r.cigars[p].assign(pool + off[p], (size_t)len[p]);
+        }
+        apa_free(pool);
+        r.pair_stats.resize(n ? n : 1);
+        check(apa_batch_download_pair_stats(engine_, bt, r.pair_stats.data()), "apa_batch_download_pair_stats");
+        r.pair_stats.resize(n);
+        check(apa_batch_get_stats(bt, &r.stats), "apa_batch_get_stats");
+        apa_batch_free(engine_, bt);
+        return r;
+    }
+
     // Concatenated form (what the C-ABI takes): pair p is a_all[a_off[p] .. a_off[p+1]) vs b_all[b_off[p] .. b_off[p+1]).
     BatchResult align_batch_concat(const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all, const int64_t* b_off, size_t n,
                                    bool trace) {
         BatchResult r;
         std::vector<int64_t> costs(n ? n : 1), off(n ? n : 1), len(n ? n : 1);
         char* pool = nullptr;
-        int rc = apa_align_batch(engine_, (int)preset_, trace ? 1 : 0, n, a_all, a_off, b_all, b_off, costs.data(), &pool, off.data(),
-                                 len.data(), &r.stats);
+        int rc = has_params_ ? apa_align_batch_params(engine_, &params_, trace ? 1 : 0, n, a_all, a_off, b_all, b_off, costs.data(), &pool,
+                                                      off.data(), len.data(), &r.stats)
+                             : apa_align_batch(engine_, (int)preset_, trace ? 1 : 0, n, a_all, a_off, b_all, b_off, costs.data(), &pool,
+                                               off.data(), len.data(), &r.stats);
         if (rc != APA_OK) throw Error(rc, std::string("apa_align_batch: ") + apa_last_error());
         r.costs.resize(n);
         for (size_t p = 0; p < n; p++) r.costs[p] = (Cost)costs[p];
@@ -186,7 +270,10 @@ class AstarPa2 {
     apa_engine* engine_ = nullptr;
     Preset preset_;
     bool trace_;
+    apa_params params_{};
+    bool has_params_ = false;
 };
+inline AstarPa2 AstarPa2Params::make_aligner(bool trace, int device) const { return AstarPa2(static_cast<const apa_params&>(*this), trace, device); }
 
 // astarpa2::astarpa2_simple / astarpa2_full (astarpa2/src/lib.rs:44-53): a fresh aligner per call, with trace.
 inline std::pair<Cost, Cigar> astarpa2_simple(Seq a, Seq b) {

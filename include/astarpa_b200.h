@@ -74,6 +74,15 @@ int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace);
  * strlen cigar_len[p] (pairs finish in any order, so offsets are not monotone). */
 int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len);
 int apa_batch_get_stats(apa_batch* b, apa_batch_stats* out);
+/* Per-pair counters of the last run (the stats surface of AstarPa2StatsAligner::align_with_stats, astarpa2/src/lib.rs:200-208):
+ * AstarPa2Stats.f_max_tries (domain.rs:36), h0 = h(0,0) (lib.rs:124), pa_heuristic's num_matches and h_calls (GCSH only, 0
+ * otherwise), BlockStats-style computed cells (64 * lanes * cols actually evaluated here: blocks are always recomputed, so
+ * this is >= the reference's incremental count), TraceStats.dt_trace_success and fill_tries (trace.rs:3-14). Timers are
+ * per batch (apa_batch_stats), not per pair. */
+typedef struct apa_pair_stats {
+    int64_t f_max_tries, h0, num_matches, h_calls, computed_cells, dt_trace_success, fill_tries, reserved;
+} apa_pair_stats;
+int apa_batch_download_pair_stats(apa_engine* e, apa_batch* b, apa_pair_stats* out /* n_pairs entries */);
 void apa_batch_free(apa_engine* e, apa_batch* b);
 void apa_free(void* p);
 /* Page-locked host buffers for the end-to-end path (H2D/D2H at full PCIe rate). */

@@ -71,6 +71,31 @@ int main(int argc, char** argv) {
         auto [c1, g1] = astarpa2_simple(a, b);
         auto [c2, g2] = astarpa2_full(a, b);
         CHECK(c1 == 2 && c2 == 2 && g1.verify(a, b) == 2 && g2.verify(a, b) == 2);
+        // explicit parameters (general kernel) and the stats surface (align_with_stats, lib.rs:200-208)
+        {
+            AstarPa2Params q = AstarPa2Params::nw();  // params.rs:46-68: the full n*m rectangle in one pass
+            AstarPa2 nw = q.make_aligner(true);
+            auto [al, st] = nw.align_with_stats(a, b);
+            CHECK(al.first == 2 && al.second.has_value() && al.second->verify(a, b) == 2);
+            CHECK(st.f_max_tries == 1 && st.h0 == 0 && st.num_matches == 0);
+            AstarPa2Params g = AstarPa2Params::simple();
+            g.domain = APA_DOMAIN_GAP_GAP;  // Edlib-like band (tests.rs:24-32)
+            g.block_width = 64;
+            g.doubling_start = APA_START_GAP;
+            CHECK(g.make_aligner(false).cost(a, b) == 2);
+            AstarPa2 full = AstarPa2::full(true);
+            auto [al2, st2] = full.align_with_stats(a, b);
+            CHECK(al2.first == 2 && st2.f_max_tries >= 1 && st2.h0 <= 2);
+            bool threw2 = false;
+            try {
+                AstarPa2Params bad = AstarPa2Params::full();
+                bad.r = 2;  // inexact matches are not built
+                bad.make_aligner(true).align(a, b);
+            } catch (const Error& e) {
+                threw2 = e.code == APA_ERR_BAD_INPUT;
+            }
+            CHECK(threw2);
+        }
         AstarPa2 cost_only = AstarPa2::full(false);
         auto r = cost_only.align(a, b);
         CHECK(r.first == 2 && !r.second.has_value());  // trace = false: Aligner::align returns no CIGAR (lib.rs:74-77)

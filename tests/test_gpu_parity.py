@@ -305,3 +305,48 @@ def test_general_params_rejects_unsupported_gpu(apa):
                 P.simple().replace(doubling="none"), P.simple().replace(max_g=100)):
         with pytest.raises(apa.AstarPaError):
             apa.AstarPa2(bad, True).align(b"ACGT", b"ACGT")
+
+
+@pytest.mark.parametrize("preset", GENERAL_PRESETS)
+def test_pair_stats_match_oracle_gpu(apa, oracle, preset):
+    # SURVEY 8f row 4, the stats surface (align_with_stats, astarpa2/src/lib.rs:200-208): the counters that do not depend
+    # on incremental-vs-recompute accounting must equal the oracle's AstarPa2Stats / TraceStats, pair by pair.
+    pairs = [apa.generate_pair(n, e, m, 991 + n) for n, e, m in [(0, 0.0, 0), (50, 0.2, 1), (700, 0.1, 2), (3000, 0.05, 0), (3000, 0.2, 3)]]
+    for aligner in ([apa.AstarPa2(preset, True)] if preset < 2 else []) + [apa.AstarPa2(params_for(apa, preset), True)]:
+        costs, cigars, stats = aligner.align_batch_with_stats(pairs)
+        for (a, b), c, cg, st in zip(pairs, costs, cigars, stats):
+            oc, ocg, ost = oracle.align(a, b, preset, True)
+            assert (int(c), cg) == (oc, ocg)
+            par = params_for(apa, preset)
+            gcsh = par.domain == 3 and par.heuristic == 2  # h_calls / num_matches are GCSH counters (0 otherwise)
+            keys = ("f_max_tries", "h0", "dt_trace_success", "fill_tries") + (("num_matches", "h_calls") if gcsh else ())
+            got = {k: st[k] for k in keys}
+            want = {k: ost[k] for k in got}
+            assert got == want, (preset, len(a), got, want)
+            assert st["computed_cells"] >= ost["computed_cells"] >= 0
+
+
+# ---------------------------------------------------------------------------------------------- intra-pair parallelism
+@pytest.mark.parametrize("coop", ["1", "4", "8"])
+@pytest.mark.parametrize("preset", PRESETS)
+def test_coop_pass_kernel_gpu(apa, oracle, preset, coop, monkeypatch):
+    # apa_coop.cuh: the warps of a CTA share the chunks of one pair's band. Small batches pick it automatically (8 warps per
+    # pair); APA_COOP forces 1 / 4 / 8 so that every variant sees the same shapes: tall bands (astarpa2_simple at high
+    # divergence: tens of chunks per block), single-chunk bands, empty and tiny pairs.
+    monkeypatch.setenv("APA_COOP", coop)
+    pairs = [apa.generate_pair(n, e, model, 4242 + n + model) for n, e, model in
+             [(0, 0.0, 0), (1, 1.0, 0), (40, 0.3, 1), (700, 0.5, 2), (5000, 0.3, 0), (20000, 0.25, 3), (60000, 0.1, 0), (60000, 0.02, 1),
+              (100000, 0.05, 0)]]
+    _check_pairs(apa, oracle, pairs, preset)
+    _check_pairs(apa, oracle, pairs[3:7], preset, trace=False)
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_waves_when_arenas_do_not_fit_gpu(apa, oracle, preset, monkeypatch):
+    # A work list whose per-pair arenas exceed the memory budget runs the phase-split path in waves (BASELINE configs[3] does
+    # this for real); the budget is forced down so that 40 pairs take several waves.
+    rng = np.random.default_rng(5)
+    pairs = [apa.generate_pair(int(rng.integers(2000, 30000)), float(rng.choice([0.05, 0.15])), 0, int(rng.integers(1 << 40)))
+             for _ in range(40)]
+    monkeypatch.setenv("APA_BUDGET_BYTES", str(12 << 20))
+    _check_pairs(apa, oracle, pairs, preset)
