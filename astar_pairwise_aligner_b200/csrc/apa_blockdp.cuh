@@ -18,6 +18,11 @@ namespace APA_NS {
 // instead of an a-mask load and 2 LOP3: the ALU pipe is the one the block DP saturates (profiles/README.md), the FMA pipe
 // and the shared-memory pipe have room. Measured on B200: pass kernel of astarpa2_simple 150.1 -> 137.2 ms per 2 000 pairs,
 // astarpa2_full 47.5 -> 47.1 ms per 10 000 pairs. APA_DP_V2=0 keeps the first formulation (make ab) for A/B measurements.
+// APA_SMALL_CODE (default): the ramp-up / ramp-down loops of dp_chunk are not unrolled. The pass kernel stalls on
+// instruction fetch (no_instruction is its #3 stall reason, profiles/r1c_*): 16.3k -> 10.3k SASS instructions, 47.8 -> 45.7 ms.
+#ifndef APA_SMALL_CODE
+#define APA_SMALL_CODE 1
+#endif
 #ifndef APA_DP_V2
 #define APA_DP_V2 1
 #endif
@@ -168,6 +173,9 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
     };
     int t = 0;
     const int t_steady = min(nact - 1, ncols);  // first step at which every active lane has a valid column
+#if APA_SMALL_CODE
+#pragma unroll 1
+#endif
     for (; t < t_steady; t++) step_guarded(t);
     if (nact - 1 < ncols) {
         // steady state: every lane has a valid column; the eq word of the next step is fetched one step ahead
@@ -183,6 +191,9 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
         }
     }
     const int T = ncols + nact - 1;
+#if APA_SMALL_CODE
+#pragma unroll 1
+#endif
     for (; t < T; t++) step_guarded(t);
 }
 

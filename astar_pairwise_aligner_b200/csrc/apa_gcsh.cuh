@@ -85,6 +85,7 @@ struct GcshH {
     // streams - band end, fixed-range start, fixed-range end - each of which moves smoothly from block to block),
     // then, on a miss, strided probes away from that window (stride 1, 16, 256, ...) until the answer is bracketed,
     // then 32-ary refinement. The result does not depend on the hints.
+    // (kept inlined at its call sites: a __noinline__ score() shrinks the pass kernel by 15 % but measured 5 % slower)
     __device__ int score(I qx, I qy, int slot) {
         const int lane = threadIdx.x & 31;
         if (nlayers == 0) return 0;

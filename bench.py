@@ -107,7 +107,8 @@ KERNELS = ["apa_phase_build_kernel", "apa_phase_pass_kernel", "apa_phase_trace_k
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from the `ncu --set full` captures of the headline
 # shape (astarpa2_full, n=100k, e=5 %, cost+CIGAR), in MB PER PAIR; scaled by the pairs of a launch. Source files are
 # named next to each figure. None for shapes that were not captured.
-NCU_TRAFFIC_MB_PER_PAIR = {}
+NCU_TRAFFIC_MB_PER_PAIR = {  # profiles/r1c_dram_bytes.csv (10 000 pairs per launch)
+    "apa_phase_build_kernel": 5.574, "apa_phase_pass_kernel": 0.949, "apa_phase_trace_kernel": 0.272}
 
 
 def traffic_per_launch(args, kernel):
@@ -165,7 +166,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     trace = not args.no_trace
     preset_id = {"simple": 0, "full": 1}[args.preset]
-    workload = (f"BASELINE configs[2]: {args.pairs} pairs/GPU, n={args.n}, e={args.e:g}, uniform errors, astarpa2_{args.preset}, "
+    # which BASELINE.json config this shape is (the default run is configs[2], the one the metric is quoted on)
+    shape = (args.n, round(args.e, 3), trace, args.preset)
+    cfg = {(100000, 0.05, True, "full"): "BASELINE configs[2]", (10000, 0.05, False, "full"): "BASELINE configs[1]",
+           (1000000, 0.15, True, "full"): "BASELINE configs[3]", (10000000, 0.05, True, "full"): "BASELINE configs[4]"}.get(shape, "other shape")
+    workload = (f"{cfg}: {args.pairs} pairs/GPU, n={args.n}, e={args.e:g}, uniform errors, astarpa2_{args.preset}, "
                 f"{'cost+CIGAR' if trace else 'cost only'}; inputs {2 * args.pairs * args.n / 1e9:.2f} GB/GPU > L2 (no flush needed)")
     config = {"workload": workload, "pairs_per_gpu": args.pairs, "n": args.n, "e": args.e, "preset": args.preset, "trace": trace,
               "sharding": f"independent pairs, {world} rank(s), no data-path collective", "l2": "inputs larger than L2"}
