@@ -23,9 +23,14 @@ namespace APA_NS {
 #ifndef APA_SMALL_CODE
 #define APA_SMALL_CODE 1
 #endif
+#ifndef APA_DP_UNROLL
+#define APA_DP_UNROLL 4
+#endif
 #ifndef APA_DP_V2
 #define APA_DP_V2 1
 #endif
+
+constexpr int DP_UNROLL = APA_DP_UNROLL;  // steady-state steps per loop iteration of dp_chunk
 
 struct WarpSmem {
 #if APA_DP_V2
@@ -181,7 +186,7 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
         // steady state: every lane has a valid column; the eq word of the next step is fetched one step ahead
         // (achar is padded, so the fetch past the last column of lane 0 stays in bounds)
         uint32_t eq_next = load_eq(t - r);
-#pragma unroll 4
+#pragma unroll DP_UNROLL
         for (; t < ncols; t++) {
             const uint32_t eq = eq_next;
             eq_next = load_eq(t + 1 - r);
