@@ -108,7 +108,7 @@ KERNELS = ["apa_phase_build_kernel", "apa_phase_pass_kernel", "apa_phase_trace_k
 # shape (astarpa2_full, n=100k, e=5 %, cost+CIGAR), in MB PER PAIR; scaled by the pairs of a launch. Source files are
 # named next to each figure. None for shapes that were not captured.
 NCU_TRAFFIC_MB_PER_PAIR = {  # profiles/r1c_dram_bytes.csv (10 000 pairs per launch)
-    "apa_phase_build_kernel": 5.574, "apa_phase_pass_kernel": 0.949, "apa_phase_trace_kernel": 0.272}
+    "apa_phase_build_kernel": 5.447, "apa_phase_pass_kernel": 0.784, "apa_phase_trace_kernel": 0.271}
 
 
 def traffic_per_launch(args, kernel):
