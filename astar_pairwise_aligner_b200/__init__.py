@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 __all__ = ["AstarPa2", "AstarPa2Params", "AstarPaError", "Engine", "astarpa2_simple", "astarpa2_full", "generate_pair",
-           "generate_batch", "PRESET_SIMPLE", "PRESET_FULL", "lib_path", "load_library"]
+           "generate_batch", "search", "PRESET_SIMPLE", "PRESET_FULL", "lib_path", "load_library"]
 
 PRESET_SIMPLE, PRESET_FULL = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -129,6 +129,7 @@ def load_library():
     L.apa_debug_band_log_params.restype = C.c_int64
     L.apa_debug_band_log_params.argtypes = [C.c_void_p, pp, C.c_int, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64]
     L.apa_batch_download_pair_stats.argtypes = [C.c_void_p, C.c_void_p, vp]
+    L.apa_search.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, C.c_float, vp]
     L.apa_free.argtypes = [C.c_void_p]
     L.apa_pinned_alloc.restype = C.c_void_p
     L.apa_pinned_alloc.argtypes = [C.c_uint64]
@@ -253,6 +254,15 @@ class Engine:
     def free_pool(self, pool):
         if pool and pool.value:
             self._L.apa_free(pool)
+
+    def search(self, pattern: bytes, text: bytes, unmatched_cost: float = 0.0):
+        """pa_bitpacking::search(pattern, text, unmatched_cost).out (pa-bitpacking/src/search.rs:46-118) as a numpy int32 array:
+        the costs along the bottom row and up the right column of the semi-global DP, |pattern| + |text| + 1 values."""
+        out = np.zeros(len(pattern) + len(text) + 1, dtype=np.int32)
+        pb = np.frombuffer(pattern, dtype=np.uint8) if pattern else np.zeros(1, np.uint8)
+        tb = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(1, np.uint8)
+        _check(self._L.apa_search(self._h, pb.ctypes.data, len(pattern), tb.ctypes.data, len(text), float(unmatched_cost), out.ctypes.data))
+        return out
 
     def block_compute(self, a: bytes, b: bytes, v=None):
         """pa_bitpacking::simd::compute on the GPU with +1 top deltas. Returns (bottom_sum, h_out, v_out)."""
@@ -419,6 +429,11 @@ class AstarPa2:
             return self.align(a, b)[0]
         finally:
             self.trace = saved
+
+
+def search(pattern: bytes, text: bytes, unmatched_cost: float = 0.0, device=0):
+    """pa_bitpacking::search (pa-bitpacking/src/search.rs:46): see Engine.search."""
+    return _engine(device).search(pattern, text, unmatched_cost)
 
 
 def astarpa2_simple(a: bytes, b: bytes):

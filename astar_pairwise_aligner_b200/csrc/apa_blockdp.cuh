@@ -125,7 +125,8 @@ __device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restric
 // lanes 1 .. nact-1 (at most 31). Otherwise lane 0 is the first row and takes its incoming deltas from sm.hrow, where
 // the last lane of the previous chunk left them. HAND_OFF: the last lane publishes its bottom deltas for the next chunk.
 // The sweep is split into ramp-up / steady / ramp-down so the steady state (all lanes busy) runs without guards.
-template <bool FILL, bool FIRST, bool HAND_OFF>
+// CUSTOM_ETAB: the caller has filled sm.etab itself (match masks that are not plain base equality: apa_search).
+template <bool FILL, bool FIRST, bool HAND_OFF, bool CUSTOM_ETAB = false>
 __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint32_t b0, uint32_t b1, uint32_t& vp, uint32_t& vm,
                                          uint2* __restrict__ fillcol /* fillvals + hw of this lane */, int nhw) {
     const int lane = threadIdx.x & 31;
@@ -136,7 +137,7 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
     const int r = act_lane ? lane : 0;  // idle lanes shadow lane 0 on valid addresses; their results are never stored
     uint32_t cp_o = FIRST ? 1u : 0u, cm_o = 0u;  // the feeder's constant output (idle lanes carry it too, unused)
 #if APA_DP_V2
-    stage_etab(sm, b0, b1, lane);
+    if (!CUSTOM_ETAB) stage_etab(sm, b0, b1, lane);
     __syncwarp();
     const uint32_t etab_lane = (uint32_t)__cvta_generic_to_shared(&sm.etab[lane]);
     // eq word of this lane's rows against column `col`: etab[achar[col] * 32 + lane]; the address is one IMAD

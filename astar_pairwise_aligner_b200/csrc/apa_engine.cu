@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -393,6 +394,48 @@ __global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof,
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// pa_bitpacking::search on one warp (pa-bitpacking/src/search.rs:46-118, simd/scatter_profile.rs): the text runs along the columns
+// in slabs of 256, the (short) pattern along the rows. Top deltas are 0 (a match may start anywhere in the text), so every
+// chunk takes its incoming deltas from sm.hrow (zeroed for the first chunk) and leaves its bottom deltas there; what the last
+// chunk leaves is the bottom row of the slab. The equality words are the pattern's match masks (wildcards N * Y R and the
+// all-matching padding rows, profile.rs:39-66), which the per-lane table of the block DP takes as they are.
+__global__ void apa_search_kernel(const uint8_t* __restrict__ text, int nt, const uint4* __restrict__ pmask, int nhw, uint2* v,
+                                  int8_t* __restrict__ hdelta) {
+    __shared__ WarpSmem sm;
+    const int lane = threadIdx.x & 31;
+    const int nchunks = (nhw + 31) / 32;
+    for (int c0 = 0; c0 < nt; c0 += BLOCK_W) {
+        const int nc = min(BLOCK_W, nt - c0);
+        for (int k = lane; k < BLOCK_W + 4; k += 32) sm.achar[k] = k < nc ? (uint8_t)((text[c0 + k] >> 1) & 3u) : (uint8_t)0;  // A0 C1 T2 G3
+        for (int k = lane; k < BLOCK_W; k += 32) sm.hrow[k] = 0;
+        __syncwarp();
+        for (int c = 0; c < nchunks; c++) {
+            const int nrow = min(32, nhw - 32 * c);
+            const bool is_row = lane < nrow;
+            const int hw = 32 * c + (is_row ? lane : 0);
+            uint32_t vp = 0u, vm = 0u;
+            uint4 pm = make_uint4(0u, 0u, 0u, 0u);
+            if (is_row) {
+                const uint2 x = v[hw];
+                vp = x.x, vm = x.y;
+                pm = pmask[hw];
+            }
+            sm.etab[0 * 32 + lane] = pm.x;
+            sm.etab[1 * 32 + lane] = pm.y;
+            sm.etab[2 * 32 + lane] = pm.z;
+            sm.etab[3 * 32 + lane] = pm.w;
+            dp_chunk<false, false, true, true>(sm, nc, nrow, 0u, 0u, vp, vm, nullptr, nhw);
+            __syncwarp();
+            if (is_row) v[hw] = make_uint2(vp, vm);
+        }
+        for (int k = lane; k < nc; k += 32) {
+            const uint32_t x = sm.hrow[k];
+            hdelta[c0 + k] = (int8_t)((int)(x & 1u) - (int)(x >> 1));
+        }
+        __syncwarp();
+    }
+}
+
 struct apa_engine;
 static cudaError_t eng_alloc(apa_engine* e, void** out, size_t bytes);
 static void eng_release(apa_engine* e, void* p);
@@ -1320,6 +1363,111 @@ static int64_t band_log_impl(apa_engine* e, int preset, const apa_params* params
     }
     for (size_t t = 0; t < o.size() && t < cap; t++) out[t] = o[t];
     return (int64_t)o.size();
+}
+
+// ------------------------------------------------------------------------------------------------ pa_bitpacking::search
+extern "C" int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t np, const uint8_t* text, uint64_t nt, float unmatched_cost,
+                          int32_t* out) {
+    if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
+    if (!(unmatched_cost >= 0.0f && unmatched_cost <= 1.0f)) return set_err(APA_ERR_BAD_INPUT, "unmatched_cost must be in [0, 1]");
+    if (nt >= (1ull << 31) - 1024 || np >= (1ull << 24)) return set_err(APA_ERR_TOO_LARGE, "search: text < 2^31, pattern < 2^24");
+    CUDA_TRY(cudaSetDevice(e->device));
+    // ScatterProfile::build (profile.rs:28-66): per 32 rows of the pattern, the rows matching A / C / T / G.
+    const uint64_t nwords = (np + 63) / 64, nhw = nwords * 2;
+    std::vector<uint32_t> pmask(nhw * 4, 0u), v0(nhw * 2, 0u);
+    for (uint64_t j = 0; j < np; j++) {
+        uint32_t m4 = 0;  // bit i: matches base i (A0 C1 T2 G3)
+        switch (pattern[j]) {
+            case 'a': case 'A': m4 = 1; break;
+            case 'c': case 'C': m4 = 2; break;
+            case 't': case 'T': m4 = 4; break;
+            case 'g': case 'G': m4 = 8; break;
+            case 'n': case 'N': case '*': m4 = 15; break;
+            case 'y': case 'Y': m4 = 6; break;  // C or T
+            case 'r': case 'R': m4 = 9; break;  // A or G
+            default: return set_err(APA_ERR_BAD_INPUT, "search: unknown pattern base (ACGT, N, *, Y, R)");
+        }
+        for (int i = 0; i < 4; i++)
+            if (m4 >> i & 1) pmask[(j / 32) * 4 + i] |= 1u << (j % 32);
+    }
+    for (uint64_t j = np; j < nwords * 64; j++)
+        for (int i = 0; i < 4; i++) pmask[(j / 32) * 4 + i] |= 1u << (j % 32);  // padding rows match everything
+    for (uint64_t i = 0; i < nt; i++) {
+        const uint8_t c = text[i] & 0xDF;  // acgtACGT only (profile.rs:31-38)
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return set_err(APA_ERR_BAD_INPUT, "search: text byte outside acgtACGT");
+    }
+    if (unmatched_cost > 0.0f) {  // search.rs:58-66
+        for (uint64_t i = 0;; i++) {
+            const uint64_t idx = (uint64_t)std::ceil((float)i / unmatched_cost);
+            if (idx >= np) break;
+            v0[(idx / 32) * 2] |= 1u << (idx % 32);
+        }
+    }
+    std::vector<uint32_t> vfin(v0);
+    std::vector<int8_t> hd(std::max<uint64_t>(nt, 1), 0);
+    if (nt > 0 && nhw > 0) {
+        uint8_t* d_text = nullptr;
+        uint4* d_pmask = nullptr;
+        uint2* d_v = nullptr;
+        int8_t* d_h = nullptr;
+        cudaStream_t st = e->stream;
+        cudaError_t ce = cudaMalloc(&d_text, nt);
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_pmask, nhw * 16);
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_v, nhw * 8);
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_h, nt);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_text, text, nt, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_pmask, pmask.data(), nhw * 16, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_v, v0.data(), nhw * 8, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) {
+            apa_search_kernel<<<1, 32, 0, st>>>(d_text, (int)nt, d_pmask, (int)nhw, d_v, d_h);
+            ce = cudaGetLastError();
+        }
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(vfin.data(), d_v, nhw * 8, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(hd.data(), d_h, nt, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        cudaFree(d_text);
+        cudaFree(d_pmask);
+        cudaFree(d_v);
+        cudaFree(d_h);
+        if (ce != cudaSuccess) return set_err(APA_ERR_CUDA, std::string("apa_search: ") + cudaGetErrorString(ce));
+    }
+    // Output assembly (search.rs:72-104): bottom row, then up the right column; the first `padding` values are skipped
+    // because the pattern was rounded up to a multiple of 64 rows.
+    auto word = [&](const std::vector<uint32_t>& vv, uint64_t w, int pm) -> uint64_t {
+        return (uint64_t)vv[(2 * w) * 2 + pm] | ((uint64_t)vv[(2 * w + 1) * 2 + pm] << 32);
+    };
+    auto value = [&](const std::vector<uint32_t>& vv, uint64_t w) -> int {
+        return __builtin_popcountll(word(vv, w, 0)) - __builtin_popcountll(word(vv, w, 1));
+    };
+    auto suffix = [&](const std::vector<uint32_t>& vv, uint64_t w, int j) -> int {
+        const uint64_t mask = ~((1ull << (64 - j)) - 1ull);  // V::value_of_suffix, encoding.rs:33-38 (0 < j <= 64)
+        return __builtin_popcountll(word(vv, w, 0) & mask) - __builtin_popcountll(word(vv, w, 1) & mask);
+    };
+    const uint64_t padding = nwords * 64 - np;
+    int b = 0;
+    for (uint64_t w = 0; w < nwords; w++) b += value(v0, w);
+    uint64_t n_out = 0, skipped = 0;
+    out[n_out++] = b;
+    for (uint64_t i = 0; i < nt; i++) {
+        b += hd[i];
+        if (skipped < padding)
+            skipped++;
+        else
+            out[n_out++] = b;
+    }
+    for (uint64_t w = nwords; w-- > 0;) {
+        for (int j = 1; j <= 64; j++) {
+            const int val = b - suffix(vfin, w, j) + suffix(v0, w, j);
+            if (skipped < padding)
+                skipped++;
+            else
+                out[n_out++] = val;
+        }
+        b -= value(vfin, w);
+        b += value(v0, w);
+    }
+    if (n_out != np + nt + 1) return set_err(APA_ERR_INTERNAL, "search: output length");
+    return APA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ block KAT entry

@@ -11,6 +11,7 @@
 //   astarpa2::AstarPa2Params{...}.make_aligner(trace)    AstarPa2Params::make_aligner (params.rs:132-226): other domains,
 //                                                        heuristics, doubling types, block widths (general kernel)
 //   AstarPa2::align_with_stats(a, b)                     AstarPa2StatsAligner::align_with_stats, astarpa2/src/lib.rs:200-208
+//   astarpa2::search(pattern, text, unmatched_cost)     pa_bitpacking::search(..).out, pa-bitpacking/src/search.rs:46-118
 //   AstarPa2::align_batch(pairs)                         no reference counterpart: one call carries a whole batch
 //                                                        to the GPU (SURVEY 8b "needed extension")
 //   Cigar::{to_string, parse, verify}                    pa_types::Cigar (external crate; text format pinned by
@@ -274,6 +275,20 @@ class AstarPa2 {
     bool has_params_ = false;
 };
 inline AstarPa2 AstarPa2Params::make_aligner(bool trace, int device) const { return AstarPa2(static_cast<const apa_params&>(*this), trace, device); }
+
+// pa_bitpacking::search(pattern, text, unmatched_cost).out (pa-bitpacking/src/search.rs:46-118): the costs along the bottom row
+// and up the right column of the semi-global DP; |pattern| + |text| + 1 values. Pattern may hold N, *, Y, R.
+inline std::vector<Cost> search(Seq pattern, Seq text, float unmatched_cost = 0.0f, int device = 0) {
+    apa_engine* e = nullptr;
+    int rc = apa_engine_create(device, &e);
+    if (rc != APA_OK) throw Error(rc, std::string("apa_engine_create: ") + apa_last_error());
+    std::vector<Cost> out(pattern.size() + text.size() + 1);
+    rc = apa_search(e, (const uint8_t*)pattern.data(), pattern.size(), (const uint8_t*)text.data(), text.size(), unmatched_cost, out.data());
+    std::string msg = rc == APA_OK ? "" : std::string("apa_search: ") + apa_last_error();
+    apa_engine_destroy(e);
+    if (rc != APA_OK) throw Error(rc, msg);
+    return out;
+}
 
 // astarpa2::astarpa2_simple / astarpa2_full (astarpa2/src/lib.rs:44-53): a fresh aligner per call, with trace.
 inline std::pair<Cost, Cigar> astarpa2_simple(Seq a, Seq b) {

@@ -147,6 +147,14 @@ int64_t apa_debug_band_log_params(apa_engine* e, const apa_params* params, int t
 int64_t apa_debug_band_log(apa_engine* e, int preset, int trace, const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m,
                            int32_t* out, uint64_t cap);
 
+/* pa_bitpacking::search (pa-bitpacking/src/search.rs:46-118): semi-global search of a short pattern (may contain the
+ * wildcards N, *, Y = C|T, R = A|G) in a long text (acgtACGT). A match may start anywhere in the text and anywhere in the
+ * pattern; unmatched pattern rows cost `unmatched_cost` each (0..1, realised as one +1 row every 1/unmatched_cost rows).
+ * out receives pattern_len + text_len + 1 costs: along the bottom row, then up the right column (search.rs:36-45). The DP
+ * runs on the GPU (the block-DP step with zero top deltas and the pattern's match masks as equality words). */
+int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t pattern_len, const uint8_t* text, uint64_t text_len,
+               float unmatched_cost, int32_t* out);
+
 /* Block-DP kernel on its own (pa_bitpacking::simd::compute semantics, pa-bitpacking/src/simd.rs:98-226):
  * rectangle a[na] x b[mb]; h one byte per column (bit0 = +1, bit1 = -1), in/out; v interleaved (p,m) u64 pairs
  * per 64-row word, in/out. Returns the sum of the bottom-row deltas via *bottom_sum. */

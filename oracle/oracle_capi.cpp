@@ -16,6 +16,7 @@
 #include <thread>
 
 #include "astarpa2.hpp"
+#include "search.hpp"
 
 using namespace oracle;
 
@@ -288,6 +289,17 @@ int64_t oracle_bp_compute(const uint8_t* a, size_t na, const uint8_t* b, size_t 
 }
 
 uint64_t oracle_to_qgram(const uint8_t* s, int k) { return QGrams::to_qgram(s, k); }
+
+// pa_bitpacking::search (search.rs:46-118): out must hold np + nt + 1 values. Returns the count, or -1 on a reference panic.
+int64_t oracle_search(const uint8_t* pattern, size_t np, const uint8_t* text, size_t nt, float unmatched_cost, int32_t* out) {
+    try {
+        std::vector<Cost> o = search(pattern, np, text, nt, unmatched_cost);
+        for (size_t i = 0; i < o.size(); i++) out[i] = o[i];
+        return (int64_t)o.size();
+    } catch (const RefPanic&) {
+        return -1;
+    }
+}
 
 // GCSH introspection: number of matches kept after transform filter + local pruning, and h(0,0).
 int64_t oracle_gcsh_info(const uint8_t* a, size_t n, const uint8_t* b, size_t m, int k, int p, int64_t* h0,

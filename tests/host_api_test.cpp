@@ -96,6 +96,11 @@ int main(int argc, char** argv) {
             }
             CHECK(threw2);
         }
+        {   // pa_bitpacking::search doc-test (pa-bitpacking/src/search.rs:29-32)
+            std::vector<Cost> out = search("AC", "CTTACTTA", 0.0f);
+            const std::vector<Cost> want = {0, 0, 1, 2, 1, 0, 1, 2, 1, 0, 0};
+            CHECK(out == want);
+        }
         AstarPa2 cost_only = AstarPa2::full(false);
         auto r = cost_only.align(a, b);
         CHECK(r.first == 2 && !r.second.has_value());  // trace = false: Aligner::align returns no CIGAR (lib.rs:74-77)

@@ -55,6 +55,8 @@ def lib():
         L.oracle_align_batch.restype = C.c_double
         L.oracle_align_batch.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_search.restype = C.c_int64
+        L.oracle_search.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_float, C.c_void_p]
         L.oracle_hardware_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -135,3 +137,12 @@ def align_batch(a_all, a_off, b_all, b_off, preset=PRESET_FULL, trace=True, thre
                                b_off.ctypes.data, threads, costs.ctypes.data, clens.ctypes.data, cells.ctypes.data,
                                chash.ctypes.data)
     return sec, costs, clens, cells, chash
+
+
+def search(pattern: bytes, text: bytes, unmatched_cost: float = 0.0):
+    """pa_bitpacking::search(...).out (pa-bitpacking/src/search.rs:46-118) as a list of ints."""
+    out = np.zeros(len(pattern) + len(text) + 1, dtype=np.int32)
+    w = lib().oracle_search(pattern, len(pattern), text, len(text), unmatched_cost, out.ctypes.data)
+    if w < 0:
+        raise OraclePanic("panic in search")
+    return out[:w].tolist()

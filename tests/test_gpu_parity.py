@@ -350,3 +350,27 @@ def test_waves_when_arenas_do_not_fit_gpu(apa, oracle, preset, monkeypatch):
              for _ in range(40)]
     monkeypatch.setenv("APA_BUDGET_BYTES", str(12 << 20))
     _check_pairs(apa, oracle, pairs, preset)
+
+
+# ---------------------------------------------------------------------------------------------- pa_bitpacking::search
+def test_search_gpu(apa, oracle):
+    # SURVEY 8f row 4, second half: the semi-global pattern search (pa-bitpacking/src/search.rs:46-118) on the block-DP
+    # kernel. The reference's doc-test vector, then random patterns with wildcards against the oracle: single- and multi-chunk
+    # patterns (up to 3 000 rows), single- and multi-slab texts, every unmatched_cost class, empty inputs.
+    assert apa.search(b"AC", b"CTTACTTA", 0.0).tolist() == [0, 0, 1, 2, 1, 0, 1, 2, 1, 0, 0]
+    import random
+    rng = random.Random(3)
+    for n_p, n_t in [(1, 0), (1, 1), (5, 70), (63, 200), (64, 256), (65, 257), (130, 1000), (1000, 3000), (1025, 600), (3000, 5000),
+                     (20, 100000), (0, 10)]:
+        for u in (0.0, 1.0, 0.5, 0.3):
+            p = bytes(rng.choice(b"ACGTACGTACGTNYR*acgt") for _ in range(n_p))
+            t = bytes(rng.choice(b"ACGTacgt") for _ in range(n_t))
+            assert apa.search(p, t, u).tolist() == oracle.search(p, t, u), (n_p, n_t, u)
+    # a planted occurrence is found with cost 0 at its end column
+    t = bytes(rng.choice(b"ACGT") for _ in range(4000))
+    p = t[1234:1300]
+    out = apa.search(p, t, 0.0)
+    assert out[1300] == 0 and out[:len(t) + 1].min() == 0
+    for bad in ((b"AX", b"ACGT", 0.0), (b"AC", b"ACGN", 0.0), (b"AC", b"ACGT", 2.0)):
+        with pytest.raises(apa.AstarPaError):
+            apa.search(*bad)

@@ -1,0 +1,68 @@
+"""pa_bitpacking::search: the oracle restatement against the reference's own doc-test vector and against an
+independent dynamic program of the documented semantics (pa-bitpacking/src/search.rs:16-45)."""
+import math
+import random
+
+import pytest
+
+
+def _match(pc, tc):
+    pc, tc = pc.upper(), tc.upper()
+    if pc in "N*":
+        return True
+    if pc == "Y":
+        return tc in "CT"
+    if pc == "R":
+        return tc in "AG"
+    return pc == tc
+
+
+def brute_search(p: bytes, t: bytes, u: float):
+    """Semi-global DP: free start anywhere in the text (top row 0); unmatched pattern prefix / suffix rows cost 1 where the
+    reference sets a bit of v0 (every ceil(i / u)-th row, search.rs:58-66). Output: bottom row, then up the right column with
+    the unmatched suffix added."""
+    n_p, n_t = len(p), len(t)
+    ones = set()
+    if u > 0:
+        i = 0
+        while True:
+            idx = math.ceil(i / u)
+            if idx >= n_p:
+                break
+            ones.add(idx)
+            i += 1
+    col0 = [0]
+    for j in range(n_p):
+        col0.append(col0[-1] + (1 if j in ones else 0))
+    D = [[0] * (n_t + 1) for _ in range(n_p + 1)]
+    for j in range(n_p + 1):
+        D[j][0] = col0[j]
+    for i in range(1, n_t + 1):
+        for j in range(1, n_p + 1):
+            D[j][i] = min(D[j - 1][i] + 1, D[j][i - 1] + 1, D[j - 1][i - 1] + (0 if _match(chr(p[j - 1]), chr(t[i - 1])) else 1))
+    return D[n_p][:] + [D[j][n_t] + col0[n_p] - col0[j] for j in range(n_p - 1, -1, -1)]
+
+
+def test_search_reference_doctest(oracle):
+    # pa-bitpacking/src/search.rs:29-32
+    assert oracle.search(b"AC", b"CTTACTTA", 0.0) == [0, 0, 1, 2, 1, 0, 1, 2, 1, 0, 0]
+
+
+def test_search_against_independent_dp(oracle):
+    rng = random.Random(1)
+    for _ in range(400):
+        n_p = rng.choice([1, 2, 5, 63, 64, 65, 100, 128, 130])
+        n_t = rng.choice([0, 1, 3, 10, 70, 200])
+        p = bytes(rng.choice(b"ACGTNYR*acgt") for _ in range(n_p))
+        t = bytes(rng.choice(b"ACGTacgt") for _ in range(n_t))
+        u = rng.choice([0.0, 1.0, 0.5, 0.25])
+        assert oracle.search(p, t, u) == brute_search(p, t, u), (n_p, n_t, u)
+
+
+def test_search_panics_like_the_reference(oracle):
+    with pytest.raises(oracle.OraclePanic):
+        oracle.search(b"AC", b"ACGN", 0.0)  # text must be acgtACGT (profile.rs:37)
+    with pytest.raises(oracle.OraclePanic):
+        oracle.search(b"AX", b"ACGT", 0.0)
+    with pytest.raises(oracle.OraclePanic):
+        oracle.search(b"AC", b"ACGT", 1.5)
