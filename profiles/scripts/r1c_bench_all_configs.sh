@@ -1,4 +1,5 @@
 #!/bin/bash
+# Run on a B200 box from the repo root (under gpurun): the commands behind the profiles/r1c_* artefacts.
 mkdir -p gpurun_out
 summ() { python - "$1" <<'PY'
 import json,sys

@@ -1,4 +1,5 @@
 #!/bin/bash
+# Run on a B200 box from the repo root (under gpurun): the commands behind the profiles/r1c_* artefacts.
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 summ() { python - "$1" <<'PY'
