@@ -78,3 +78,19 @@ def test_host_packer_matches_layout(apa):
         if n > 40:
             buf[37] = ord("N")
             assert L.apa_pack_planes_host(buf.ctypes.data, n, 0, nhw, ref.ctypes.data) == 1
+
+
+def test_params_presets_and_struct_layout(apa):
+    """apa_params / apa_pair_stats as the C header declares them (17 int32/float fields = 68 bytes, 8 int64 = 64 bytes), and the
+    presets filled by apa_params_preset equal AstarPa2Params::simple() / ::full() (astarpa2/src/params.rs:70-128). Host only."""
+    assert ctypes.sizeof(apa.AstarPa2Params) == 68 and ctypes.sizeof(apa.PairStats) == 64
+    s, f = apa.AstarPa2Params.simple(), apa.AstarPa2Params.full()
+    for q in (s, f):
+        assert (q.domain, q.doubling, q.doubling_start, q.block_width) == (3, 1, 2, 256)  # Astar, BandDoubling{H0, 2.0}
+        assert (q.factor, q.sparse, q.dt_trace, q.max_g, q.fr_drop, q.sparse_h) == (2.0, 1, 1, 40, 10, 1)
+    assert (s.heuristic, s.prune, s.incremental_doubling) == (1, 0, 0)  # GapCost, no pruning (params.rs:70-96)
+    assert (f.heuristic, f.k, f.r, f.p, f.prune, f.incremental_doubling) == (2, 12, 1, 14, 1, 1)  # GCSH (params.rs:98-128)
+    nw = apa.AstarPa2Params.nw()
+    assert (nw.domain, nw.doubling, nw.dt_trace) == (0, 0, 0)  # params.rs:46-68
+    g = f.replace(domain="gap_gap", block_width=64, doubling_start="gap")
+    assert (g.domain, g.block_width, g.doubling_start, g.k) == (2, 64, 1, 12) and f.domain == 3  # replace() copies
