@@ -702,8 +702,16 @@ struct Packer {  // packs all tasks with a few host threads; per-chunk completio
 };
 
 static int pack_threads() {
+    // Host threads that pack bases for one engine. One process per GPU: under torchrun the ranks of a node share the host
+    // cores, so each takes its share (LOCAL_WORLD_SIZE) instead of oversubscribing them; APA_PACK_THREADS overrides.
+    if (const char* ev = getenv("APA_PACK_THREADS")) return std::max(1, atoi(ev));
     unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(16u, hc ? hc : 4u));
+    unsigned n = std::max(1u, std::min(16u, hc ? hc : 4u));
+    if (const char* ev = getenv("LOCAL_WORLD_SIZE")) {
+        const unsigned ranks = (unsigned)std::max(1, atoi(ev));
+        n = std::max(2u, std::min(n, (hc ? hc : 4u) / ranks));
+    }
+    return (int)n;
 }
 
 static int upload_planes(apa_engine* e, apa_batch* b, bool streaming);
