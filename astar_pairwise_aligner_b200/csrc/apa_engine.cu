@@ -1337,7 +1337,12 @@ static int64_t band_log_impl(apa_engine* e, int preset, const apa_params* params
     apa_batch* bt = nullptr;
     int rc = apa_batch_upload(e, 1, a, a_off, b, b_off, &bt);
     if (rc != APA_OK) return rc;
-    const uint32_t rec_cap = 7u * 64u * (uint32_t)(n / (params ? std::max(1, params->block_width) : BLOCK_W) + 2);
+    const uint64_t rec_cap64 = 7ull * 64ull * (n / (uint64_t)(params ? std::max(1, params->block_width) : BLOCK_W) + 2);
+    if (rec_cap64 > (1ull << 28)) {
+        apa_batch_free(e, bt);
+        return set_err(APA_ERR_TOO_LARGE, "band log: too many blocks for the debug log");
+    }
+    const uint32_t rec_cap = (uint32_t)rec_cap64;
     std::vector<int32_t> rec(rec_cap);
     uint32_t nrec = 0;
     cudaError_t ce = cudaMalloc(&bt->d_dbg, rec_cap * 4);
