@@ -374,3 +374,21 @@ def test_search_gpu(apa, oracle):
     for bad in ((b"AX", b"ACGT", 0.0), (b"AC", b"ACGN", 0.0), (b"AC", b"ACGT", 2.0)):
         with pytest.raises(apa.AstarPaError):
             apa.search(*bad)
+
+
+@pytest.mark.parametrize("preset", GENERAL_PRESETS)
+def test_committed_config_vectors_gpu(apa, oracle, preset):
+    # the CUDA path against the committed fixtures (tests/golden/config_vectors.json), not only against the live oracle:
+    # cost, CIGAR text, f_max tries and the band-log digest of 4 seeded pairs per configuration.
+    import hashlib
+    g = json.load(open(os.path.join(HERE, "golden", "config_vectors.json")))
+    params = params_for(apa, preset)
+    pairs = [apa.generate_pair(n, e, model, seed) for n, e, model, seed in g["cases"]]
+    aligners = [apa.AstarPa2(params, True)] + ([apa.AstarPa2(preset, True)] if preset < 2 else [])
+    for al in aligners:
+        costs, cigars, stats = al.align_batch_with_stats(pairs)
+        for k, want in enumerate(g["configs"][str(preset)]):
+            assert (int(costs[k]), cigars[k], stats[k]["f_max_tries"]) == (want["cost"], want["cigar"], want["f_max_tries"]), (preset, k)
+    for (a, b), want in zip(pairs, g["configs"][str(preset)]):
+        log = oracle.parse_band_log(_gpu_band_log_params(apa, a, b, params))
+        assert hashlib.sha256(json.dumps(log).encode()).hexdigest()[:16] == want["band_log"], preset

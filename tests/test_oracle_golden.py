@@ -110,3 +110,24 @@ def test_bad_input_panics(oracle):
     # BitProfile::build panics on bytes outside ACGT (pa-bitpacking/src/profile.rs:113)
     with pytest.raises(oracle.OraclePanic):
         oracle.align(b"ACGN", b"ACGT", 0)
+
+
+def _config_goldens():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_vectors.json")))
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_oracle_matches_committed_config_vectors(oracle, apa, preset):
+    # tests/golden/config_vectors.json (tests/golden/make_config_goldens.py): frozen oracle outputs per configuration - cost,
+    # CIGAR text, number of f_max tries, digest of the band log - so that oracle and CUDA path cannot drift together.
+    import hashlib
+    import json
+    g = _config_goldens()
+    for (n, e, model, seed), want in zip(g["cases"], g["configs"][str(preset)]):
+        a, b = apa.generate_pair(n, e, model, seed)
+        cost, cigar, st = oracle.align(a, b, preset, True)
+        assert (cost, cigar, st["f_max_tries"]) == (want["cost"], want["cigar"], want["f_max_tries"]), (preset, n)
+        digest = hashlib.sha256(json.dumps(oracle.band_log(a, b, preset, True)).encode()).hexdigest()[:16]
+        assert digest == want["band_log"], (preset, n)
