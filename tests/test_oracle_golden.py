@@ -131,3 +131,15 @@ def test_oracle_matches_committed_config_vectors(oracle, apa, preset):
         assert (cost, cigar, st["f_max_tries"]) == (want["cost"], want["cigar"], want["f_max_tries"]), (preset, n)
         digest = hashlib.sha256(json.dumps(oracle.band_log(a, b, preset, True)).encode()).hexdigest()[:16]
         assert digest == want["band_log"], (preset, n)
+
+
+@pytest.mark.parametrize("preset", [p for p in PRESETS if p >= 2])
+def test_configurations_larger(oracle, apa, preset):
+    # the non-preset configurations on longer pairs: optimal cost (independent Levenshtein), valid CIGAR, cost-only == traced
+    big = preset in (9, 13)  # Domain::Full computes the whole rectangle
+    for n, e, model in [(3000, 0.05, 0), (3000, 0.2, 1)] if big else [(6000, 0.05, 0), (6000, 0.15, 2), (12000, 0.08, 3)]:
+        a, b = apa.generate_pair(n, e, model, 4000 + n + preset)
+        lev = oracle.levenshtein(a, b)
+        cost, cigar, _ = oracle.align(a, b, preset, True, self_check=True)
+        assert cost == lev and oracle.cigar_verify(cigar, a, b) == lev, (preset, n, e)
+        assert oracle.align(a, b, preset, False)[0] == lev
