@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 __all__ = ["AstarPa2", "AstarPa2Params", "AstarPaError", "Engine", "astarpa2_simple", "astarpa2_full", "generate_pair",
-           "generate_batch", "search", "PRESET_SIMPLE", "PRESET_FULL", "lib_path", "load_library"]
+           "generate_batch", "search", "PRESET_SIMPLE", "PRESET_FULL", "lib_path", "load_library", "align_batch_multi", "free_pool",
+           "cigar_digests", "gen_library"]
 
 PRESET_SIMPLE, PRESET_FULL = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -33,7 +34,8 @@ class BatchStats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("computed_cells", C.c_uint64),
                 ("dp_word_steps", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("retries", C.c_uint64), ("fill_blocks", C.c_uint64), ("dt_blocks", C.c_uint64),
-                ("phase_cycles", C.c_uint64 * 8), ("phase_ms", C.c_double * 3), ("score_calls", C.c_uint64), ("score_probes", C.c_uint64)]
+                ("phase_cycles", C.c_uint64 * 8), ("phase_ms", C.c_double * 3), ("score_calls", C.c_uint64), ("score_probes", C.c_uint64),
+                ("pass_warps_per_pair", C.c_uint32), ("upload_mode", C.c_uint32), ("upload_chunks", C.c_uint32), ("waves", C.c_uint32), ("dp_issue_steps", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -134,9 +136,9 @@ def load_library():
     L.apa_pinned_alloc.restype = C.c_void_p
     L.apa_pinned_alloc.argtypes = [C.c_uint64]
     L.apa_pinned_free.argtypes = [C.c_void_p]
-    L.apa_generate_pair.restype = C.c_int64
-    L.apa_generate_pair.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64]
-    L.apa_generate_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64, vp, C.c_int]
+    L.apa_align_batch_multi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(C.c_void_p), vp, vp, vp]
+    L.apa_int32_peak.argtypes = [C.c_void_p, vp]
+    L.apa_pack_planes_device.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.apa_block_compute.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.POINTER(C.c_int64)]
     for name in ("astarpa2_simple", "astarpa2_full", "astarpa"):
         f = getattr(L, name)
@@ -156,9 +158,41 @@ def _check(rc):
 
 
 # ----------------------------------------------------------------------------------------------- generator
+_GEN = None
+
+
+def gen_library():
+    """libapa_generate.so: the synthetic-input generator and text digests (host code for tests / bench.py, include/apa_generate.h).
+    Deliberately a library of its own: the product library holds the aligner only."""
+    global _GEN
+    if _GEN is None:
+        path = os.path.join(_HERE, "libapa_generate.so")
+        if not os.path.exists(path):
+            raise AstarPaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        G = C.CDLL(path)
+        vp = C.c_void_p
+        G.apa_generate_pair.restype = C.c_int64
+        G.apa_generate_pair.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64]
+        G.apa_generate_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_uint64, vp, vp, C.c_uint64, vp, C.c_int]
+        G.apa_fnv1a_batch.argtypes = [vp, vp, vp, C.c_uint64, vp]
+        G.apa_fnv1a_batch.restype = None
+        _GEN = G
+    return _GEN
+
+
+def cigar_digests(pool, off, ln):
+    """FNV-1a (64 bit) of every CIGAR text of a downloaded pool (pool: c_void_p; off / ln: int64 arrays) -> uint64 array."""
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ln = np.ascontiguousarray(ln, dtype=np.int64)
+    out = np.zeros(len(off), dtype=np.uint64)
+    if len(off):
+        gen_library().apa_fnv1a_batch(pool, off.ctypes.data, ln.ctypes.data, len(off), out.ctypes.data)
+    return out
+
+
 def generate_pair(n, e, model=0, seed=31415):
     """Synthetic pair (stands in for pa_generate::generate_model, pa-test/src/lib.rs:60)."""
-    L = load_library()
+    L = gen_library()
     a = np.empty(max(n, 1), dtype=np.uint8)
     cap = 3 * n + 64
     b = np.empty(cap, dtype=np.uint8)
@@ -170,7 +204,7 @@ def generate_pair(n, e, model=0, seed=31415):
 
 def generate_batch(n_pairs, n, e, model=0, seed0=31415, threads=None):
     """Returns (a_all, a_off, b_all, b_off) numpy arrays; pair p uses seed seed0 + p."""
-    L = load_library()
+    L = gen_library()
     threads = threads or (os.cpu_count() or 1)
     stride = int(n * (1 + e) + n * e + 64)
     a_all = np.empty(max(n_pairs * n, 1), dtype=np.uint8)
@@ -254,6 +288,25 @@ class Engine:
     def free_pool(self, pool):
         if pool and pool.value:
             self._L.apa_free(pool)
+
+    def int32_peak(self):
+        """apa_int32_peak: measured integer issue rates of this GPU (lane-operations per second), for the block-DP roofline."""
+        out = np.zeros(7, dtype=np.float64)
+        _check(self._L.apa_int32_peak(self._h, out.ctypes.data))
+        d = dict(zip(["lop3", "shf", "iadd3", "imad", "dp_mix_alu", "clock_hz", "dp_mix_imad"], [float(x) for x in out]))
+        # the ALU pipe's ceiling for the block DP: the better of LOP3 alone and the LOP3 + SHF share of the DP mix
+        d["alu_lane_ops_per_s"] = max(d["lop3"], d["dp_mix_alu"])
+        return d
+
+    def pack_planes(self, seq: bytes):
+        """K0 on the device (apa_pack_planes_device): the 2-bit planes of one sequence as a uint32 array, 2 per half-word."""
+        nhw = ((((len(seq) + 63) // 64) * 2 + 2 + 15) // 16) * 16
+        out = np.zeros(2 * nhw, dtype=np.uint32)
+        got = C.c_uint64()
+        sb = np.frombuffer(seq, dtype=np.uint8) if seq else np.zeros(1, np.uint8)
+        _check(self._L.apa_pack_planes_device(self._h, sb.ctypes.data, len(seq), out.ctypes.data, nhw, C.byref(got)))
+        assert got.value == nhw
+        return out
 
     def search(self, pattern: bytes, text: bytes, unmatched_cost: float = 0.0):
         """pa_bitpacking::search(pattern, text, unmatched_cost).out (pa-bitpacking/src/search.rs:46-118) as a numpy int32 array:
@@ -372,6 +425,33 @@ def _concat(pairs):
     a_all = np.frombuffer(b"".join(a for a, _ in pairs), dtype=np.uint8)
     b_all = np.frombuffer(b"".join(b for _, b in pairs), dtype=np.uint8)
     return a_all, a_off, b_all, b_off
+
+
+def align_batch_multi(devices, a_all, a_off, b_all, b_off, preset=PRESET_FULL, trace=True):
+    """apa_align_batch_multi: one call, the GPUs of `devices` (contiguous shards balanced by bases, no collective).
+    Returns (costs, pool pointer or None, cigar_off, cigar_len, list of per-device stats dicts); free the pool with apa_free
+    (Engine.free_pool of any engine, or free_pool below)."""
+    L = load_library()
+    a_all = np.ascontiguousarray(a_all, dtype=np.uint8)
+    b_all = np.ascontiguousarray(b_all, dtype=np.uint8)
+    a_off = np.ascontiguousarray(a_off, dtype=np.int64)
+    b_off = np.ascontiguousarray(b_off, dtype=np.int64)
+    n = len(a_off) - 1
+    devs = (C.c_int * len(devices))(*devices)
+    costs = np.zeros(max(n, 1), dtype=np.int64)
+    off = np.zeros(max(n, 1), dtype=np.int64)
+    ln = np.zeros(max(n, 1), dtype=np.int64)
+    pool = C.c_void_p()
+    st = (BatchStats * len(devices))()
+    _check(L.apa_align_batch_multi(C.cast(devs, C.c_void_p), len(devices), preset, int(trace), n, a_all.ctypes.data if a_all.size else None,
+                                   a_off.ctypes.data, b_all.ctypes.data if b_all.size else None, b_off.ctypes.data, costs.ctypes.data,
+                                   C.byref(pool), off.ctypes.data, ln.ctypes.data, C.cast(st, C.c_void_p)))
+    return costs[:n], pool, off[:n], ln[:n], [x.as_dict() for x in st]
+
+
+def free_pool(pool):
+    if pool and pool.value:
+        load_library().apa_free(pool)
 
 
 _DEFAULT_ENGINES = {}

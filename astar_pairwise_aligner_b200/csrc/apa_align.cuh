@@ -28,7 +28,8 @@ struct PairCtx {
     uint32_t hi_bot;     // lowest byte used by the downward-growing region at the arena end (CIGAR elements)
     int status;          // ST_PENDING while healthy
     // stats
-    unsigned long long word_steps, computed_cells;
+    DpCounters dpc;  // block-DP lane-steps: useful / issued
+    unsigned long long computed_cells;
     int passes;
     int fill_blocks, dt_blocks;
     // phase timers (SM clock cycles of this warp): [0] heuristic build [1] block DP [2] passes total [3] traceback total
@@ -82,7 +83,7 @@ __device__ __forceinline__ void dbg_log(PairCtx& cx, Cost f_max, int t, JRange j
 
 __device__ __forceinline__ uint32_t arena_alloc(PairCtx& cx, uint32_t bytes) {
     bytes = (bytes + 15u) & ~15u;
-    if (cx.v_top + bytes > cx.hi_bot) {
+    if ((uint64_t)cx.v_top + bytes > (uint64_t)cx.hi_bot) {  // 64-bit: arenas go up to 0xF0000000 bytes
         cx.status = ST_OVERFLOW;
         return 0xffffffffu;
     }
@@ -240,7 +241,7 @@ constexpr Cost PASS_NONE = -1;
 __device__ __forceinline__ Cost run_block_dp(WarpSmem& sm, PairCtx& cx, const BlkView& prev, I is, int ncols, I njs, I nje,
                                              uint2* vout, int32_t* cumout, Cost top_val) {
     stage_amask(sm, cx.aprof, is, ncols, threadIdx.x & 31);
-    return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.word_steps);
+    return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc);
 }
 
 template <class Hh, class SM>

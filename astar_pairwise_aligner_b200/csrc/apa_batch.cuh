@@ -31,6 +31,10 @@ struct BatchDev {
     uint32_t q0;        // phase-split path: first work-order position of this wave (arena slot = q - q0)
     const volatile uint32_t* ready;  // streaming upload: number of pairs (in work order) whose bases are in HBM; nullptr = all
     long long* pair_stats;  // 8 per pair: apa_pair_stats (f_max_tries, h0, num_matches, h_calls, computed_cells, dt blocks, fill tries, -)
+    // Device-side K0: when non-null, the raw bases as uploaded (byte offsets a_off / b_off); the kernel that opens a pair packs
+    // them into aprof / bprof first (dev_pack_planes). Null: the planes were packed before the launch.
+    const uint8_t* raw_a;
+    const uint8_t* raw_b;
     int32_t* dbg;  // band log of the (single) pair, or nullptr
     uint32_t dbg_cap;
     uint32_t* dbg_n;

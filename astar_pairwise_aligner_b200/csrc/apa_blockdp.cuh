@@ -32,6 +32,11 @@ namespace APA_NS {
 
 constexpr int DP_UNROLL = APA_DP_UNROLL;  // steady-state steps per loop iteration of dp_chunk
 
+struct DpCounters {  // statistics of the block DP (bench.py: lane_utilisation = word_steps / issue_steps)
+    unsigned long long word_steps;   // useful 32-row x 1-column lane-steps
+    unsigned long long issue_steps;  // lane-steps issued: 32 lanes x anti-diagonals swept, ramps and idle lanes included
+};
+
 struct WarpSmem {
 #if APA_DP_V2
     uint32_t etab[4 * 32];   // etab[c * 32 + lane]: BitProfile::eq of base c against the 32 rows of b this lane owns
@@ -213,7 +218,7 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
 template <bool FILL>
 __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const BlkView& prev, int ncols, I njs, I nje,
                          uint2* __restrict__ vout, int32_t* __restrict__ cumout, Cost top_val_new, uint2* __restrict__ fillvals,
-                         unsigned long long& word_steps) {
+                         DpCounters& dpc) {
     const int lane = threadIdx.x & 31;
     const int nhw = (nje - njs) >> 5;
     // chunks of at most 31 rows (the first chunk gives lane 0 to the feeder), evenly sized
@@ -265,8 +270,10 @@ __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const Bl
         }
         if (is_row) cumout[hw] = running + incl - val;
         running += __shfl_sync(FULL, incl, 31);
-        word_steps += (unsigned long long)ncols * (unsigned long long)nrow;
+        dpc.word_steps += (unsigned long long)ncols * (unsigned long long)nrow;
     }
+    // lane-steps issued: every chunk sweeps ncols + nact - 1 anti-diagonals on 32 lanes (nact = rows, + the feeder in chunk 0)
+    if (nchunks) dpc.issue_steps += 32ull * (unsigned long long)(nchunks * (ncols - 1) + nhw + 1);
     if (lane == 0) cumout[nhw] = running;
     __syncwarp();
     return running;

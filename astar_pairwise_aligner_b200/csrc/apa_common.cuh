@@ -50,6 +50,7 @@ enum Status : int32_t {
     ST_OVERFLOW = 2,   // scratch arena too small: host re-runs the pair with a larger arena
     ST_BAD_INPUT = 3,  // byte outside ACGT
     ST_ASSERT = 4,     // a reference panic path was reached
+    ST_TOO_LARGE = 5,  // a CIGAR run of 2^30 or more equal operations
 };
 
 struct JRange {
@@ -126,6 +127,36 @@ __device__ __forceinline__ uint32_t rank_acgt(uint32_t c) {
     return x ^ (x >> 1);         // -> A0 C1 G2 T3
 }
 __device__ __forceinline__ bool is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// K0 on the device: BitProfile::build (pa-bitpacking/src/profile.rs:112-133) for one sequence, by one warp (or by the warps
+// of a grid, each taking every `stride`-th group of 32 half-words starting at `first`). raw: the bases as uploaded (any
+// alignment; read with ld.global.cg - the bytes may have been written by a copy engine while this kernel was already running,
+// and L1 is not coherent with those writes); prof: nhw plane words (negated rank bits of A0 C1 G2 T3 per 32 bases, zero past
+// the end of the sequence, padding half-words included). Returns true (warp-uniform) if a byte outside ACGT was seen: the
+// reference panics there (profile.rs:113).
+__device__ __forceinline__ bool dev_pack_planes(const uint8_t* __restrict__ raw, I len, uint2* __restrict__ prof, int nhw, int first = 0,
+                                                int stride = 1) {
+    const int lane = threadIdx.x & 31;
+    bool bad = false;
+    for (int g = first; 32 * g < nhw; g += stride) {
+        // this warp packs half-words [32 g, 32 g + 32): one ballot pair per half-word, lane t of the result keeps half-word t
+        uint32_t keep0 = 0u, keep1 = 0u;
+        const int hw_end = min(32, nhw - 32 * g);
+#pragma unroll 4
+        for (int t = 0; t < hw_end; t++) {
+            const I pos = (I)((32 * g + t) * 32 + lane);
+            const bool in = pos < len;
+            const uint32_t c = in ? (uint32_t)__ldcg(raw + pos) : (uint32_t)'T';  // rank 3: both negated planes 0
+            const uint32_t r = rank_acgt(c);
+            const uint32_t p0 = __ballot_sync(FULL, !(r & 1u));
+            const uint32_t p1 = __ballot_sync(FULL, !(r & 2u));
+            bad |= in && !is_acgt(c);
+            if (lane == t) keep0 = p0, keep1 = p1;
+        }
+        if (lane < hw_end) prof[32 * g + lane] = make_uint2(keep0, keep1);
+    }
+    return __any_sync(FULL, bad);
+}
 
 // ---- 2-bit-plane packed sequences: prof[hw] = (negated rank bit0, negated rank bit1) of 32 consecutive bases.
 // Every per-pair plane array carries two zero half-words of padding, so extract32 may read prof[hw + 1].

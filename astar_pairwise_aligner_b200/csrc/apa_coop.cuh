@@ -201,7 +201,7 @@ __device__ __forceinline__ Cost run_block_dp(CoopSmem<W>& cs, PairCtx& cx, const
     const int nchunks = (nhw + 30) / 31;
     stage_amask(cs.lead, cx.aprof, is, ncols, lane);
     if (nchunks < 2 || nchunks > COOP_MAX_CHUNKS)
-        return block_dp<false>(cs.lead, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.word_steps);
+        return block_dp<false>(cs.lead, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc);
     if (lane == 0) {
         cs.quit = 0;
         cs.ncols = ncols;
@@ -221,7 +221,8 @@ __device__ __forceinline__ Cost run_block_dp(CoopSmem<W>& cs, PairCtx& cx, const
     if (lane <= W) cs.progress[lane] = -1;
     __syncwarp();
     coop_bar<W>(COOP_BAR_START);
-    cx.word_steps += (unsigned long long)ncols * (unsigned long long)nhw;
+    cx.dpc.word_steps += (unsigned long long)ncols * (unsigned long long)nhw;
+    cx.dpc.issue_steps += 32ull * (unsigned long long)(((nhw + 30) / 31) * (ncols - 1) + nhw + 1);  // chunks of 31 half-words, as block_dp counts
     return coop_work<W>(cs, 0);
 }
 

@@ -43,6 +43,38 @@ static int set_err(int code, const std::string& msg) {
 #include "apa_batch.cuh"
 
 
+// Streaming upload: wait until pair number q of the work order has landed in HBM. The wait is bounded (about 20 s without
+// the counter moving past q) so that a copy that never comes - a failed upload, a profiler that serialises the launch ahead
+// of the copies - ends in ST_ASSERT for the pair instead of a hung GPU. The fence orders the loads of the pair's bases after
+// the observation of the counter.
+__device__ __forceinline__ bool wait_ready(const BatchDev& bd, unsigned long long q) {
+    if (!bd.ready) return true;
+    const int lane = threadIdx.x & 31;
+    int ok = 1;
+    if (lane == 0) {
+        unsigned long long spins = 0;
+        while (*bd.ready <= (uint32_t)q) {
+            __nanosleep(500);
+            if (++spins > 40000000ull) {
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence();
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    return ok != 0;
+}
+// Device-side K0 for the pair a warp is about to align (BatchDev::raw_a / raw_b): returns true on a byte outside ACGT.
+__device__ __forceinline__ bool pack_pair(const BatchDev& bd, uint32_t p, I n, I m) {
+    if (!bd.raw_a) return false;
+    const int nhw_a = (int)(bd.ap_off[p + 1] - bd.ap_off[p]), nhw_b = (int)(bd.bp_off[p + 1] - bd.bp_off[p]);
+    bool bad = dev_pack_planes(bd.raw_a + bd.a_off[p], n, bd.aprof + bd.ap_off[p], nhw_a);
+    bad |= dev_pack_planes(bd.raw_b + bd.b_off[p], m, bd.bprof + bd.bp_off[p], nhw_b);
+    __syncwarp();
+    return bad;
+}
+
 // K1+K3 fused per pair: a persistent warp pulls pairs from the device work queue and runs the band-doubling
 // search, the traceback and the CIGAR text emission for each.
 __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* smem) {
@@ -51,7 +83,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
     WarpSmem& sm = smem[wib];
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + wib;
     uint8_t* arena = bd.arena + (size_t)slot * bd.arena_size;
-    unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0;
+    unsigned long long acc_steps = 0, acc_issue = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0;
     long long acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     for (;;) {
@@ -59,12 +91,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         if (lane == 0) q = atomicAdd(bd.queue, 1ull);
         q = __shfl_sync(FULL, q, 0);
         if (q >= bd.n_order) break;
-        if (bd.ready) {  // streaming upload: wait until this pair's bases have landed in HBM
-            if (lane == 0) {
-                while (*bd.ready <= (uint32_t)q) __nanosleep(500);
-            }
-            __syncwarp();
-        }
+        const bool landed = wait_ready(bd, q);  // streaming upload: this pair's bases are in HBM
         const uint32_t p = bd.order[q];
 
         PairCtx cx;
@@ -83,7 +110,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.v_top = meta_bytes;
         cx.hi_bot = bd.arena_size;
         cx.status = ST_PENDING;
-        cx.word_steps = cx.computed_cells = 0;
+        cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
         cx.passes = 0;
         cx.fill_blocks = cx.dt_blocks = 0;
         for (int t = 0; t < 8; t++) cx.tphase[t] = 0;
@@ -91,6 +118,8 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.dbg_cap = bd.dbg_cap;
         cx.dbg_n = 0;
         if (meta_bytes + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
+        if (!landed) cx.status = ST_ASSERT;
+        else if (pack_pair(bd, p, cx.n, cx.m)) cx.status = ST_BAD_INPUT;
 
         Cost cost = -1;
         long long cig_off = -1, cig_len = 0;
@@ -153,7 +182,8 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
             ps[5] = cx.dt_blocks, ps[6] = cx.fill_blocks, ps[7] = 0;
         }
         if (bd.dbg_n && lane == 0) *bd.dbg_n = cx.dbg_n;
-        acc_steps += cx.word_steps;
+        acc_steps += cx.dpc.word_steps;
+        acc_issue += cx.dpc.issue_steps;
         acc_cells += cx.computed_cells;
         acc_pass += cx.passes;
         acc_fill += cx.fill_blocks;
@@ -162,6 +192,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
     }
     if (lane == 0) {
         atomicAdd(&bd.stats[0], acc_steps);
+        atomicAdd(&bd.stats[15], acc_issue);
         atomicAdd(&bd.stats[1], acc_cells);
         atomicAdd(&bd.stats[2], acc_pass);
         atomicAdd(&bd.stats[3], acc_fill);
@@ -188,18 +219,14 @@ static_assert(sizeof(PairState) <= ARENA_HEADER, "PairState must fit the arena h
 template <int PHASE, class SM>
 __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
     const int lane = threadIdx.x & 31;
-    unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0, acc_h = 0, acc_probe = 0;
+    unsigned long long acc_steps = 0, acc_issue = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0, acc_h = 0, acc_probe = 0;
     for (;;) {
         unsigned long long q = 0;
         if (lane == 0) q = atomicAdd(bd.queue + 24 + PHASE, 1ull) + bd.q0;
         q = __shfl_sync(FULL, q, 0);
         if (q >= bd.n_order) break;
-        if (PHASE <= 1 && bd.ready) {
-            if (lane == 0) {
-                while (*bd.ready <= (uint32_t)q) __nanosleep(500);
-            }
-            __syncwarp();
-        }
+        bool landed = true;
+        if (PHASE == 0) landed = wait_ready(bd, q);  // later phases run after the build kernel, which saw every pair land
         const uint32_t p = bd.order[q];
         uint8_t* arena = bd.arena + (size_t)(q - bd.q0) * bd.arena_size;
         PairState* ps = (PairState*)arena;
@@ -220,7 +247,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             cx.v_top = cx.v_base;
             cx.hi_bot = bd.arena_size;
             cx.status = ST_PENDING;
-            cx.word_steps = cx.computed_cells = 0;
+            cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
             cx.passes = 0;
             cx.fill_blocks = cx.dt_blocks = 0;
             for (int t = 0; t < 8; t++) cx.tphase[t] = 0;
@@ -228,6 +255,8 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             cx.dbg_cap = bd.dbg_cap;
             cx.dbg_n = 0;
             if (cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
+            if (!landed) cx.status = ST_ASSERT;
+            else if (pack_pair(bd, p, cx.n, cx.m)) cx.status = ST_BAD_INPUT;
             GcshH hh;
             if (cx.status == ST_PENDING && bd.preset == APA_PRESET_FULL) gcsh_build(cx, sm, hh);
             __syncwarp();
@@ -294,7 +323,8 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             pst[0] = cx.passes, pst[4] = (long long)cx.computed_cells, pst[5] = cx.dt_blocks, pst[6] = cx.fill_blocks, pst[7] = 0;
         }
         if (bd.dbg_n && lane == 0) *bd.dbg_n = cx.dbg_n;
-        acc_steps += cx.word_steps;
+        acc_steps += cx.dpc.word_steps;
+        acc_issue += cx.dpc.issue_steps;
         acc_cells += cx.computed_cells;
         acc_pass += cx.passes;
         acc_fill += cx.fill_blocks;
@@ -306,6 +336,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
     }
     if (PHASE >= 1 && lane == 0) {
         atomicAdd(&bd.stats[0], acc_steps);
+        atomicAdd(&bd.stats[15], acc_issue);
         atomicAdd(&bd.stats[1], acc_cells);
         atomicAdd(&bd.stats[2], acc_pass);
         atomicAdd(&bd.stats[3], acc_fill);
@@ -383,7 +414,7 @@ __global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof,
     prev.v = v;
     prev.cum = nullptr;
     prev.ones = 0;
-    unsigned long long ws = 0;
+    DpCounters ws{0, 0};
     // the rectangle may be wider than one block: sweep it in 256-column slabs, each slab's right column feeding the next
     for (int c0 = 0; c0 < na; c0 += BLOCK_W) {
         int nc = min(BLOCK_W, na - c0);
@@ -391,6 +422,20 @@ __global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof,
         block_dp<true>(sm, bprof, prev, nc, 0, nhw * 32, v, cum, 0, fillvals + (size_t)c0 * nhw, ws);
         __syncwarp();
     }
+}
+
+// K0 as a kernel of its own (resident uploads from page-locked host memory: raw bases by DMA, packed here): CTA x takes every
+// gridDim.x-th pair, its warps (and those of the gridDim.y CTAs sharing the pair) every (8 gridDim.y)-th group of 32 half-words
+// of a, then of b. *bad is set when a byte outside ACGT was seen.
+__global__ void __launch_bounds__(256) apa_pack_kernel(BatchDev bd, int* bad) {
+    const int wid = threadIdx.x >> 5, first = blockIdx.y * 8 + wid, stride = gridDim.y * 8;
+    bool any_bad = false;
+    for (uint64_t p = blockIdx.x; p < bd.n_pairs; p += gridDim.x) {
+        const I n = (I)(bd.a_off[p + 1] - bd.a_off[p]), m = (I)(bd.b_off[p + 1] - bd.b_off[p]);
+        any_bad |= dev_pack_planes(bd.raw_a + bd.a_off[p], n, bd.aprof + bd.ap_off[p], (int)(bd.ap_off[p + 1] - bd.ap_off[p]), first, stride);
+        any_bad |= dev_pack_planes(bd.raw_b + bd.b_off[p], m, bd.bprof + bd.bp_off[p], (int)(bd.bp_off[p + 1] - bd.bp_off[p]), first, stride);
+    }
+    if (any_bad && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -467,6 +512,8 @@ struct apa_batch {
     I max_n = 0, max_m = 0;
     int64_t *d_a_off = nullptr, *d_b_off = nullptr, *d_bp_off = nullptr, *d_ap_off = nullptr;
     uint2 *d_bprof = nullptr, *d_aprof = nullptr;
+    uint8_t *d_araw = nullptr, *d_braw = nullptr;  // raw bases (device-side K0); kept for the whole run, see batch_run
+    bool raw = false;                              // inputs are page-locked: upload raw bytes, pack on the device
     int32_t *d_status = nullptr, *d_cost = nullptr;
     int64_t *d_cig_off = nullptr, *d_cig_len = nullptr;
     long long* d_pair_stats = nullptr;  // 8 per pair (apa_pair_stats)
@@ -530,6 +577,7 @@ extern "C" int apa_device_count(void) {
     return n;
 }
 
+extern "C" void apa_engine_destroy(apa_engine* e);
 extern "C" int apa_engine_create(int device, apa_engine** out) {
     *out = nullptr;
     int n = 0;
@@ -542,7 +590,13 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return set_err(APA_ERR_NO_DEVICE, "built for sm_100a; device is older");
-    apa_engine* eng = new apa_engine();
+    struct EngineGuard {  // every CUDA_TRY below may return early
+        apa_engine* e;
+        ~EngineGuard() {
+            if (e) apa_engine_destroy(e);
+        }
+    } guard{new apa_engine()};
+    apa_engine* eng = guard.e;
     eng->device = device;
     eng->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
@@ -560,7 +614,11 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
         for (int ph = 0; ph < 3; ph++)
             for (int regs = 48; regs <= 64; regs += 8) CUDA_TRY(cudaFuncGetAttributes(&fa, phase_kernel(ph, regs)));
         CUDA_TRY(cudaFuncGetAttributes(&fa, apa_block_kernel));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_pack_kernel));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<4>));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<8>));
     }
+    guard.e = nullptr;
     *out = eng;
     return APA_OK;
 }
@@ -602,7 +660,7 @@ static void* pinned_pool_get(size_t bytes) {
         g_pin_free.erase(g_pin_free.begin() + best);
     } else {
         cap = bytes + bytes / 4 + 4096;
-        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) return nullptr;
     }
     g_pin_live[p] = cap;
     return p;
@@ -628,7 +686,7 @@ extern "C" void apa_free(void* p) {
 // Pinned (page-locked) host memory for the end-to-end path.
 extern "C" void* apa_pinned_alloc(uint64_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
         set_err(APA_ERR_CUDA, "cudaHostAlloc failed");
         return nullptr;
     }
@@ -646,6 +704,8 @@ extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     eng_release(e, b->d_bp_off);
     eng_release(e, b->d_bprof);
     eng_release(e, b->d_aprof);
+    eng_release(e, b->d_araw);
+    eng_release(e, b->d_braw);
     eng_release(e, b->d_ap_off);
     eng_release(e, b->d_status);
     eng_release(e, b->d_cost);
@@ -715,31 +775,63 @@ static int pack_threads() {
 }
 
 static int upload_planes(apa_engine* e, apa_batch* b, bool streaming);
+static int upload_raw(apa_engine* e, apa_batch* b, bool streaming, cudaStream_t cs);
+static void fill_batch_dev(apa_engine* e, apa_batch* b, BatchDev& bd);
+
+// Frees a half-built batch on every early return of batch_prepare (CUDA_TRY returns from the middle of the function).
+struct BatchGuard {
+    apa_engine* e;
+    apa_batch* b;
+    ~BatchGuard() {
+        if (b) apa_batch_free(e, b);
+    }
+    apa_batch* release() {
+        apa_batch* t = b;
+        b = nullptr;
+        return t;
+    }
+};
+
+// Page-locked host memory can be read by the copy engines directly: such inputs go to HBM as raw bytes and are packed
+// there (device-side K0). Pageable inputs are packed by host threads into a pinned staging buffer (4x fewer bytes through
+// the driver's pageable-copy path). APA_RAW=0 / 1 overrides the detection (1 is only safe for pinned buffers when streaming).
+static bool host_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
 
 static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all,
                          const int64_t* b_off, bool defer_data, apa_batch** out) {
     *out = nullptr;
     if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
     CUDA_TRY(cudaSetDevice(e->device));
-    apa_batch* b = new apa_batch();
+    BatchGuard guard{e, new apa_batch()};
+    apa_batch* b = guard.b;
     b->n_pairs = n_pairs;
     b->a_off.assign(a_off, a_off + n_pairs + 1);
     b->b_off.assign(b_off, b_off + n_pairs + 1);
     b->bp_off.resize(n_pairs + 1);
     b->ap_off.resize(n_pairs + 1);
+    // Plane arrays: ceil(len / 64) * 2 half-words + 2 of padding (extract32 reads one half-word ahead), each pair starting on
+    // a 128-byte line (16 half-word entries): no cache line ever holds bases of two pairs, so a line a warp reads after its
+    // pair has landed cannot carry stale bytes of a pair that is still on its way (streaming upload).
+    auto plane_hw = [](int64_t len) { return (uint64_t)(((len + 63) / 64) * 2 + 2 + 15) & ~(uint64_t)15; };
     uint64_t hw = 0, hwa = 0;
     for (uint64_t p = 0; p < n_pairs; p++) {
         int64_t n = a_off[p + 1] - a_off[p], m = b_off[p + 1] - b_off[p];
-        if (n < 0 || m < 0 || n >= (1ll << 31) - 1024 || m >= (1ll << 31) - 1024) {
-            delete b;
+        if (n < 0 || m < 0 || n >= (1ll << 31) - 1024 || m >= (1ll << 31) - 1024)
             return set_err(APA_ERR_TOO_LARGE, "sequence length must be < 2^31 (I = i32)");
-        }
         b->max_n = std::max<I>(b->max_n, (I)n);
         b->max_m = std::max<I>(b->max_m, (I)m);
         b->bp_off[p] = (int64_t)hw;
-        hw += (uint64_t)((m + 63) / 64) * 2 + 2;
+        hw += plane_hw(m);
         b->ap_off[p] = (int64_t)hwa;
-        hwa += (uint64_t)((n + 63) / 64) * 2 + 2;
+        hwa += plane_hw(n);
     }
     b->bp_off[n_pairs] = (int64_t)hw;
     b->ap_off[n_pairs] = (int64_t)hwa;
@@ -751,6 +843,8 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     b->h_b = b_all;
     b->h_a_off0 = a_off[0];
     b->h_b_off0 = b_off[0];
+    b->raw = host_pinned(a_all ? a_all + a_off[0] : nullptr) && host_pinned(b_all ? b_all + b_off[0] : nullptr);
+    if (const char* ev = getenv("APA_RAW")) b->raw = atoi(ev) != 0;
     // Offsets rebased to the first pair (only lengths matter on the device).
     std::vector<int64_t> ao(b->a_off), bo(b->b_off);
     for (auto& x : ao) x -= a_off[0];
@@ -767,7 +861,8 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     };
     if (n_pairs) {
         const uint64_t total = b->total_a + b->total_b;
-        const uint64_t n_chunks = defer_data ? std::min<uint64_t>(200, std::max<uint64_t>(1, total / (32ull << 20))) : 1;
+        const bool want_stream = defer_data && !(getenv("APA_STREAM") && atoi(getenv("APA_STREAM")) == 0);
+        const uint64_t n_chunks = want_stream ? std::min<uint64_t>(200, std::max<uint64_t>(1, total / (32ull << 20))) : 1;
         const uint64_t per = (total + n_chunks - 1) / n_chunks;
         uint64_t acc = 0, start = 0;
         for (uint64_t p = 0; p < n_pairs; p++) {
@@ -795,14 +890,19 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     CUDA_TRY(eng_alloc(e, (void**)&b->d_cig_len, std::max<uint64_t>(n_pairs, 1) * 8));
     CUDA_TRY(eng_alloc(e, (void**)&b->d_pair_stats, std::max<uint64_t>(n_pairs, 1) * 64));
     CUDA_TRY(eng_alloc(e, (void**)&b->d_order, std::max<uint64_t>(n_pairs, 1) * 8));  // [0,n): work order, [n,2n): retry list
-    // pinned staging for the packed planes: [aprof | bprof]
-    const size_t stage_words = (size_t)(hwa + hw) * 2 + 16;
-    if (e->h_stage_cap < stage_words) {
-        if (e->h_stage) cudaFreeHost(e->h_stage);
-        e->h_stage = nullptr;
-        e->h_stage_cap = 0;
-        CUDA_TRY(cudaHostAlloc((void**)&e->h_stage, stage_words * 4, cudaHostAllocDefault));
-        e->h_stage_cap = stage_words;
+    if (b->raw) {
+        CUDA_TRY(eng_alloc(e, (void**)&b->d_araw, b->total_a + 64));
+        CUDA_TRY(eng_alloc(e, (void**)&b->d_braw, b->total_b + 64));
+    } else {
+        // pinned staging for the packed planes: [aprof | bprof]
+        const size_t stage_words = (size_t)(hwa + hw) * 2 + 16;
+        if (e->h_stage_cap < stage_words) {
+            if (e->h_stage) cudaFreeHost(e->h_stage);
+            e->h_stage = nullptr;
+            e->h_stage_cap = 0;
+            CUDA_TRY(cudaHostAlloc((void**)&e->h_stage, stage_words * 4, cudaHostAllocDefault));
+            e->h_stage_cap = stage_words;
+        }
     }
     CUDA_TRY(cudaMemcpyAsync(b->d_a_off, ao.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_b_off, bo.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -810,20 +910,59 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     CUDA_TRY(cudaMemcpyAsync(b->d_ap_off, b->ap_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_pairs) CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), n_pairs * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    b->stats.h2d_bytes = (hwa + hw) * 8 + 4 * (n_pairs + 1) * 8 + n_pairs * 4;
+    b->stats.h2d_bytes = (b->raw ? b->total_a + b->total_b : (hwa + hw) * 8) + 4 * (n_pairs + 1) * 8 + n_pairs * 4;
     if (!defer_data) {
-        int rc = upload_planes(e, b, /*streaming=*/false);
-        if (rc != APA_OK) {
-            apa_batch_free(e, b);
-            return rc;
+        int rc;
+        if (b->raw) {  // raw bases by DMA, packed by apa_pack_kernel; the raw copy is not kept
+            rc = upload_raw(e, b, /*streaming=*/false, st);
+            if (rc == APA_OK && n_pairs) {
+                BatchDev bd{};
+                fill_batch_dev(e, b, bd);
+                int* d_bad = (int*)(e->d_ready + 8);
+                CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, st));
+                const unsigned gx = (unsigned)std::min<uint64_t>(n_pairs, 4096);
+                const unsigned gy = n_pairs >= 4ull * e->sm_count ? 1u : (unsigned)((4ull * e->sm_count + n_pairs - 1) / n_pairs);
+                apa_pack_kernel<<<dim3(gx, gy), 256, 0, st>>>(bd, d_bad);
+                CUDA_TRY(cudaGetLastError());
+                int h_bad = 0;
+                CUDA_TRY(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (h_bad) rc = set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT (the reference panics here: pa-bitpacking/src/profile.rs:113)");
+            }
+            eng_release(e, b->d_araw);
+            eng_release(e, b->d_braw);
+            b->d_araw = b->d_braw = nullptr;
+            b->raw = false;
+        } else {
+            rc = upload_planes(e, b, /*streaming=*/false);
         }
+        if (rc != APA_OK) return rc;
     }
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
     b->stats.h2d_ms = ms;
-    *out = b;
+    *out = guard.release();
+    return APA_OK;
+}
+
+// Raw bases from page-locked host memory to HBM, chunk by chunk, on stream cs. With streaming every chunk is followed by
+// the ready counter the running kernel polls. Nothing here blocks the host: all copies are asynchronous DMA.
+static int upload_raw(apa_engine* e, apa_batch* b, bool streaming, cudaStream_t cs) {
+    const size_t n_chunks = b->chunk_pair_end.size();
+    uint32_t p0 = 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const uint32_t p1 = b->chunk_pair_end[c];
+        const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
+        if (a1 > a0) CUDA_TRY(cudaMemcpyAsync(b->d_araw + a0, b->h_a + b->h_a_off0 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, cs));
+        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(b->d_braw + b0, b->h_b + b->h_b_off0 + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
+        if (streaming) {
+            e->h_ready[c] = p1;
+            CUDA_TRY(cudaMemcpyAsync(e->d_ready, &e->h_ready[c], 4, cudaMemcpyHostToDevice, cs));
+        }
+        p0 = p1;
+    }
     return APA_OK;
 }
 
@@ -878,6 +1017,7 @@ extern "C" int apa_batch_upload(apa_engine* e, uint64_t n_pairs, const uint8_t* 
                                 const int64_t* b_off, apa_batch** out) {
     return batch_prepare(e, n_pairs, a_all, a_off, b_all, b_off, false, out);
 }
+
 
 static uint32_t estimate_arena(const apa_batch* b, int preset, int trace, const RunParams* gp) {
     // meta + V columns of one pass + traceback scratch + CIGAR elements. Deliberately modest: pairs that do
@@ -959,6 +1099,33 @@ extern "C" int apa_params_preset(int preset, apa_params* out) {
     return APA_OK;
 }
 
+static void fill_batch_dev(apa_engine* e, apa_batch* b, BatchDev& bd) {
+    bd.n_pairs = b->n_pairs;
+    bd.a_off = b->d_a_off;
+    bd.b_off = b->d_b_off;
+    bd.bp_off = b->d_bp_off;
+    bd.bprof = b->d_bprof;
+    bd.ap_off = b->d_ap_off;
+    bd.aprof = b->d_aprof;
+    bd.status = b->d_status;
+    bd.cost = b->d_cost;
+    bd.cig_off = b->d_cig_off;
+    bd.cig_len = b->d_cig_len;
+    bd.pair_stats = b->d_pair_stats;
+    bd.order = b->d_order;
+    bd.n_order = (uint32_t)b->n_pairs;
+    bd.queue = e->d_queue;
+    bd.pool = b->d_pool;
+    bd.pool_cursor = e->d_queue + 1;
+    bd.pool_cap = b->pool_cap;
+    bd.stats = e->d_queue + 2;
+    bd.raw_a = b->raw ? b->d_araw : nullptr;
+    bd.raw_b = b->raw ? b->d_braw : nullptr;
+    bd.dbg = b->d_dbg;
+    bd.dbg_cap = b->dbg_cap;
+    bd.dbg_n = b->d_dbg_n;
+}
+
 static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool stream_data, const RunParams* gp = nullptr) {
     if (!e || !b) return set_err(APA_ERR_NO_DEVICE, "null engine/batch");
     if (!gp && preset != APA_PRESET_SIMPLE && preset != APA_PRESET_FULL) return set_err(APA_ERR_BAD_INPUT, "unknown preset");
@@ -981,30 +1148,9 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         b->pool_cap = pool_need;
     }
     BatchDev bd{};
-    bd.n_pairs = b->n_pairs;
-    bd.a_off = b->d_a_off;
-    bd.b_off = b->d_b_off;
-    bd.bp_off = b->d_bp_off;
-    bd.bprof = b->d_bprof;
-    bd.ap_off = b->d_ap_off;
-    bd.aprof = b->d_aprof;
-    bd.status = b->d_status;
-    bd.cost = b->d_cost;
-    bd.cig_off = b->d_cig_off;
-    bd.cig_len = b->d_cig_len;
-    bd.pair_stats = b->d_pair_stats;
-    bd.order = b->d_order;
-    bd.n_order = (uint32_t)b->n_pairs;
-    bd.queue = e->d_queue;
-    bd.pool = b->d_pool;
-    bd.pool_cursor = e->d_queue + 1;
-    bd.pool_cap = b->pool_cap;
-    bd.stats = e->d_queue + 2;
+    fill_batch_dev(e, b, bd);
     bd.preset = preset;
     bd.trace = trace;
-    bd.dbg = b->d_dbg;
-    bd.dbg_cap = b->dbg_cap;
-    bd.dbg_n = b->d_dbg_n;
 
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
     CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, 32 * sizeof(unsigned long long), st));
@@ -1089,16 +1235,33 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             bd.order = b->d_order + b->n_pairs;
             CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(unsigned long long), st));
         }
-        bool streaming = stream_data && attempt == 0 && !b->chunk_pair_end.empty() && !gp;
-        if (streaming && split && wave_n < n_work) {  // waves: plain upload first, the waves then find their bases in HBM
-            int rc = upload_planes(e, b, /*streaming=*/false);
+        // The bases of a deferred batch (apa_align_batch) reach HBM here. A batch of several upload chunks streams: the
+        // persistent kernel starts on the first chunk while the later ones are still on their way (H2D overlaps compute).
+        // One chunk, waves, the general kernel and retries take the plain upload: nothing to overlap with. Raw (page-locked)
+        // inputs are copied by DMA alone and packed by the kernel that opens each pair; the host never blocks, so every copy is
+        // queued before the kernel is launched (a serialising profiler can then not dead-lock the ready wait). Pageable inputs
+        // are packed by host threads, chunk by chunk, after the launch.
+        const bool first_upload = stream_data && attempt == 0 && !b->chunk_pair_end.empty();
+        bool streaming = first_upload && !gp && b->chunk_pair_end.size() >= 2 && !(split && wave_n < n_work);
+        if (first_upload && !streaming) {
+            int rc = b->raw ? upload_raw(e, b, /*streaming=*/false, st) : upload_planes(e, b, /*streaming=*/false);
             if (rc != APA_OK) return rc;
-            streaming = false;
         }
         bd.ready = streaming ? e->d_ready : nullptr;
         if (streaming) {
             CUDA_TRY(cudaMemsetAsync(e->d_ready, 0, 4, st));
             CUDA_TRY(cudaStreamSynchronize(st));  // offsets, order, zeroed queue are in place before anything overlaps
+            if (b->raw) {
+                int rc = upload_raw(e, b, /*streaming=*/true, e->copy_stream);
+                if (rc != APA_OK) return rc;
+            }
+        }
+        const bool host_streaming = streaming && !b->raw;  // host threads pack while the build kernel already runs
+        if (attempt == 0) {
+            b->stats.upload_mode = !first_upload ? 0u : (b->raw ? (streaming ? 4u : 3u) : (streaming ? 2u : 1u));
+            b->stats.upload_chunks = first_upload ? (uint32_t)b->chunk_pair_end.size() : 0u;
+            b->stats.pass_warps_per_pair = split ? (uint32_t)coop_w : 0u;
+            b->stats.waves = split ? (uint32_t)((n_work + wave_n - 1) / wave_n) : 0u;
         }
         // register variant: 64 registers when the slots fit 8 CTAs per SM
         int regs = slots <= (uint64_t)e->sm_count * 8 * WARPS_PER_CTA ? 64 : (slots <= (uint64_t)e->sm_count * 10 * WARPS_PER_CTA ? 48 : 40);
@@ -1145,7 +1308,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
                 // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
                 // done, so the pass / trace kernels are launched after upload_planes() below.
-                if (!streaming) CUDA_TRY(launch_pass_trace());
+                if (!host_streaming) CUDA_TRY(launch_pass_trace());
                 if (w0 + wave_n < n_work) {  // more waves follow: the arenas are reused
                     CUDA_TRY(cudaStreamSynchronize(st));
                     CUDA_TRY(add_phase_ms());
@@ -1161,7 +1324,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             apa_align_kernel_r40<<<(unsigned)(slots / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(bd);
         if (!split) b->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
-        if (streaming) {
+        if (host_streaming) {
             // host threads pack the bases while the persistent kernel already consumes the chunks that have landed
             int rc = upload_planes(e, b, /*streaming=*/true);
             if (rc != APA_OK) {
@@ -1176,6 +1339,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        if (streaming) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));  // the caller's buffers are no longer being read
         if (split) CUDA_TRY(add_phase_ms());
         pending.clear();
         for (uint64_t p = 0; p < b->n_pairs; p++)
@@ -1217,9 +1381,11 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
     for (int t = 0; t < 8; t++) b->stats.phase_cycles[t] = h_q[7 + t];
     b->stats.score_calls = h_q[15];
     b->stats.score_probes = h_q[16];
+    b->stats.dp_issue_steps = h_q[17];
     b->ran = true;
     for (uint64_t p = 0; p < b->n_pairs; p++) {
         if (b->h_status[p] == ST_BAD_INPUT) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT in pair " + std::to_string(p));
+        if (b->h_status[p] == ST_TOO_LARGE) return set_err(APA_ERR_TOO_LARGE, "CIGAR run of 2^30 or more operations in pair " + std::to_string(p));
         if (b->h_status[p] != ST_DONE)
             return set_err(APA_ERR_INTERNAL, "device assertion in pair " + std::to_string(p) + " (status " + std::to_string(b->h_status[p]) + ")");
     }
@@ -1228,7 +1394,8 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
 
 extern "C" int apa_batch_run(apa_engine* e, apa_batch* b, int preset, int trace) { return batch_run(e, b, preset, trace, false); }
 
-extern "C" int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len) {
+// dst != nullptr: the CIGAR text goes to the caller's (page-locked) buffer of at least pool_used bytes instead of a fresh pool.
+static int batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len, char* dst) {
     if (!e || !b || !b->ran) return set_err(APA_ERR_BAD_INPUT, "batch has not been run");
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
@@ -1239,8 +1406,8 @@ extern "C" int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, c
     CUDA_TRY(cudaMemcpyAsync(c32.data(), b->d_cost, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
     uint64_t bytes = b->n_pairs * 4;
     char* pool = nullptr;
-    if (b->trace && cigar_pool && cigar_off && cigar_len) {
-        pool = (char*)pinned_pool_get(std::max<uint64_t>(b->pool_used, 1));
+    if (b->trace && (cigar_pool || dst) && cigar_off && cigar_len) {
+        pool = dst ? dst : (char*)pinned_pool_get(std::max<uint64_t>(b->pool_used, 1));
         if (!pool) return set_err(APA_ERR_TOO_LARGE, "host allocation of the CIGAR pool failed");
         CUDA_TRY(cudaMemcpyAsync(pool, b->d_pool, b->pool_used, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(cigar_off, b->d_cig_off, b->n_pairs * 8, cudaMemcpyDeviceToHost, st));
@@ -1250,12 +1417,15 @@ extern "C" int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, c
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (uint64_t p = 0; p < b->n_pairs; p++) costs[p] = c32[p];
-    if (pool) *cigar_pool = pool;
+    if (pool && cigar_pool) *cigar_pool = pool;
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]));
     b->stats.d2h_ms = ms;
     b->stats.d2h_bytes = bytes;
     return APA_OK;
+}
+extern "C" int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar_pool, int64_t* cigar_off, int64_t* cigar_len) {
+    return batch_download(e, b, costs, cigar_pool, cigar_off, cigar_len, nullptr);
 }
 
 extern "C" int apa_batch_download_pair_stats(apa_engine* e, apa_batch* b, apa_pair_stats* out) {
@@ -1483,6 +1653,155 @@ extern "C" int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t np, co
     return APA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ INT32 issue-rate probe
+// Measures what the block DP's roofline is quoted against ("must be measured, do not assume"): the rate at which
+// this GPU retires the integer instructions of the Myers step when every SM is full of warps that do nothing else. Eight
+// independent dependent chains per thread, operands the compiler cannot fold. MODE 0 LOP3, 1 SHF (funnel shift), 2 IADD3,
+// 3 IMAD (FMA pipe), 4 the block-DP mix per step: 8 LOP3 + 2 SHF on the ALU pipe next to 4 IMAD on the FMA pipe.
+template <int MODE>
+__global__ void __launch_bounds__(256) apa_peak_kernel(uint32_t* out, int iters, uint32_t k1, uint32_t k2) {
+    uint32_t x[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) x[c] = threadIdx.x * 2654435761u + c * 40503u + blockIdx.x;
+    asm volatile("" : "+r"(k1), "+r"(k2));  // operands in registers, opaque to constant folding
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t v = x[c];
+            if (MODE == 0) {
+#pragma unroll
+                for (int r = 0; r < 16; r++) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v) : "r"(k1), "r"(k2));
+            } else if (MODE == 1) {
+#pragma unroll
+                for (int r = 0; r < 16; r++) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(v) : "r"(k1), "r"(k2));
+            } else if (MODE == 2) {
+#pragma unroll
+                for (int r = 0; r < 16; r++) asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(v) : "r"(k1), "r"(k2));
+            } else if (MODE == 3) {
+#pragma unroll
+                for (int r = 0; r < 16; r++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v) : "r"(k1), "r"(k2));
+            } else {
+                uint32_t w = v ^ k2;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {  // two Myers-step mixes: (4 LOP3, 1 SHF, 2 IMAD) x 2
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v) : "r"(w), "r"(k2));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w) : "r"(k1), "r"(v));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(v) : "r"(w), "r"(k1));
+                    asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(w) : "r"(v), "r"(k2));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x1e;" : "+r"(v) : "r"(w), "r"(k2));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w) : "r"(k1), "r"(v));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v) : "r"(w), "r"(k1));
+                }
+                v ^= w;
+            }
+            x[c] = v;
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc ^= x[c];
+    if (acc == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;  // keeps the chains alive, (almost) never stores
+}
+
+// out[0..4]: lane-operations per second of LOP3 / SHF / IADD3 / IMAD alone and of the ALU-pipe instructions (LOP3 + SHF) inside
+// the block-DP mix; out[5]: SM clock in Hz during the probe (cycles of SM 0 / elapsed time is not available from the host: the
+// value is the device's current clock rate attribute); out[6]: the IMADs retired per second next to that mix.
+extern "C" int apa_int32_peak(apa_engine* e, double* out) {
+    if (!e || !out) return set_err(APA_ERR_NO_DEVICE, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    uint32_t* d_out = nullptr;
+    const int grid = e->sm_count * 8, block = 256, iters = 2000;
+    CUDA_TRY(cudaMalloc(&d_out, (size_t)grid * block * 4));
+    struct Free {
+        void* p;
+        ~Free() { cudaFree(p); }
+    } fr{d_out};
+    cudaStream_t st = e->stream;
+    auto run = [&](int mode, double& ms_out) -> cudaError_t {
+        for (int rep = 0; rep < 2; rep++) {  // first repetition warms up
+            cudaEventRecord(e->ev[0], st);
+            switch (mode) {
+                case 0: apa_peak_kernel<0><<<grid, block, 0, st>>>(d_out, iters, 0x9e3779b9u, 0x7f4a7c15u); break;
+                case 1: apa_peak_kernel<1><<<grid, block, 0, st>>>(d_out, iters, 0x9e3779b9u, 7u); break;
+                case 2: apa_peak_kernel<2><<<grid, block, 0, st>>>(d_out, iters, 0x9e3779b9u, 0x7f4a7c15u); break;
+                case 3: apa_peak_kernel<3><<<grid, block, 0, st>>>(d_out, iters, 0x9e3779b9u, 0x7f4a7c15u); break;
+                default: apa_peak_kernel<4><<<grid, block, 0, st>>>(d_out, iters, 0x9e3779b9u, 13u); break;
+            }
+            cudaEventRecord(e->ev[1], st);
+            cudaError_t ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess) return ce;
+            float ms = 0;
+            ce = cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+            if (ce != cudaSuccess) return ce;
+            ms_out = ms;
+        }
+        return cudaGetLastError();
+    };
+    const double lanes = (double)grid * block * iters * 8.0;
+    for (int mode = 0; mode < 4; mode++) {
+        double ms = 0;
+        CUDA_TRY(run(mode, ms));
+        out[mode] = lanes * 16.0 / (ms * 1e-3);  // MODE 2: the two adds of a round fuse into one IADD3
+    }
+    double ms = 0;
+    CUDA_TRY(run(4, ms));
+    out[4] = lanes * 10.0 / (ms * 1e-3);
+    out[6] = lanes * 4.0 / (ms * 1e-3);
+    int khz = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device));
+    out[5] = khz * 1e3;
+    return APA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K0 on its own (tests)
+extern "C" int apa_pack_planes_device(apa_engine* e, const uint8_t* seq, uint64_t len, uint32_t* out, uint64_t out_cap_halfwords,
+                                      uint64_t* n_halfwords) {
+    if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
+    if (len >= (1ull << 31) - 1024) return set_err(APA_ERR_TOO_LARGE, "sequence length must be < 2^31");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const uint64_t nhw = (((len + 63) / 64) * 2 + 2 + 15) & ~15ull;
+    if (n_halfwords) *n_halfwords = nhw;
+    if (out_cap_halfwords < nhw) return set_err(APA_ERR_TOO_LARGE, "apa_pack_planes_device: output too small");
+    uint8_t* d_raw = nullptr;
+    uint2* d_prof = nullptr;
+    int64_t* d_off = nullptr;
+    int* d_bad = nullptr;
+    struct Free {
+        void** p[4];
+        ~Free() {
+            for (void** q : p) cudaFree(*q);
+        }
+    } free_all{{(void**)&d_raw, (void**)&d_prof, (void**)&d_off, (void**)&d_bad}};
+    // the sequence is placed at an odd offset: the kernel must not assume any alignment of the raw bases
+    CUDA_TRY(cudaMalloc(&d_raw, len + 64));
+    CUDA_TRY(cudaMalloc(&d_prof, nhw * 8));
+    CUDA_TRY(cudaMalloc(&d_off, 6 * 8));
+    CUDA_TRY(cudaMalloc(&d_bad, 4));
+    const int64_t offs[6] = {3, 3 + (int64_t)len, 0, 0, 0, (int64_t)nhw};  // a_off[2] | b_off[2] (empty b) | plane offsets[2]
+    CUDA_TRY(cudaMemcpy(d_off, offs, sizeof offs, cudaMemcpyHostToDevice));
+    if (len) CUDA_TRY(cudaMemcpy(d_raw + 3, seq, len, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(d_prof, 0xff, nhw * 8));
+    CUDA_TRY(cudaMemset(d_bad, 0, 4));
+    BatchDev bd{};
+    bd.n_pairs = 1;
+    bd.a_off = d_off;
+    bd.b_off = d_off + 2;
+    bd.ap_off = d_off + 4;
+    bd.bp_off = d_off + 2;  // {0, 0}: b is empty and owns no half-words
+    bd.aprof = d_prof;
+    bd.bprof = d_prof;
+    bd.raw_a = d_raw;
+    bd.raw_b = d_raw;
+    apa_pack_kernel<<<dim3(1, 4), 256, 0, e->stream>>>(bd, d_bad);
+    CUDA_TRY(cudaGetLastError());
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(out, d_prof, nhw * 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (bad) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT (the reference panics here: pa-bitpacking/src/profile.rs:113)");
+    return APA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ block KAT entry
 extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, const uint8_t* b, uint64_t mb, uint8_t* h, uint64_t* v,
                                  int64_t* bottom_sum) {
@@ -1506,8 +1825,14 @@ extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, c
         vv[2 * w] = make_uint2((uint32_t)v[2 * w], (uint32_t)v[2 * w + 1]);
         vv[2 * w + 1] = make_uint2((uint32_t)(v[2 * w] >> 32), (uint32_t)(v[2 * w + 1] >> 32));
     }
-    uint2 *d_a, *d_bp, *d_v, *d_fill;
-    int32_t* d_cum;
+    uint2 *d_a = nullptr, *d_bp = nullptr, *d_v = nullptr, *d_fill = nullptr;
+    int32_t* d_cum = nullptr;
+    struct Free {  // the CUDA_TRYs below may return early
+        void** p[5];
+        ~Free() {
+            for (void** q : p) cudaFree(*q);
+        }
+    } free_all{{(void**)&d_a, (void**)&d_bp, (void**)&d_v, (void**)&d_fill, (void**)&d_cum}};
     CUDA_TRY(cudaMalloc(&d_a, (nhw_a + 2) * 8));
     CUDA_TRY(cudaMalloc(&d_bp, (nhw + 2) * 8));
     CUDA_TRY(cudaMalloc(&d_v, nhw * 8));
@@ -1523,11 +1848,6 @@ extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, c
     std::vector<uint2> vin = vv;
     CUDA_TRY(cudaMemcpy(vv.data(), d_v, nhw * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(fill.data(), d_fill, na * nhw * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d_a);
-    cudaFree(d_bp);
-    cudaFree(d_v);
-    cudaFree(d_cum);
-    cudaFree(d_fill);
     for (uint64_t w = 0; w < nwords; w++) {
         v[2 * w] = (uint64_t)vv[2 * w].x | ((uint64_t)vv[2 * w + 1].x << 32);
         v[2 * w + 1] = (uint64_t)vv[2 * w].y | ((uint64_t)vv[2 * w + 1].y << 32);
@@ -1550,32 +1870,140 @@ extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, c
     return APA_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ drop-in symbols
-static std::mutex g_default_mu;
-static apa_engine* g_default_engine = nullptr;
+// ------------------------------------------------------------------------------------------------ process-wide engines
+// One engine per device, created on first use and shared by the single-pair drop-in symbols and apa_align_batch_multi. An
+// engine has one stream and one work queue: concurrent callers of the same device take turns (per-engine mutex).
+struct EngineSlot {
+    std::mutex mu;
+    apa_engine* eng = nullptr;
+};
+static std::mutex g_slots_mu;
+static std::unordered_map<int, EngineSlot*> g_slots;
 
-static apa_engine* default_engine() {
-    std::lock_guard<std::mutex> lk(g_default_mu);
-    if (!g_default_engine) {
-        int rc = apa_engine_create(0, &g_default_engine);
-        if (rc != APA_OK) {
-            // Same contract as the reference, whose failures are Rust panics that abort the process
-            // (astarpa-c/src/lib.rs has no error path). There is no CPU fallback.
-            fprintf(stderr, "libastarpa_c (B200): %s\n", apa_last_error());
-            abort();
-        }
+static EngineSlot* engine_slot(int device) {  // nullptr on failure (apa_last_error() says why)
+    EngineSlot* sl;
+    {
+        std::lock_guard<std::mutex> lk(g_slots_mu);
+        auto it = g_slots.find(device);
+        if (it == g_slots.end()) it = g_slots.emplace(device, new EngineSlot()).first;
+        sl = it->second;
     }
-    return g_default_engine;
+    std::lock_guard<std::mutex> lk(sl->mu);
+    if (!sl->eng && apa_engine_create(device, &sl->eng) != APA_OK) return nullptr;
+    return sl;
 }
 
-static uint64_t align_one(int preset, const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len, uint8_t** cigar_ptr,
-                          uintptr_t* cigar_len) {
-    apa_engine* e = default_engine();
-    std::lock_guard<std::mutex> lk(g_default_mu);  // one stream per engine: serialise concurrent callers
+// ------------------------------------------------------------------------------------------------ multi-GPU batch call
+// Pairs are independent (astarpa2/src/lib.rs:50-53 builds a fresh aligner per call): the batch is cut into contiguous shards
+// balanced by bases, one per device, each aligned by that device's engine on its own host thread - no data-path collective
+// (SURVEY 8e). Results come back in input order; the CIGAR texts of all shards share one page-locked pool.
+extern "C" int apa_align_batch_multi(const int* devices, int n_devices, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all,
+                                     const int64_t* a_off, const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool,
+                                     int64_t* cigar_off, int64_t* cigar_len, apa_batch_stats* stats) {
+    if (cigar_pool) *cigar_pool = nullptr;
+    if (!devices || n_devices < 1) return set_err(APA_ERR_BAD_INPUT, "apa_align_batch_multi: no devices");
+    for (int d = 0; d < n_devices; d++)
+        for (int d2 = 0; d2 < d; d2++)
+            if (devices[d] == devices[d2]) return set_err(APA_ERR_BAD_INPUT, "apa_align_batch_multi: device listed twice");
+    // shard bounds: the prefix of pairs whose bases reach (d + 1) / n_devices of the total
+    std::vector<uint64_t> lo(n_devices + 1, n_pairs);
+    lo[0] = 0;
+    {
+        const long double total = (long double)(a_off[n_pairs] - a_off[0]) + (long double)(b_off[n_pairs] - b_off[0]);
+        uint64_t p = 0;
+        for (int d = 1; d < n_devices; d++) {
+            const long double target = total * d / n_devices;
+            while (p < n_pairs && (long double)(a_off[p] - a_off[0]) + (long double)(b_off[p] - b_off[0]) < target) p++;
+            lo[d] = p;
+        }
+    }
+    struct Shard {
+        EngineSlot* slot = nullptr;
+        apa_batch* b = nullptr;
+        int rc = APA_OK;
+        std::string err;
+        uint64_t pool_base = 0;
+    };
+    std::vector<Shard> sh(n_devices);
+    for (int d = 0; d < n_devices; d++) {
+        sh[d].slot = engine_slot(devices[d]);
+        if (!sh[d].slot) return APA_ERR_NO_DEVICE;  // message set by apa_engine_create
+    }
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int d = 0; d < n_devices; d++) locks.emplace_back(sh[d].slot->mu);
+    auto for_each_shard = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int d = 1; d < n_devices; d++) th.emplace_back([&, d]() { fn(d); if (sh[d].rc != APA_OK) sh[d].err = g_last_error; });
+        fn(0);
+        if (sh[0].rc != APA_OK) sh[0].err = g_last_error;
+        for (auto& t : th) t.join();
+    };
+    for_each_shard([&](int d) {  // phase 1: upload + run
+        Shard& s = sh[d];
+        apa_engine* e = s.slot->eng;
+        s.rc = batch_prepare(e, lo[d + 1] - lo[d], a_all, a_off + lo[d], b_all, b_off + lo[d], true, &s.b);
+        if (s.rc == APA_OK) s.rc = batch_run(e, s.b, preset, trace, true);
+    });
+    int rc = APA_OK;
+    for (int d = 0; d < n_devices && rc == APA_OK; d++)
+        if (sh[d].rc != APA_OK) rc = set_err(sh[d].rc, "device " + std::to_string(devices[d]) + ": " + sh[d].err);
+    char* pool = nullptr;
+    if (rc == APA_OK) {
+        uint64_t total_pool = 0;
+        for (int d = 0; d < n_devices; d++) {
+            sh[d].pool_base = total_pool;
+            total_pool += sh[d].b->pool_used;
+        }
+        const bool want_cigars = trace && cigar_pool && cigar_off && cigar_len;
+        if (want_cigars) {
+            pool = (char*)pinned_pool_get(std::max<uint64_t>(total_pool, 1));
+            if (!pool) rc = set_err(APA_ERR_TOO_LARGE, "host allocation of the CIGAR pool failed");
+        }
+        if (rc == APA_OK) {
+            for_each_shard([&](int d) {  // phase 2: download, every shard into its slice of the outputs
+                Shard& s = sh[d];
+                const uint64_t p0 = lo[d], np = lo[d + 1] - lo[d];
+                s.rc = batch_download(s.slot->eng, s.b, costs + p0, nullptr, want_cigars ? cigar_off + p0 : nullptr,
+                                      want_cigars ? cigar_len + p0 : nullptr, want_cigars ? pool + s.pool_base : nullptr);
+                if (s.rc == APA_OK && want_cigars)
+                    for (uint64_t p = 0; p < np; p++) cigar_off[p0 + p] += (int64_t)s.pool_base;
+                if (s.rc == APA_OK && stats) stats[d] = s.b->stats;
+            });
+            for (int d = 0; d < n_devices && rc == APA_OK; d++)
+                if (sh[d].rc != APA_OK) rc = set_err(sh[d].rc, "device " + std::to_string(devices[d]) + ": " + sh[d].err);
+        }
+    }
+    for (int d = 0; d < n_devices; d++) apa_batch_free(sh[d].slot->eng, sh[d].b);
+    if (rc != APA_OK) {
+        if (pool) apa_free(pool);
+        return rc;
+    }
+    if (cigar_pool) *cigar_pool = pool;
+    return APA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ drop-in symbols
+// The reference's single-pair entry points (astarpa-c/src/lib.rs:8-101) on the device APA_DEVICE names (default 0).
+static int default_device() {
+    const char* ev = getenv("APA_DEVICE");
+    return ev ? atoi(ev) : 0;
+}
+
+static uint64_t align_one(int preset, const apa_params* params, const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len,
+                          uint8_t** cigar_ptr, uintptr_t* cigar_len) {
+    EngineSlot* sl = engine_slot(default_device());
+    if (!sl) {
+        // Same contract as the reference, whose failures are Rust panics that abort the process
+        // (astarpa-c/src/lib.rs has no error path). There is no CPU fallback.
+        fprintf(stderr, "libastarpa_c (B200): %s\n", apa_last_error());
+        abort();
+    }
+    std::lock_guard<std::mutex> lk(sl->mu);  // one stream per engine: serialise concurrent callers
     int64_t a_off[2] = {0, (int64_t)a_len}, b_off[2] = {0, (int64_t)b_len};
     int64_t cost = -1, coff = 0, clen = 0;
     char* pool = nullptr;
-    int rc = apa_align_batch(e, preset, 1, 1, a, a_off, b, b_off, &cost, &pool, &coff, &clen, nullptr);
+    int rc = params ? apa_align_batch_params(sl->eng, params, 1, 1, a, a_off, b, b_off, &cost, &pool, &coff, &clen, nullptr)
+                    : apa_align_batch(sl->eng, preset, 1, 1, a, a_off, b, b_off, &cost, &pool, &coff, &clen, nullptr);
     if (rc != APA_OK) {
         fprintf(stderr, "libastarpa_c (B200): %s\n", apa_last_error());
         abort();
@@ -1591,19 +2019,42 @@ static uint64_t align_one(int preset, const uint8_t* a, uintptr_t a_len, const u
 
 extern "C" uint64_t astarpa2_simple(const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len, uint8_t** cigar_ptr,
                                     uintptr_t* cigar_len) {
-    return align_one(APA_PRESET_SIMPLE, a, a_len, b, b_len, cigar_ptr, cigar_len);
+    return align_one(APA_PRESET_SIMPLE, nullptr, a, a_len, b, b_len, cigar_ptr, cigar_len);
 }
 extern "C" uint64_t astarpa2_full(const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len, uint8_t** cigar_ptr,
                                   uintptr_t* cigar_len) {
-    return align_one(APA_PRESET_FULL, a, a_len, b, b_len, cigar_ptr, cigar_len);
+    return align_one(APA_PRESET_FULL, nullptr, a, a_len, b, b_len, cigar_ptr, cigar_len);
 }
-// A*PA v1 entry points (astarpa-c/src/lib.rs:54-95): served by the A*PA2 engine — same optimal cost, a valid CIGAR.
+// A*PA v1 entry points (astarpa-c/src/lib.rs:54-95). The v1 engine (astar_dt, an A* over single states) is out of scope
+// (SURVEY 8f row 2); these symbols are served by the A*PA2 block engine bounded by the heuristic the caller names: GCSH with
+// exact matches of length k, no local pruning (MatchConfig::new(k, r), pa-heuristic/src/matches.rs:404-410), pruning by match
+// start. The cost is the edit distance either way and the CIGAR is an optimal alignment; its tie-breaks are A*PA2's, not v1's.
+// Arguments the heuristic cannot honour are refused loudly, never ignored: inexact matches (r = 2, matches/inexact.rs) and
+// Prune::Both (prune_end) are not built, so `astarpa` (= astarpa_gcsh(r = 2, k = 15, false), lib.rs:54-64) runs GCSH(r = 1,
+// k = 15) and says so once on stderr, and astarpa_gcsh aborts with a message for r != 1 or prune_end, as a reference panic would.
+static uint64_t align_gcsh(const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len, uintptr_t k, uint8_t** cigar_ptr,
+                           uintptr_t* cigar_len) {
+    apa_params q;
+    apa_params_preset(APA_PRESET_FULL, &q);
+    q.k = (int32_t)k;
+    q.p = 0;
+    return align_one(-1, &q, a, a_len, b, b_len, cigar_ptr, cigar_len);
+}
 extern "C" uint64_t astarpa(const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len, uint8_t** cigar_ptr,
                             uintptr_t* cigar_len) {
-    return align_one(APA_PRESET_FULL, a, a_len, b, b_len, cigar_ptr, cigar_len);
+    static std::atomic<bool> said{false};
+    if (!said.exchange(true))
+        fprintf(stderr, "libastarpa_c (B200): astarpa() = A*PA v1 with inexact matches (r = 2, k = 15) is served by the A*PA2 engine with "
+                        "GCSH(r = 1, k = 15): same cost, an optimal CIGAR with A*PA2's tie-breaks\n");
+    return align_gcsh(a, a_len, b, b_len, 15, cigar_ptr, cigar_len);
 }
-extern "C" uint64_t astarpa_gcsh(const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len, uintptr_t, uintptr_t, bool,
-                                 uint8_t** cigar_ptr, uintptr_t* cigar_len) {
-    return align_one(APA_PRESET_FULL, a, a_len, b, b_len, cigar_ptr, cigar_len);
+extern "C" uint64_t astarpa_gcsh(const uint8_t* a, uintptr_t a_len, const uint8_t* b, uintptr_t b_len, uintptr_t r, uintptr_t k,
+                                 bool prune_end, uint8_t** cigar_ptr, uintptr_t* cigar_len) {
+    if (r != 1 || prune_end || k < 4 || k > 16) {
+        fprintf(stderr, "libastarpa_c (B200): astarpa_gcsh(r = %zu, k = %zu, prune_end = %d): only r = 1 (exact matches), k = 4..16, "
+                        "prune_end = false are built\n", (size_t)r, (size_t)k, (int)prune_end);
+        abort();
+    }
+    return align_gcsh(a, a_len, b, b_len, k, cigar_ptr, cigar_len);
 }
 extern "C" void astarpa_free_cigar(uint8_t* cigar) { free(cigar); }

@@ -19,7 +19,7 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
     WarpSmem& sm = smem[wib];
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + wib;
     uint8_t* arena = bd.arena + (size_t)slot * bd.arena_size;
-    unsigned long long acc_steps = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0, acc_h = 0, acc_probe = 0;
+    unsigned long long acc_steps = 0, acc_issue = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0, acc_h = 0, acc_probe = 0;
 
     for (;;) {
         unsigned long long q = 0;
@@ -46,7 +46,7 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
         cx.v_top = meta_bytes;
         cx.hi_bot = bd.arena_size;
         cx.status = ST_PENDING;
-        cx.word_steps = cx.computed_cells = 0;
+        cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
         cx.passes = 0;
         cx.fill_blocks = cx.dt_blocks = 0;
         for (int t = 0; t < 8; t++) cx.tphase[t] = 0;
@@ -110,7 +110,8 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
             ps[0] = cx.passes, ps[4] = (long long)cx.computed_cells, ps[5] = cx.dt_blocks, ps[6] = cx.fill_blocks, ps[7] = 0;
         }
         if (bd.dbg_n && lane == 0) *bd.dbg_n = cx.dbg_n;
-        acc_steps += cx.word_steps;
+        acc_steps += cx.dpc.word_steps;
+        acc_issue += cx.dpc.issue_steps;
         acc_cells += cx.computed_cells;
         acc_pass += cx.passes;
         acc_fill += cx.fill_blocks;
@@ -118,6 +119,7 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
     }
     if (lane == 0) {
         atomicAdd(&bd.stats[0], acc_steps);
+        atomicAdd(&bd.stats[15], acc_issue);
         atomicAdd(&bd.stats[1], acc_cells);
         atomicAdd(&bd.stats[2], acc_pass);
         atomicAdd(&bd.stats[3], acc_fill);

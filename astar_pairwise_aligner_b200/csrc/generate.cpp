@@ -19,7 +19,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/astarpa_b200.h"
+#include "../../include/apa_generate.h"
 
 namespace {
 
@@ -175,3 +175,12 @@ int apa_generate_batch(uint64_t n_pairs, uint64_t n, double e, int model, uint64
 }
 
 }  // extern "C"
+
+extern "C" void apa_fnv1a_batch(const char* pool, const int64_t* off, const int64_t* len, uint64_t n_texts, uint64_t* out) {
+    for (uint64_t p = 0; p < n_texts; p++) {
+        uint64_t h = 1469598103934665603ull;
+        const unsigned char* s = (const unsigned char*)pool + off[p];
+        for (int64_t k = 0; k < len[p]; k++) h = (h ^ s[k]) * 1099511628211ull;
+        out[p] = h;
+    }
+}

@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/apa_generate.h"
 #include "../../include/astarpa2.hpp"
 #include "pa_input.hpp"
 

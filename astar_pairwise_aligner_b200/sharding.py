@@ -3,6 +3,8 @@ bases, no data-path collective; torch.distributed (NCCL on GPUs, gloo in the CPU
 
 The reference has no parallelism of its own; pairs are independent because a fresh aligner is built per call
 (astarpa2/src/lib.rs:50-53)."""
+import ctypes as C
+
 import numpy as np
 
 
@@ -57,3 +59,20 @@ def align_batch_sharded(a_all, a_off, b_all, b_off, preset, trace, align_fn, dis
         if trace:
             out_cigars[gs:ge] = gcig
     return out_costs, out_cigars
+
+
+def gpu_align_fn(device):
+    """The product aligner for `align_batch_sharded`: this rank's shard through the multi-GPU C-ABI entry
+    (apa_align_batch_multi) on its own device - (costs, list of CIGAR strings or None)."""
+    import astar_pairwise_aligner_b200 as A
+
+    def fn(a_all, a_off, b_all, b_off, preset, trace):
+        costs, pool, off, ln, _ = A.align_batch_multi([device], a_all, a_off, b_all, b_off, preset, trace)
+        cigars = None
+        if trace and pool.value:
+            cigars = [C.string_at(pool.value + int(off[p]), int(ln[p])).decode() for p in range(len(costs))]
+        elif trace:
+            cigars = []
+        A.free_pool(pool)
+        return costs, cigars
+    return fn

@@ -5,7 +5,10 @@
   python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
 
 A "step" is one pass of the hot path over one batch of synthetic pairs (BASELINE.json configs[2]:
-n = 100 000, e = 5 %, with CIGAR traceback; --pairs pairs per GPU, weak scaling).
+n = 100 000, e = 5 %, with CIGAR traceback). --scaling weak (default): --pairs pairs per GPU; --scaling strong: --pairs
+pairs in total, cut into contiguous shards balanced by bases (astar_pairwise_aligner_b200/sharding.py), one per rank.
+Every run checks the GPU results against the oracle on the pairs of the CPU-baseline sample (cost and CIGAR text digest)
+and the e2e results against the resident ones on every pair; a mismatch fails the run (`parity_checked_pairs`).
 `value`   : effective GCUPS = sum |a||b| / device time, inputs already resident in HBM (CUDA events on the
             engine's stream around the kernels of each step).
 `e2e`     : the same metric through the public C-ABI batch call with HOST (pinned) buffers: H2D of the sequences,
@@ -46,7 +49,9 @@ def parse():
     ap.add_argument("--e", type=float, default=0.05)
     ap.add_argument("--no-trace", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end iterations (0 = --steps)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --pairs per GPU; strong: --pairs in total, sharded over the ranks")
     return ap.parse_args()
 
 
@@ -151,12 +156,34 @@ def cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, sample):
                                                     b_off[:sample + 1], preset_id, trace, threads)
     assert (costs >= 0).all(), "oracle panic in the CPU baseline"
     eff = float(np.sum((a_off[1:sample + 1] - a_off[:sample]).astype(np.float64) * (b_off[1:sample + 1] - b_off[:sample])))
+    cpu_leg.sample_results = (costs.copy(), chash.copy())  # for the in-run parity check of the GPU results
     return {"value": eff / sec / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{sample} pairs of the same workload (n={args.n}, e={args.e}, preset {args.preset}, "
                       f"{'with' if trace else 'no'} CIGAR), {sec:.2f} s wall on {threads} threads",
             "computed_gcups": float(cells.sum()) / sec / 1e9, "bp_per_s": float(a_off[sample]) / sec, "seconds": sec,
             "pairs": sample, "pairs_per_s": sample / sec, "hardware_threads": O.lib().oracle_hardware_threads(),
             "cgroup_cpu_quota": quota}
+
+
+def cpu_micro():
+    """The reference's own micro-benchmark (pa-bitpacking/benches/nw/main.rs:139-159): the block kernel
+    on a 256-column x h-row rectangle with +1 input deltas, one thread, restated reference layout (oracle port). GCUPS."""
+    import oracle_lib as O
+    L = O.lib()
+    import astar_pairwise_aligner_b200 as A
+    out = {}
+    for h in (64, 128, 256, 512):
+        a, _ = A.generate_pair(256, 0.0, 0, 31415)
+        b, _ = A.generate_pair(h, 0.0, 0, 31416)
+        hb = np.ones(256, dtype=np.uint8)
+        v = np.zeros(2 * (h // 64), dtype=np.uint64)
+        reps = 20000
+        t0 = time.perf_counter()
+        L.oracle_bp_compute_bench(a, len(a), b, len(b), reps)
+        dt = time.perf_counter() - t0
+        out[f"256x{h}"] = 256.0 * h * reps / dt / 1e9
+    return {"gcups_one_thread": out, "what": "oracle_bp_compute (restated simd::compute, 4 x u64 lanes x 2) on 256 columns x h rows, +1 deltas",
+            "source": "pa-bitpacking/benches/nw/main.rs:139-159"}
 
 
 def main():
@@ -170,7 +197,8 @@ def main():
     shape = (args.n, round(args.e, 3), trace, args.preset)
     cfg = {(100000, 0.05, True, "full"): "BASELINE configs[2]", (10000, 0.05, False, "full"): "BASELINE configs[1]",
            (1000000, 0.15, True, "full"): "BASELINE configs[3]", (10000000, 0.05, True, "full"): "BASELINE configs[4]"}.get(shape, "other shape")
-    workload = (f"{cfg}: {args.pairs} pairs/GPU, n={args.n}, e={args.e:g}, uniform errors, astarpa2_{args.preset}, "
+    per = "pairs/GPU" if args.scaling == "weak" else f"pairs in total over {world} GPU(s)"
+    workload = (f"{cfg}: {args.pairs} {per}, n={args.n}, e={args.e:g}, uniform errors, astarpa2_{args.preset}, "
                 f"{'cost+CIGAR' if trace else 'cost only'}; inputs {2 * args.pairs * args.n / 1e9:.2f} GB/GPU > L2 (no flush needed)")
     config = {"workload": workload, "pairs_per_gpu": args.pairs, "n": args.n, "e": args.e, "preset": args.preset, "trace": trace,
               "sharding": f"independent pairs, {world} rank(s), no data-path collective", "l2": "inputs larger than L2"}
@@ -196,7 +224,7 @@ def main():
         last["value"] = val
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+                          "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
                           "cpu_baseline": last, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}))
         return
@@ -212,7 +240,16 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    a_all, a_off, b_all, b_off = make_batch(A, args, rank)
+    if args.scaling == "strong":
+        # one batch of --pairs pairs in total (the same on every rank: seeded), this rank aligns its contiguous shard
+        from astar_pairwise_aligner_b200.sharding import shard_bounds, slice_batch
+        full = make_batch(A, args, 0)
+        s0, s1 = shard_bounds(full[1], full[3], world)[rank]
+        a_all, a_off, b_all, b_off = slice_batch(*full, s0, s1)
+        del full
+    else:
+        a_all, a_off, b_all, b_off = make_batch(A, args, rank)
+    n_local = len(a_off) - 1
     eng = A.Engine(local_rank)
     eff_cells = float(np.sum((a_off[1:] - a_off[:-1]).astype(np.float64) * (b_off[1:] - b_off[:-1])))
     total_bp = float(a_off[-1])
@@ -235,31 +272,38 @@ def main():
         launches += st["kernel_launches"]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
     costs, pool, off, ln = batch.download_raw()
+    digests = A.cigar_digests(pool, off, ln) if trace else None
     d2h_bytes = batch.stats()["d2h_bytes"]
     batch.free_pool(pool)
     ms_step = kernel_ms / args.steps
 
-    # ---- end-to-end through the public batch call with host buffers (e2e)
+    # ---- end-to-end through the public multi-GPU batch call with host (page-locked) buffers (e2e): H2D of this step's bases,
+    # kernels, D2H of costs + CIGAR texts inside the timed region, every step; this rank drives its own GPU
     e2e_ms = []
     h2d_bytes = 0
-    for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+    e2e_steps = args.e2e_steps or args.steps
+    s2 = None
+    for it in range(args.warmup + e2e_steps):
         barrier()
         t1 = time.perf_counter()
-        c2, pool2, off2, ln2, s2 = eng.align_batch_raw(a_pin, a_off, b_pin, b_off, preset_id, trace)  # the public batch call
+        c2, pool2, off2, ln2, s2 = A.align_batch_multi([local_rank], a_pin, a_off, b_pin, b_off, preset_id, trace)
         dt = (time.perf_counter() - t1) * 1e3
+        s2 = s2[0]
         h2d_bytes, d2h_bytes = s2["h2d_bytes"], s2["d2h_bytes"]
-        eng.free_pool(pool2)
-        if it > 0:
+        if it >= args.warmup:
             e2e_ms.append(dt)
-        assert (c2 == costs).all()
+        if it == 0:  # the e2e path gives what the resident path gives, on every pair
+            assert (c2 == costs).all(), "e2e costs differ from the resident run"
+            assert not trace or (A.cigar_digests(pool2, off2, ln2) == digests).all(), "e2e CIGARs differ from the resident run"
+        A.free_pool(pool2)
+    clocks = sampler.stop()
     e2e_step = float(np.mean(e2e_ms)) if e2e_ms else float('nan')
 
     # ---- reduce over ranks: max time, sum of work
     agg = np.array([ms_step, e2e_step, *(phase_ms / args.steps)], dtype=np.float64)
-    work = np.array([eff_cells, float(st["computed_cells"]), total_bp, float(st["dp_word_steps"]), float(a_off[-1] + b_off[-1])],
-                    dtype=np.float64)
+    work = np.array([eff_cells, float(st["computed_cells"]), total_bp, float(st["dp_word_steps"]), float(a_off[-1] + b_off[-1]),
+                     float(st["dp_issue_steps"]), float(n_local)], dtype=np.float64)
     if dist is not None:
         import torch
         t_agg = torch.tensor(agg, device="cuda")
@@ -273,7 +317,7 @@ def main():
         return
     ms_step, e2e_step = float(agg[0]), float(agg[1])
     k_ms = [float(x) for x in agg[2:5]]
-    eff_all, comp_all, bp_all, wsteps_all, bases_all = work
+    eff_all, comp_all, bp_all, wsteps_all, bases_all, isteps_all, pairs_all = work
     value = eff_all / (ms_step / 1e3) / 1e9
     hbm_peak, peak_src, sm_max = peaks()
     comp_gpu = comp_all / world
@@ -292,19 +336,26 @@ def main():
         dom = KERNELS[int(np.argmax(k_ms))]
         dom_ms = max(k_ms)
     achieved = alg[dom] / (dom_ms / 1e3) / 1e9
-    # int32 ALU view of the block DP: ~17 ALU-pipe instructions per 32-row word step; pipe peak = 148 SMs x 64 lanes/clk
-    int_ops = (wsteps_all / world) * 17.0
-    int_peak = 148 * 64 * sm_mhz * 1e6
+    # INT32 view of the block DP: ALU-pipe instructions per 32-row word step (csrc/apa_blockdp.cuh: 8 LOP3 + 2 SHF; the 4 IMAD
+    # run on the FMA pipe and are not counted) against the ALU-pipe issue rate MEASURED on this GPU by apa_int32_peak
+    # (a dependent LOP3/SHF chain per warp, all SMs full) - not an assumed figure.
+    int_peak_meas = eng.int32_peak()
+    int_ops = (wsteps_all / world) * 10.0
+    int_peak = int_peak_meas["alu_lane_ops_per_s"]
     pass_ms = k_ms[1] if k_ms[1] > 0 else ms_step
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-vectors (i32 costs)",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32 bit-vectors (i32 costs)",
         "data": "synthetic", "config": config,
         "computed_gcups": comp_all / (ms_step / 1e3) / 1e9, "aligned_bp_per_s": bp_all / (ms_step / 1e3),
-        "pairs_per_s": args.pairs * world / (ms_step / 1e3), "wall_ms_per_step": wall_ms / args.steps,
-        "passes_per_pair": st["passes"] / args.pairs, "retries": st["retries"],
-        "h_queries_per_pair": st["score_calls"] / args.pairs,
+        "pairs_per_s": pairs_all / (ms_step / 1e3), "wall_ms_per_step": wall_ms / args.steps,
+        "passes_per_pair": st["passes"] / max(n_local, 1), "retries": st["retries"],
+        "h_queries_per_pair": st["score_calls"] / max(n_local, 1),
         "contour_probe_rounds_per_query": (st["score_probes"] / st["score_calls"]) if st["score_calls"] else None,
+        # block DP: useful 32-row lane-steps / lane-steps issued (32 lanes x steps of every chunk sweep, ramps included)
+        "lane_utilisation": (wsteps_all / isteps_all) if isteps_all else None,
+        "path": {"pass_warps_per_pair": st["pass_warps_per_pair"], "waves": st["waves"], "e2e_upload_mode": s2["upload_mode"] if s2 else None,
+                 "e2e_upload_chunks": s2["upload_chunks"] if s2 else None},
         "kernels": [{"name": k, "ms_per_launch": t, "share_of_step": t / ms_step if ms_step else None,
                      "algorithmic_gb_per_launch": alg[k] / 1e9} for k, t in zip(KERNELS, k_ms)],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -313,9 +364,11 @@ def main():
                      "note": "integer/latency-bound path: ~0.003 algorithmic B/cell in the block DP; the INT32-pipe view of the "
                              "block DP (apa_phase_pass_kernel) is in the int32_* fields",
                      "int32_ops_per_s": int_ops / (pass_ms / 1e3), "int32_peak_ops_per_s": int_peak,
-                     "int32_frac": int_ops / (pass_ms / 1e3) / int_peak},
+                     "int32_frac": int_ops / (pass_ms / 1e3) / int_peak,
+                     "int32_peak_source": "measured in this run (apa_int32_peak: LOP3 + SHF chains, ALU pipe)",
+                     "int32_peak_detail": int_peak_meas},
         "e2e": {"value": eff_all / (e2e_step / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                "ms_per_step": e2e_step},
+                "ms_per_step": e2e_step, "steps": len(e2e_ms), "api": "apa_align_batch_multi (host page-locked buffers in, host buffers out)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if any(st["phase_cycles"]):  # only with a TIMERS=1 build
@@ -323,6 +376,15 @@ def main():
                                         "prune_update"], [int(x) for x in st["phase_cycles"]]))
     if world == 1:
         out["cpu_baseline"] = cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, args.cpu_sample)
+        # in-run parity: the GPU results of this very batch against the oracle's, on every pair of the CPU sample
+        o_costs, o_digests = cpu_leg.sample_results
+        k = len(o_costs)
+        assert (costs[:k] == o_costs).all(), f"GPU costs differ from the oracle on pairs {np.flatnonzero(costs[:k] != o_costs)[:5]}"
+        if trace:
+            assert (digests[:k] == o_digests).all(), f"GPU CIGARs differ from the oracle on pairs {np.flatnonzero(digests[:k] != o_digests)[:5]}"
+        out["parity_checked_pairs"] = int(k)
+        out["parity"] = "GPU cost" + (" + CIGAR text (FNV-1a)" if trace else "") + f" == oracle on the first {k} pairs of the batch; e2e == resident on all {n_local}"
+        out["cpu_baseline"]["micro"] = cpu_micro()
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

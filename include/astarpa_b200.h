@@ -13,12 +13,6 @@
 extern "C" {
 #endif
 
-/* ---------------------------------------------------------------- synthetic input (stands in for pa-generate) */
-/* Error models: 0 Uniform, 1 NoisyInsert, 2 NoisyDelete, 3 SymmetricRepeat (pa-test/src/lib.rs:42-47). */
-int64_t apa_generate_pair(uint64_t n, double e, int model, uint64_t seed, uint8_t* a_out, uint8_t* b_out, uint64_t b_cap);
-int apa_generate_batch(uint64_t n_pairs, uint64_t n, double e, int model, uint64_t seed0, uint8_t* a_all, uint8_t* b_all,
-                       uint64_t b_stride, int64_t* b_len, int n_threads);
-
 /* ---------------------------------------------------------------- engine */
 #define APA_PRESET_SIMPLE 0 /* AstarPa2Params::simple(), astarpa2/src/params.rs:70-96  */
 #define APA_PRESET_FULL 1   /* AstarPa2Params::full(),   astarpa2/src/params.rs:98-128 */
@@ -55,6 +49,14 @@ typedef struct apa_batch_stats {
     /* GCSH queries of the pass kernel: h() calls and 32-layer probe rounds of the contour search (rounds / calls ~ 1 when
      * the per-stream extrapolation of the search start is good). Zero for astarpa2_simple and on the fused path. */
     uint64_t score_calls, score_probes;
+    /* Which path the last run took (tests assert the shape they mean to cover):
+     * pass_warps_per_pair: 1 = apa_phase_pass_kernel (one warp per pair), 4 / 8 = apa_phase_pass_coop_kernel, 0 = fused or general kernel;
+     * upload_mode: 0 resident batch (apa_batch_upload), 1 host-packed planes, plain copy, 2 host-packed planes, streamed under
+     * the running kernel, 3 raw bases by DMA + device-side K0, plain copy, 4 raw bases streamed under the running kernel;
+     * upload_chunks: H2D chunks of the bases; waves: arena waves of the phase-split path (1 = all pairs at once). */
+    uint32_t pass_warps_per_pair, upload_mode, upload_chunks, waves;
+    uint64_t dp_issue_steps; /* 32-row lane-steps ISSUED by the block DP: 32 lanes x anti-diagonals swept by every chunk (ramps, idle lanes
+                                and the feeder lane included); dp_word_steps / dp_issue_steps = lane utilisation */
 } apa_batch_stats;
 
 const char* apa_last_error(void);
@@ -89,10 +91,27 @@ void apa_free(void* p);
 void* apa_pinned_alloc(uint64_t bytes);
 void apa_pinned_free(void* p);
 
-/* Convenience: upload + run + download. */
+/* Host buffers in, host buffers out: upload + run + download in one call (the end-to-end path). Batches of more than one
+ * upload chunk (~32 MB of bases) stream: the kernels start on the first chunk while later chunks are still in flight.
+ * Page-locked inputs (apa_pinned_alloc, cudaHostAlloc, cudaHostRegister) are copied by DMA as raw bytes and packed to 2-bit
+ * planes on the device (K0 = BitProfile::build, pa-bitpacking/src/profile.rs:112-133, inside the kernel that opens each pair):
+ * no host thread touches the bases. Pageable inputs are packed by host threads into a pinned staging buffer first. */
 int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off,
                     const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool, int64_t* cigar_off,
                     int64_t* cigar_len, apa_batch_stats* stats);
+/* The same over several GPUs of one box: pairs are independent, so the batch is cut into n_devices contiguous
+ * shards balanced by bases, shard d runs on devices[d] (process-wide engine of that device, one host thread per device, no
+ * collective on the data path), and the results come back in input order with ONE page-locked CIGAR pool (release with
+ * apa_free). stats: NULL or n_devices entries (per-device timings of its shard). */
+int apa_align_batch_multi(const int* devices, int n_devices, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all,
+                          const int64_t* a_off, const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool,
+                          int64_t* cigar_off, int64_t* cigar_len, apa_batch_stats* stats);
+/* K0 on its own (tests): BitProfile::build of one sequence on the device, layout as in the engine - per 32 bases one
+ * (plane0, plane1) pair of u32 with the NEGATED rank bits of A0 C1 G2 T3, ceil(len / 64) * 2 + 2 half-words rounded up to
+ * a multiple of 16, zero past the end. out receives 2 u32 per half-word; *n_halfwords the count. Returns APA_ERR_BAD_INPUT for
+ * a byte outside ACGT (the reference panics, profile.rs:113). */
+int apa_pack_planes_device(apa_engine* e, const uint8_t* seq, uint64_t len, uint32_t* out, uint64_t out_cap_halfwords,
+                           uint64_t* n_halfwords);
 
 /* ---------------------------------------------------------------- general parameters
  * AstarPa2Params (astarpa2/src/params.rs:8-42) beyond the two presets: the other Domains and DoublingTypes, block widths,
@@ -154,6 +173,12 @@ int64_t apa_debug_band_log(apa_engine* e, int preset, int trace, const uint8_t* 
  * runs on the GPU (the block-DP step with zero top deltas and the pattern's match masks as equality words). */
 int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t pattern_len, const uint8_t* text, uint64_t text_len,
                float unmatched_cost, int32_t* out);
+
+/* INT32 issue-rate probe (bench.py's roofline denominator for the block DP, SURVEY 8d "must be measured"): lane-operations
+ * per second with every SM full of warps running dependent chains of out[0] LOP3, out[1] SHF, out[2] IADD3 (three-input add),
+ * out[3] IMAD; out[4] = the ALU-pipe instructions (8 LOP3 + 2 SHF per Myers step) of the block-DP instruction mix with its
+ * 4 IMAD per step running next to them on the FMA pipe, out[6] = those IMADs per second; out[5] = the device clock attribute in Hz. */
+int apa_int32_peak(apa_engine* e, double* out /* 7 doubles */);
 
 /* Block-DP kernel on its own (pa_bitpacking::simd::compute semantics, pa-bitpacking/src/simd.rs:98-226):
  * rectangle a[na] x b[mb]; h one byte per column (bit0 = +1, bit1 = -1), in/out; v interleaved (p,m) u64 pairs

@@ -288,6 +288,23 @@ int64_t oracle_bp_compute(const uint8_t* a, size_t na, const uint8_t* b, size_t 
     return s;
 }
 
+// The reference's micro-benchmark of the block kernel (pa-bitpacking/benches/nw/main.rs:139-159): `reps` evaluations of the
+// a[na] x b[mb] rectangle with all-(+1) input deltas, profile built once. Returns the last bottom-delta sum (keeps the loop live).
+int64_t oracle_bp_compute_bench(const uint8_t* a, size_t na, const uint8_t* b, size_t mb, int reps) {
+    std::vector<Bits> pa, pb;
+    bitprofile_build(a, na, b, mb, pa, pb);
+    std::vector<H> hh(na);
+    std::vector<V> vv(pb.size());
+    Cost s = 0;
+    for (int r = 0; r < reps; r++) {
+        for (size_t i = 0; i < na; i++) hh[i] = H{1, 0};
+        for (size_t j = 0; j < pb.size(); j++) vv[j] = V{~0ull, 0ull};
+        s += bp_compute(pa.data(), na, pb.data(), pb.size(), hh.data(), vv.data());
+        asm volatile("" ::"r"(hh.data()), "r"(vv.data()) : "memory");
+    }
+    return s;
+}
+
 uint64_t oracle_to_qgram(const uint8_t* s, int k) { return QGrams::to_qgram(s, k); }
 
 // pa_bitpacking::search (search.rs:46-118): out must hold np + nt + 1 values. Returns the count, or -1 on a reference panic.

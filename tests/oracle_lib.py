@@ -47,6 +47,8 @@ def lib():
         L.oracle_cigar_verify.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, u8p, C.c_size_t]
         L.oracle_bp_compute.restype = C.c_int64
         L.oracle_bp_compute.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.oracle_bp_compute_bench.restype = C.c_int64
+        L.oracle_bp_compute_bench.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_int]
         L.oracle_to_qgram.restype = C.c_uint64
         L.oracle_to_qgram.argtypes = [u8p, C.c_int]
         L.oracle_gcsh_info.restype = C.c_int64
