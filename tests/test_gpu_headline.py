@@ -28,7 +28,7 @@ def _check_against(apa, costs, pool, off, ln, want_costs, want_digests, what):
 
 
 @pytest.mark.parametrize("preset", [1, 0])
-def test_headline_shape_one_warp_per_pair_gpu(apa, oracle, engine, preset):
+def test_headline_shape_one_warp_per_pair_gpu(apa, oracle, engine, preset, monkeypatch):
     # 2 000 pairs of n = 100 000 at e = 5 % (400 MB of bases): more pairs than the cooperative kernel takes (1 184), more
     # bases than one upload chunk. All costs and CIGARs against the oracle, through (1) the resident path bench.py times as
     # `value`, (2) apa_align_batch from pageable memory (host-packed planes streamed under the running kernel), (3)
@@ -60,6 +60,7 @@ def test_headline_shape_one_warp_per_pair_gpu(apa, oracle, engine, preset):
     engine.free_pool(pool)
 
     a_pin, b_pin = apa.pinned_copy(a_all), apa.pinned_copy(b_all)
+    monkeypatch.setenv("APA_RAW", "1")  # (an engine with >= 12 host threads to itself would host-pack a batch this large)
     costs, pool, off, ln, st = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, preset, True)
     assert st["upload_mode"] == 4 and st["upload_chunks"] >= 8 and st["pass_warps_per_pair"] == 1, st
     _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "pinned, raw streamed")
