@@ -155,6 +155,14 @@ static AstarPa2Params preset_params(int preset) {
             q.delta = 200;
             return q;
         }
+        case 16:    // the heuristic of the legacy C entry points (astarpa-c/src/lib.rs:54-95): GCSH(MatchConfig::new(k, r = 1)) =
+        case 17:    // exact matches of length k, no local pruning (matches.rs:404-410), Prune::Start - on the A*PA2 block engine
+        case 18: {  // with the knobs of full(). k = 8 / 12 / 15.
+            AstarPa2Params q = AstarPa2Params::full();
+            q.k = preset == 16 ? 8 : (preset == 17 ? 12 : 15);
+            q.p = 0;
+            return q;
+        }
     }
     throw RefPanic("unknown preset");
 }

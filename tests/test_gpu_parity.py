@@ -119,6 +119,51 @@ def test_drop_in_symbols_gpu(apa):
         L.astarpa_free_cigar(cig)
 
 
+LEGACY_WORKER = r'''
+import ctypes as C, sys
+sys.path.insert(0, {root!r})
+import astar_pairwise_aligner_b200 as A
+L = A.load_library()
+cig, ln = C.c_void_p(), C.c_size_t()
+L.astarpa_gcsh(b"ACGTACGTACGTAAC", 15, b"ACGTACGTACGTAAC", 15, {r}, {k}, {pe}, C.byref(cig), C.byref(ln))
+print("RETURNED")
+'''
+
+
+def test_legacy_gcsh_symbols_gpu(apa, oracle, tmp_path):
+    # astarpa-c/src/lib.rs:54-95: astarpa_gcsh(r, k, prune_end) and astarpa() (= r 2, k 15). r = 1: the heuristic the caller
+    # names - GCSH with exact matches of length k, no local pruning, pruning by start - bounds the A*PA2 engine; cost and CIGAR
+    # against the oracle configured the same way (configurations 16 / 17 / 18 = k 8 / 12 / 15). Arguments that are not built
+    # (r = 2, prune_end) are refused with a message and an abort (the reference's failure mode is a panic), never ignored.
+    import subprocess
+    import sys
+    L = apa.load_library()
+    pairs = [apa.generate_pair(n, e, m, 77 + n) for n, e, m in [(0, 0.0, 0), (40, 0.1, 1), (900, 0.05, 0), (5000, 0.1, 2), (20000, 0.05, 3)]]
+    pairs.append((b"ACTCGCT", b"AACTCGTT"))  # astarpa-c/example.c
+    for k, cfg in ((8, 16), (12, 17), (15, 18)):
+        for a, b in pairs:
+            cig, ln = C.c_void_p(), C.c_size_t()
+            cost = L.astarpa_gcsh(a, len(a), b, len(b), 1, k, False, C.byref(cig), C.byref(ln))
+            text = C.string_at(cig.value).decode()
+            assert len(text) == ln.value
+            L.astarpa_free_cigar(cig)
+            oc, ocg, _ = oracle.align(a, b, cfg, True)
+            assert (cost, text) == (oc, ocg), (k, len(a))
+    for a, b in pairs:  # astarpa(): k = 15, served with exact matches (announced once on stderr)
+        cig, ln = C.c_void_p(), C.c_size_t()
+        cost = L.astarpa(a, len(a), b, len(b), C.byref(cig), C.byref(ln))
+        text = C.string_at(cig.value).decode()
+        L.astarpa_free_cigar(cig)
+        oc, ocg, _ = oracle.align(a, b, 18, True)
+        assert (cost, text) == (oc, ocg)
+    root = os.path.dirname(HERE)
+    for r, k, pe in ((2, 15, False), (1, 12, True), (1, 40, False)):
+        script = tmp_path / f"legacy_{r}_{k}_{int(pe)}.py"
+        script.write_text(LEGACY_WORKER.format(root=root, r=r, k=k, pe=pe))
+        out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
+        assert out.returncode != 0 and "RETURNED" not in out.stdout and "only r = 1" in out.stderr, (r, k, pe, out.stderr[-500:])
+
+
 def test_drop_in_c_program_gpu(apa, tmp_path):
     # A C caller compiled against include/astarpa.h and linked to libastarpa_c.so, like astarpa-c/example.c.
     import subprocess
