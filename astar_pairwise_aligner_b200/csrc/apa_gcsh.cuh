@@ -159,6 +159,11 @@ struct GcshH {
         return r;
     }
     // HintContours::new over the active arrows (hint_contours.rs:213-255) == state after update_layers.
+    // Matches are taken from the last to the first; each asks score(end) and joins layer score + 1. Along a chain almost every
+    // query is answered by one of the top few layers, so the warp keeps the TOP 32 LAYERS IN REGISTERS (lane l: the two inline
+    // points of layer nlayers - l and whether it has an overflow list): a query is a compare + ballot with no memory round
+    // trip, an insertion updates the owning lane and writes through to layer_pts / layer_head so that the table in memory is
+    // always what the plain algorithm would have left. Queries that no cached layer contains fall back to score() on memory.
     __device__ void build_layers() {
         const int lane = threadIdx.x & 31;
         for (int w = lane; w <= nlayers + 1 && w <= M + 1; w += 32) {
@@ -168,30 +173,84 @@ struct GcshH {
         __syncwarp();
         nlayers = 0;
         hint[3] = 0;
-        for (int idx = M - 1; idx >= 0; idx--) {
-            if (!active[idx]) continue;
-            I ex = px[idx] + 1, ey = py[idx] + 1;  // transform(end): P(end.i) = P(start.i) - 1
-            if (!(ex <= ttx && ey <= tty)) continue;
-            int v = score(ex, ey, 3) + 1;
-            if (lane == 0) {
-                int4 p = (v > nlayers) ? make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN) : layer_pts[v];
-                if (v > nlayers) layer_head[v] = -1;
-                if (p.x == INT32_MIN) {
-                    p.x = px[idx];
-                    p.y = py[idx];
-                    layer_pts[v] = p;
-                } else if (p.z == INT32_MIN) {
-                    p.z = px[idx];
-                    p.w = py[idx];
-                    layer_pts[v] = p;
-                } else {
-                    next[idx] = layer_head[v];
-                    layer_head[v] = idx;
-                }
+        int4 cp = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);  // cached layer nlayers - lane (valid iff that is >= 1)
+        bool covf = false;                                                 // ... has an overflow list
+        for (int base = M - 1; base >= 0; base -= 32) {
+            // the next 32 matches (indices base, base - 1, ...): one coalesced load each of active / px / py
+            const int my = base - lane;
+            I mx = 0, my_y = 0;
+            bool mok = false;
+            if (my >= 0 && active[my]) {
+                mx = px[my];
+                my_y = py[my];
+                mok = (mx + 1 <= ttx) && (my_y + 1 <= tty);  // transform(end) = transform(start) + (1, 1): P(end.i) = P(start.i) - 1
             }
-            if (v > nlayers) nlayers = v;
-            hint[3] = v;
-            __syncwarp();
+            unsigned todo = __ballot_sync(FULL, mok);
+            while (todo) {
+                const int t = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int idx = base - t;
+                const I sx = __shfl_sync(FULL, mx, t), sy = __shfl_sync(FULL, my_y, t);
+                const I ex = sx + 1, ey = sy + 1;
+                // score(end): the highest layer containing a point >= (ex, ey)
+                const int wl = nlayers - lane;
+                bool c = false;
+                if (wl >= 1) {
+                    c = (ex <= cp.x && ey <= cp.y) || (cp.z != INT32_MIN && ex <= cp.z && ey <= cp.w);
+                    if (!c && covf)
+                        for (int q = layer_head[wl]; q >= 0; q = next[q])
+                            if (ex <= px[q] && ey <= py[q]) {
+                                c = true;
+                                break;
+                            }
+                }
+                const unsigned bal = __ballot_sync(FULL, c);
+                int v;
+                if (bal)
+                    v = nlayers - (__ffs(bal) - 1) + 1;
+                else if (nlayers <= 32)
+                    v = 1;  // every layer >= 1 is cached and none contains the point: layer 0
+                else
+                    v = score(ex, ey, 3) + 1;  // below the cached window: search the table in memory
+                if (v > nlayers) {  // a new top layer: every cached layer moves one lane up
+                    cp.x = __shfl_up_sync(FULL, cp.x, 1);
+                    cp.y = __shfl_up_sync(FULL, cp.y, 1);
+                    cp.z = __shfl_up_sync(FULL, cp.z, 1);
+                    cp.w = __shfl_up_sync(FULL, cp.w, 1);
+                    covf = __shfl_up_sync(FULL, (int)covf, 1) != 0;
+                    if (lane == 0) {
+                        cp = make_int4(sx, sy, INT32_MIN, INT32_MIN);
+                        covf = false;
+                        layer_pts[v] = cp;
+                        layer_head[v] = -1;
+                    }
+                    nlayers = v;
+                } else if (nlayers - v < 32) {  // joins a cached layer: its lane updates registers and memory
+                    if (lane == nlayers - v) {
+                        if (cp.z == INT32_MIN) {
+                            cp.z = sx;
+                            cp.w = sy;
+                            layer_pts[v] = cp;
+                        } else {
+                            next[idx] = layer_head[v];
+                            layer_head[v] = idx;
+                            covf = true;
+                        }
+                    }
+                } else if (lane == 0) {  // joins a layer below the window: memory only (every layer <= nlayers has a first point)
+                    int4 p = layer_pts[v];
+                    if (p.z == INT32_MIN) {
+                        p.z = sx;
+                        p.w = sy;
+                        layer_pts[v] = p;
+                    } else {
+                        next[idx] = layer_head[v];
+                        layer_head[v] = idx;
+                    }
+                }
+                hint[3] = v;
+                __syncwarp();
+            }
         }
         hint[0] = hint[1] = hint[2] = hint[3];
         hq[0] = hq[1] = hq[2] = hq[3] = 0;
@@ -251,142 +310,74 @@ __device__ __forceinline__ T* pin_ptr(T* p) {
     return (T*)(((unsigned long long)hi << 32) | lo);
 }
 
-struct NmpdView {  // next_match_per_diag (matches.rs:147-148): diagonal -> start.i of the left-most kept match, default MAX
-    I* vb;         // biased: vb[d] for dmin <= d <= dmax
+// next_match_per_diag (matches.rs:147-148): diagonal -> start.i of the left-most kept match, default MAX. One entry per
+// diagonal the transform filter lets through (2 ns + 2 (p + 2) + 1 of them), of which a pair touches a few hundred: the array is
+// NOT initialised. A bitmap (one bit per segment of 32 entries, 64 bytes at n = 100 k) says which segments hold values; the first
+// store into a segment fills it with MAX (one coalesced store), loads from an unmarked segment answer MAX without looking.
+struct NmpdView {
+    I* vb;           // biased: vb[d] for dmin <= d <= dmax
+    uint32_t* segs;  // bit s: entries [32 s, 32 s + 32) (relative to dmin) are initialised
     I dmin, dmax;
-    __device__ __forceinline__ I get(I d) const { return (d < dmin || d > dmax) ? INT32_MAX : vb[d]; }
-};
-
-#ifndef APA_PRUNE_WIN  // 1: stage the plane windows of a local-pruning check in shared memory (measured slower: the
-#define APA_PRUNE_WIN 0  // direct loads hit L1, 83 % hit rate in the build kernel, and the staging adds two warp syncs per hit)
-#endif
-#if APA_PRUNE_WIN
-// Windows of the packed planes staged in shared memory for one local-pruning check: the check only ever looks at
-// a[ei, end_i) (<= 13 seeds = 156 bases) and b[ej, ej + 156 + 14), so one coalesced load per sequence replaces the two
-// dependent global loads every diagonal extension would otherwise issue (the build kernel is latency-bound).
-struct PruneWin {
-    uint2 a[8];   // plane words (ei >> 5) + 0..7 of a
-    uint2 b[10];  // plane words (ej >> 5) + 0..8 of b
-};
-static_assert(sizeof(PruneWin) <= sizeof(((WarpSmem*)0)->dt_i), "PruneWin lives in the DT-front area of WarpSmem");
-__device__ __forceinline__ uint2 extract32_win(const uint2* w, int hw0, I pos) {
-    const int hw = (pos >> 5) - hw0, sh = pos & 31;
-    const uint2 lo = w[hw], hi = w[hw + 1];
-    return make_uint2(__funnelshift_r(lo.x, hi.x, sh), __funnelshift_r(lo.y, hi.y, sh));
-}
-// extend_right (prepruning.rs:25-32) on the staged windows.
-__device__ __forceinline__ void extend_right_win(const PruneWin& w, int ahw0, int bhw0, I m, I& i, I j, I end_i) {
-    for (;;) {
-        int len = min(32, min(end_i - i, m - j));
-        if (len <= 0) return;
-        uint2 A = extract32_win(w.a, ahw0, i), B = extract32_win(w.b, bhw0, j);
-        uint32_t mm = (A.x ^ B.x) | (A.y ^ B.y);
-        if (len < 32) mm |= 0xffffffffu << len;
-        int run = mm ? __ffs(mm) - 1 : 32;
-        i += run;
-        j += run;
-        if (run < 32) return;
+    __device__ __forceinline__ I get(I d) const {
+        if (d < dmin || d > dmax) return INT32_MAX;
+        const uint32_t sgm = (uint32_t)(d - dmin) >> 5;
+        const uint32_t w = segs[sgm >> 5];  // both loads are issued together; the value is ignored for an unmarked segment
+        const I v = vb[d];
+        return ((w >> (sgm & 31)) & 1u) ? v : INT32_MAX;
     }
-}
-
-// preserve_for_local_pruning (prepruning.rs:95-203) for an exact match of seed `seed` starting at (seed * k, sj).
-// Warp-uniform result. Potentials in closed form: P(seed * k) = ns - seed.
-__device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin& win, const uint2* __restrict__ ap, const uint2* __restrict__ bp,
-                                               I seed, I sj, const NmpdView& nm) {
-    const int lane = threadIdx.x & 31;
-    const I si = seed * H.K();
-    const I ei = si + H.K(), ej = sj + H.K();
-    const Cost start_pot = H.nseeds - seed;
-    const I last = min(seed + H.P() - 1, H.nseeds - 1);
-    const I end_i = (last + 1) * H.K();
-    const int pd = last + 1 - seed;  // start_pot - P(end_i), <= GCSH_P
-    // lanes 0 .. 2*pd hold the front; lane d <-> diagonal e + (d - pd)
-    const I dd = ei - ej + (lane - pd);  // this lane's diagonal
-    // One round trip: the plane windows (lanes 0..7: a, 8..17: b) and this lane's next_match_per_diag entry.
-    const int ahw0 = ei >> 5, bhw0 = ej >> 5;
-    __syncwarp();  // the previous check's readers are done
-    if (lane < 8)
-        win.a[lane] = ap[min(ahw0 + lane, ((H.n + 63) >> 6) * 2 + 1)];
-    else if (lane < 18)
-        win.b[lane - 8] = bp[min(bhw0 + lane - 8, ((H.m + 63) >> 6) * 2 + 1)];
-    const I nmv = nm.get(dd);
-    __syncwarp();
-    // g = 0
-    I f0 = ei;
-    extend_right_win(win, ahw0, bhw0, H.m, f0, ej, end_i);
-    if (f0 >= end_i) return true;
-    if (__shfl_sync(FULL, nmv, pd) <= f0) return true;
-    I fr = (lane == pd) ? f0 : INT32_MIN;
-    int lo = pd, hi = pd + 1;  // d_range
-    for (Cost g = 1; g < pd; g++) {
-        // expand: next[d] = max(fr[d+1], fr[d] + 1, fr[d-1] + 1) over sources inside d_range
-        I up = __shfl_down_sync(FULL, fr, 1);  // fr[d+1]
-        I dn = __shfl_up_sync(FULL, fr, 1);    // fr[d-1]
-        I nx = INT32_MIN;
-        if (lane + 1 >= lo && lane + 1 < hi) nx = max(nx, up);
-        if (lane >= lo && lane < hi) nx = max(nx, fr + 1);
-        if (lane - 1 >= lo && lane - 1 < hi) nx = max(nx, dn + 1);
-        fr = nx;
-        lo -= 1;
-        hi += 1;
-        // check & shrink
-        bool in = lane >= lo && lane < hi;
-        bool dead = in && (g + H.pot(fr) >= start_pot);
-        unsigned alive = __ballot_sync(FULL, in && !dead);
-        if (alive == 0) return false;
-        lo = __ffs(alive) - 1;
-        hi = 32 - __clz(alive);
-        // extend
-        in = lane >= lo && lane < hi;
-        bool ok = false;
-        if (in) {
-            I j = fr - dd;
-            I old_i = fr;
-            extend_right_win(win, ahw0, bhw0, H.m, fr, j, end_i);
-            ok = (fr >= end_i) || (old_i <= nmv && nmv <= fr);
+    __device__ __forceinline__ void set(I d, I si) {  // warp-uniform arguments, called by the whole warp
+        if (d < dmin || d > dmax) return;
+        const int lane = threadIdx.x & 31;
+        const uint32_t sgm = (uint32_t)(d - dmin) >> 5;
+        const uint32_t w = segs[sgm >> 5];
+        if (!((w >> (sgm & 31)) & 1u)) {
+            const I e = dmin + (I)(sgm << 5) + lane;
+            if (e <= dmax) vb[e] = INT32_MAX;
+            __syncwarp();
+            if (lane == 0) segs[sgm >> 5] = w | (1u << (sgm & 31));
         }
-        if (__any_sync(FULL, ok)) return true;
+        if (lane == 0) vb[d] = si;
+        __syncwarp();
     }
-    return false;
-}
+};
 
-#else
 struct PruneWin {};
 // preserve_for_local_pruning (prepruning.rs:95-203) for an exact match of seed `seed` starting at (seed * k, sj).
-// Warp-uniform result. Potentials in closed form: P(seed * k) = ns - seed.
+// Warp-uniform result. Lanes 0 .. 2 pd hold the DT front, lane <-> diagonal (ei - ej) + (lane - pd): a lane's diagonal never
+// changes, so its next_match_per_diag entry is loaded once, before the loop. Potentials in closed form: P(i) = ns - ceil(i / k)
+// for i <= ns k, so "g + P(fr) >= P(start)" (prepruning.rs:158-168) is the single compare fr <= (seed + g) k.
 __device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin&, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I seed,
                                                I sj, const NmpdView& nm) {
     const int lane = threadIdx.x & 31;
-    const I si = seed * H.K();
-    const I ei = si + H.K(), ej = sj + H.K();
-    const Cost start_pot = H.nseeds - seed;
+    const int GK = H.K();
+    const I si = seed * GK;
+    const I ei = si + GK, ej = sj + GK;
     const I last = min(seed + H.P() - 1, H.nseeds - 1);
-    const I end_i = (last + 1) * H.K();
+    const I end_i = (last + 1) * GK;
     const int pd = last + 1 - seed;  // start_pot - P(end_i), <= GCSH_P
+    const I dd = ei - ej + (lane - pd);  // this lane's diagonal
+    const I nmv = (lane <= 2 * pd) ? nm.get(dd) : INT32_MAX;
     // g = 0
     I f0 = ei;
     extend_right_packed(ap, bp, H.m, f0, ej, end_i);
     if (f0 >= end_i) return true;
-    if (nm.get(ei - ej) <= f0) return true;
-    // lanes 0 .. 2*pd hold the front; lane d <-> diagonal e + (d - pd)
+    if (__shfl_sync(FULL, nmv, pd) <= f0) return true;
     I fr = (lane == pd) ? f0 : INT32_MIN;
     int lo = pd, hi = pd + 1;  // d_range
-    const I dd = ei - ej + (lane - pd);  // this lane's diagonal
-    for (Cost g = 1; g < pd; g++) {
-        // expand: next[d] = max(fr[d+1], fr[d] + 1, fr[d-1] + 1) over sources inside d_range
-        I up = __shfl_down_sync(FULL, fr, 1);  // fr[d+1]
-        I dn = __shfl_up_sync(FULL, fr, 1);    // fr[d-1]
-        I nx = INT32_MIN;
-        if (lane + 1 >= lo && lane + 1 < hi) nx = max(nx, up);
-        if (lane >= lo && lane < hi) nx = max(nx, fr + 1);
-        if (lane - 1 >= lo && lane - 1 < hi) nx = max(nx, dn + 1);
-        fr = nx;
+    I dead_below = si + GK;    // (seed + g) k at g = 1
+    for (Cost g = 1; g < pd; g++, dead_below += GK) {
+        // expand: next[d] = max(fr[d+1], fr[d] + 1, fr[d-1] + 1) over sources inside d_range (lanes outside hold MIN)
+        const I up = __shfl_down_sync(FULL, fr, 1);  // fr[d+1]
+        const I dn = __shfl_up_sync(FULL, fr, 1);    // fr[d-1]
+        const I here = (lane >= lo && lane < hi) ? fr + 1 : INT32_MIN;
+        const I from_up = (lane + 1 >= lo && lane + 1 < hi) ? up : INT32_MIN;
+        const I from_dn = (lane - 1 >= lo && lane - 1 < hi) ? dn + 1 : INT32_MIN;
+        fr = max(here, max(from_up, from_dn));
         lo -= 1;
         hi += 1;
-        // check & shrink
+        // check & shrink (from both ends only, like the reference)
         bool in = lane >= lo && lane < hi;
-        bool dead = in && (g + H.pot(fr) >= start_pot);
-        unsigned alive = __ballot_sync(FULL, in && !dead);
+        const unsigned alive = __ballot_sync(FULL, in && fr > dead_below);
         if (alive == 0) return false;
         lo = __ffs(alive) - 1;
         hi = 32 - __clz(alive);
@@ -394,18 +385,14 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin&, const 
         in = lane >= lo && lane < hi;
         bool ok = false;
         if (in) {
-            I j = fr - dd;
-            I old_i = fr;
-            extend_right_packed(ap, bp, H.m, fr, j, end_i);
-            I nmv = nm.get(dd);
+            const I old_i = fr;
+            extend_right_packed(ap, bp, H.m, fr, fr - dd, end_i);
             ok = (fr >= end_i) || (old_i <= nmv && nmv <= fr);
         }
         if (__any_sync(FULL, ok)) return true;
     }
     return false;
 }
-
-#endif
 
 constexpr uint32_t KMER_MUL = 0x9E3779B1u;
 constexpr uint32_t STAGE_MULTI = 0x40000000u;  // staged hit whose k-mer occurs in several seeds of a
@@ -454,15 +441,21 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     uint32_t off_act = arena_alloc(cx, (uint32_t)mcap);
     const uint32_t live_end = cx.v_top;
     // ---- dead after the precomputation
+    // Open-addressing table of the seeds: load factor 0.31 .. 0.63 (16 384 slots = 128 KB at n = 100 k). k-mer presence filter in
+    // front of it: a blocked Bloom filter, two bits per key inside one 32-bit word, 4 bits of filter per table slot (8 KB at
+    // n = 100 k: the filters of all resident warps, ~45 MB, stay in the 126 MB L2; about 5 % of unrelated windows pass).
     int log_t = 5;
-    while ((1 << log_t) < 2 * ns) log_t++;
+    while ((5ll << log_t) < 8ll * ns) log_t++;  // 2^log_t >= 1.6 ns
     const uint32_t tsize = 1u << log_t;
-    const int log_bm = log_t + 2;  // k-mer presence filter: 4 bits per table slot = 8..16 bits per seed
-    const uint32_t bm_words = 1u << (log_bm - 5);
+    const int log_bw = log_t + 2 - 5;  // filter words
+    const uint32_t bm_words = 1u << log_bw;
     uint32_t off_tab = arena_alloc(cx, tsize * 8u);
     uint32_t off_bm = arena_alloc(cx, bm_words * 4u);
     const I dmin = (n - m) - ns - (GP + 2), dmax = (n - m) + ns + (GP + 2);
-    uint32_t off_nm = arena_alloc(cx, (uint32_t)(dmax - dmin + 1) * 4u);
+    const uint32_t nm_entries = (uint32_t)(dmax - dmin + 1);
+    const uint32_t nm_segw = (nm_entries + 1023u) >> 10;  // bitmap words: one bit per 32 entries
+    uint32_t off_nm = arena_alloc(cx, ((nm_entries + 31u) & ~31u) * 4u);
+    uint32_t off_nmseg = arena_alloc(cx, nm_segw * 4u);
     uint32_t off_arr = arena_alloc(cx, (uint32_t)mcap * 16u);
     uint32_t off_stage = arena_alloc(cx, 32u * 32u * 8u);
     if (cx.status != ST_PENDING) return false;
@@ -475,7 +468,8 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     uint2* tab = pin_ptr((uint2*)(cx.arena + off_tab));
     uint32_t* bm = pin_ptr((uint32_t*)(cx.arena + off_bm));
     I* nm_v = (I*)(cx.arena + off_nm);
-    NmpdView nm{pin_ptr(nm_v - dmin), dmin, dmax};
+    uint32_t* nm_seg = (uint32_t*)(cx.arena + off_nmseg);
+    NmpdView nm{pin_ptr(nm_v - dmin), pin_ptr(nm_seg), dmin, dmax};
     int4* arr = pin_ptr((int4*)(cx.arena + off_arr));        // kept matches in arrival order: (seed, j, rank within seed, -)
     uint2* stage = pin_ptr((uint2*)(cx.arena + off_stage));  // per lane: up to 32 staged hits (j, first seed | STAGE_MULTI)
     const uint2* ap = pin_ptr(cx.aprof);
@@ -483,28 +477,44 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
 
     for (uint32_t t = lane; t < tsize; t += 32) tab[t] = make_uint2(0u, HT_EMPTY);
     for (uint32_t t = lane; t < bm_words; t += 32) bm[t] = 0u;
-    for (I t = lane; t <= dmax - dmin; t += 32) nm_v[t] = INT32_MAX;
+    for (uint32_t t = lane; t < nm_segw; t += 32) nm_seg[t] = 0u;
     for (I t = lane; t < ns + 2; t += 32) cnt[t] = 0u;
     __syncwarp();
 
     // ---- hash the seeds of a (hash_to_smallvec, exact.rs:48-55). Key: bit t = rank bit0 of char t, bit k+t = rank bit1.
     const uint32_t kmask = (1u << GK) - 1u;
-    for (I s0 = 0; s0 < ns; s0 += 32) {
-        I s = s0 + lane;
-        if (s < ns) {
-            const uint2 w = extract32(ap, s * GK);  // planes are stored negated
-            const uint32_t key = (~w.x & kmask) | ((~w.y & kmask) << GK);
-            const uint32_t hsh = key * KMER_MUL;
-            const uint32_t bit = hsh >> (32 - log_bm);
-            atomicOr(&bm[bit >> 5], 1u << (bit & 31));
-            uint32_t slot = hsh >> (32 - log_t);
-            unsigned long long want = ((unsigned long long)(uint32_t)s << 32) | key;  // uint2{key, seed}
-            for (;;) {
-                unsigned long long old = atomicCAS((unsigned long long*)&tab[slot], ((unsigned long long)HT_EMPTY << 32), want);
-                if (old == ((unsigned long long)HT_EMPTY << 32)) break;
-                slot = (slot + 1) & (tsize - 1);
+    // filter word and the two bits of a key: word from the top bits of the hash, bit positions from the next 5 + 5
+    auto bloom_word = [&](uint32_t hsh) -> uint32_t { return hsh >> (32 - log_bw); };
+    auto bloom_bits = [&](uint32_t hsh) -> uint32_t { return (1u << ((hsh >> 5) & 31u)) | (1u << (hsh & 31u)); };
+    // Four seeds per lane and round: the four compare-and-swaps are in flight together (each is a DRAM-latency round trip into a
+    // table no cache holds); a lane whose slot was taken walks on alone. Only this warp touches the table, the CAS settles
+    // collisions between its own lanes.
+    const unsigned long long EMPTY64 = (unsigned long long)HT_EMPTY << 32;
+    for (I s0 = 0; s0 < ns; s0 += 128) {
+        unsigned long long want[4], got[4];
+        uint32_t slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const I sd = s0 + 32 * u + lane;
+            got[u] = EMPTY64;
+            if (sd < ns) {
+                const uint2 w = extract32(ap, sd * GK);  // planes are stored negated
+                const uint32_t key = (~w.x & kmask) | ((~w.y & kmask) << GK);
+                const uint32_t hsh = key * KMER_MUL;
+                atomicOr(&bm[bloom_word(hsh)], bloom_bits(hsh));
+                slot[u] = hsh >> (32 - log_t);
+                want[u] = ((unsigned long long)(uint32_t)sd << 32) | key;  // uint2{key, seed}
             }
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (s0 + 32 * u + lane < ns) got[u] = atomicCAS((unsigned long long*)&tab[slot[u]], EMPTY64, want[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            while (got[u] != EMPTY64) {
+                slot[u] = (slot[u] + 1) & (tsize - 1);
+                got[u] = atomicCAS((unsigned long long*)&tab[slot[u]], EMPTY64, want[u]);
+            }
     }
     __syncwarp();
 
@@ -543,9 +553,9 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
 #pragma unroll 8
             for (int sft = 0; sft < 32; sft++) {
                 const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GK);
-                const uint32_t bit = (key * KMER_MUL) >> (32 - log_bm);
-                const uint32_t word = bm[bit >> 5];
-                surv |= ((word >> (bit & 31)) & 1u) << sft;
+                const uint32_t hsh = key * KMER_MUL;
+                const uint32_t bits = bloom_bits(hsh);
+                surv |= ((bm[bloom_word(hsh)] & bits) == bits ? 1u : 0u) << sft;
             }
             const int nwin = jhi - wbase + 1;  // windows above jhi belong to the previous lane
             if (nwin < 32) surv &= (1u << nwin) - 1u;
@@ -598,9 +608,8 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
                             cx.status = ST_OVERFLOW;
                             return false;
                         }
+                        nm.set(si - jj, si);
                         if (lane == 0) {
-                            const I d = si - jj;
-                            if (d >= dmin && d <= dmax) nm.vb[d] = si;
                             const uint32_t rank = cnt[seed];
                             cnt[seed] = rank + 1u;
                             arr[M] = make_int4(seed, jj, (int)rank, 0);
