@@ -20,6 +20,23 @@
 #pragma once
 #include "apa_align.cuh"
 
+// Build-kernel variants (A/B measurements on B200, profiles/README.md round 2); 1 = the shipped formulation.
+#ifndef APA_LAYER_CACHE
+#define APA_LAYER_CACHE 1  // contour build with the top 32 layers in registers
+#endif
+#ifndef APA_DT_V2
+#define APA_DT_V2 1        // local pruning: per-lane nm entry loaded once, single-compare potential test
+#endif
+#ifndef APA_NM_LAZY
+#define APA_NM_LAZY 0      // next_match_per_diag uninitialised behind a segment bitmap (less DRAM traffic, measured 2.2 ms slower: off)
+#endif
+#ifndef APA_BLOOM8
+#define APA_BLOOM8 0       // blocked Bloom filter (2 bits per key in one word) + seed table at load factor <= 0.63 (measured 1.7 ms slower: off)
+#endif
+#ifndef APA_CAS4
+#define APA_CAS4 0         // four seed insertions in flight per lane (measured 2.4 ms slower under the 56-register cap: off)
+#endif
+
 namespace APA_NS {
 
 constexpr int GCSH_K = 12;        // seed length (params.rs:103)
@@ -158,6 +175,7 @@ struct GcshH {
         APA_TOC(t_h, t0);
         return r;
     }
+#if APA_LAYER_CACHE
     // HintContours::new over the active arrows (hint_contours.rs:213-255) == state after update_layers.
     // Matches are taken from the last to the first; each asks score(end) and joins layer score + 1. Along a chain almost every
     // query is answered by one of the top few layers, so the warp keeps the TOP 32 LAYERS IN REGISTERS (lane l: the two inline
@@ -257,6 +275,48 @@ struct GcshH {
         dens = min(256, (int)(((long long)nlayers << 8) / max(1, nseeds)));
         dirty = false;
     }
+#else
+    // HintContours::new over the active arrows (hint_contours.rs:213-255) == state after update_layers.
+    __device__ void build_layers() {
+        const int lane = threadIdx.x & 31;
+        for (int w = lane; w <= nlayers + 1 && w <= M + 1; w += 32) {
+            layer_head[w] = -1;
+            layer_pts[w] = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);
+        }
+        __syncwarp();
+        nlayers = 0;
+        hint[3] = 0;
+        for (int idx = M - 1; idx >= 0; idx--) {
+            if (!active[idx]) continue;
+            I ex = px[idx] + 1, ey = py[idx] + 1;  // transform(end): P(end.i) = P(start.i) - 1
+            if (!(ex <= ttx && ey <= tty)) continue;
+            int v = score(ex, ey, 3) + 1;
+            if (lane == 0) {
+                int4 p = (v > nlayers) ? make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN) : layer_pts[v];
+                if (v > nlayers) layer_head[v] = -1;
+                if (p.x == INT32_MIN) {
+                    p.x = px[idx];
+                    p.y = py[idx];
+                    layer_pts[v] = p;
+                } else if (p.z == INT32_MIN) {
+                    p.z = px[idx];
+                    p.w = py[idx];
+                    layer_pts[v] = p;
+                } else {
+                    next[idx] = layer_head[v];
+                    layer_head[v] = idx;
+                }
+            }
+            if (v > nlayers) nlayers = v;
+            hint[3] = v;
+            __syncwarp();
+        }
+        hint[0] = hint[1] = hint[2] = hint[3];
+        hq[0] = hq[1] = hq[2] = hq[3] = 0;
+        dens = min(256, (int)(((long long)nlayers << 8) / max(1, nseeds)));
+        dirty = false;
+    }
+#endif
     __device__ void update_contours() {
         if (dirty) build_layers();
     }
@@ -318,6 +378,13 @@ struct NmpdView {
     I* vb;           // biased: vb[d] for dmin <= d <= dmax
     uint32_t* segs;  // bit s: entries [32 s, 32 s + 32) (relative to dmin) are initialised
     I dmin, dmax;
+#if !APA_NM_LAZY
+    __device__ __forceinline__ I get(I d) const { return (d < dmin || d > dmax) ? INT32_MAX : vb[d]; }
+    __device__ __forceinline__ void set(I d, I si) {
+        if (d >= dmin && d <= dmax && (threadIdx.x & 31) == 0) vb[d] = si;
+        __syncwarp();
+    }
+#else
     __device__ __forceinline__ I get(I d) const {
         if (d < dmin || d > dmax) return INT32_MAX;
         const uint32_t sgm = (uint32_t)(d - dmin) >> 5;
@@ -339,9 +406,11 @@ struct NmpdView {
         if (lane == 0) vb[d] = si;
         __syncwarp();
     }
+#endif
 };
 
 struct PruneWin {};
+#if APA_DT_V2
 // preserve_for_local_pruning (prepruning.rs:95-203) for an exact match of seed `seed` starting at (seed * k, sj).
 // Warp-uniform result. Lanes 0 .. 2 pd hold the DT front, lane <-> diagonal (ei - ej) + (lane - pd): a lane's diagonal never
 // changes, so its next_match_per_diag entry is loaded once, before the loop. Potentials in closed form: P(i) = ns - ceil(i / k)
@@ -394,6 +463,62 @@ __device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin&, const 
     return false;
 }
 
+#else
+// preserve_for_local_pruning (prepruning.rs:95-203) for an exact match of seed `seed` starting at (seed * k, sj).
+// Warp-uniform result. Potentials in closed form: P(seed * k) = ns - seed.
+__device__ bool dev_preserve_for_local_pruning(const GcshH& H, PruneWin&, const uint2* __restrict__ ap, const uint2* __restrict__ bp, I seed,
+                                               I sj, const NmpdView& nm) {
+    const int lane = threadIdx.x & 31;
+    const I si = seed * H.K();
+    const I ei = si + H.K(), ej = sj + H.K();
+    const Cost start_pot = H.nseeds - seed;
+    const I last = min(seed + H.P() - 1, H.nseeds - 1);
+    const I end_i = (last + 1) * H.K();
+    const int pd = last + 1 - seed;  // start_pot - P(end_i), <= GCSH_P
+    // g = 0
+    I f0 = ei;
+    extend_right_packed(ap, bp, H.m, f0, ej, end_i);
+    if (f0 >= end_i) return true;
+    if (nm.get(ei - ej) <= f0) return true;
+    // lanes 0 .. 2*pd hold the front; lane d <-> diagonal e + (d - pd)
+    I fr = (lane == pd) ? f0 : INT32_MIN;
+    int lo = pd, hi = pd + 1;  // d_range
+    const I dd = ei - ej + (lane - pd);  // this lane's diagonal
+    for (Cost g = 1; g < pd; g++) {
+        // expand: next[d] = max(fr[d+1], fr[d] + 1, fr[d-1] + 1) over sources inside d_range
+        I up = __shfl_down_sync(FULL, fr, 1);  // fr[d+1]
+        I dn = __shfl_up_sync(FULL, fr, 1);    // fr[d-1]
+        I nx = INT32_MIN;
+        if (lane + 1 >= lo && lane + 1 < hi) nx = max(nx, up);
+        if (lane >= lo && lane < hi) nx = max(nx, fr + 1);
+        if (lane - 1 >= lo && lane - 1 < hi) nx = max(nx, dn + 1);
+        fr = nx;
+        lo -= 1;
+        hi += 1;
+        // check & shrink
+        bool in = lane >= lo && lane < hi;
+        bool dead = in && (g + H.pot(fr) >= start_pot);
+        unsigned alive = __ballot_sync(FULL, in && !dead);
+        if (alive == 0) return false;
+        lo = __ffs(alive) - 1;
+        hi = 32 - __clz(alive);
+        // extend
+        in = lane >= lo && lane < hi;
+        bool ok = false;
+        if (in) {
+            I j = fr - dd;
+            I old_i = fr;
+            extend_right_packed(ap, bp, H.m, fr, j, end_i);
+            I nmv = nm.get(dd);
+            ok = (fr >= end_i) || (old_i <= nmv && nmv <= fr);
+        }
+        if (__any_sync(FULL, ok)) return true;
+    }
+    return false;
+}
+
+#endif
+
 constexpr uint32_t KMER_MUL = 0x9E3779B1u;
 constexpr uint32_t STAGE_MULTI = 0x40000000u;  // staged hit whose k-mer occurs in several seeds of a
 
@@ -445,9 +570,15 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     // front of it: a blocked Bloom filter, two bits per key inside one 32-bit word, 4 bits of filter per table slot (8 KB at
     // n = 100 k: the filters of all resident warps, ~45 MB, stay in the 126 MB L2; about 5 % of unrelated windows pass).
     int log_t = 5;
+#if APA_BLOOM8
     while ((5ll << log_t) < 8ll * ns) log_t++;  // 2^log_t >= 1.6 ns
     const uint32_t tsize = 1u << log_t;
     const int log_bw = log_t + 2 - 5;  // filter words
+#else  // round-1 sizes: table >= 2 ns slots, one-bit filter of 4 bits per slot
+    while ((1 << log_t) < 2 * ns) log_t++;
+    const uint32_t tsize = 1u << log_t;
+    const int log_bw = log_t + 2 - 5;
+#endif
     const uint32_t bm_words = 1u << log_bw;
     uint32_t off_tab = arena_alloc(cx, tsize * 8u);
     uint32_t off_bm = arena_alloc(cx, bm_words * 4u);
@@ -477,7 +608,11 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
 
     for (uint32_t t = lane; t < tsize; t += 32) tab[t] = make_uint2(0u, HT_EMPTY);
     for (uint32_t t = lane; t < bm_words; t += 32) bm[t] = 0u;
+#if APA_NM_LAZY
     for (uint32_t t = lane; t < nm_segw; t += 32) nm_seg[t] = 0u;
+#else
+    for (uint32_t t = lane; t < nm_entries; t += 32) nm_v[t] = INT32_MAX;
+#endif
     for (I t = lane; t < ns + 2; t += 32) cnt[t] = 0u;
     __syncwarp();
 
@@ -485,10 +620,15 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     const uint32_t kmask = (1u << GK) - 1u;
     // filter word and the two bits of a key: word from the top bits of the hash, bit positions from the next 5 + 5
     auto bloom_word = [&](uint32_t hsh) -> uint32_t { return hsh >> (32 - log_bw); };
+#if APA_BLOOM8
     auto bloom_bits = [&](uint32_t hsh) -> uint32_t { return (1u << ((hsh >> 5) & 31u)) | (1u << (hsh & 31u)); };
+#else
+    auto bloom_bits = [&](uint32_t hsh) -> uint32_t { return 1u << ((hsh >> (32 - log_bw - 5)) & 31u); };
+#endif
     // Four seeds per lane and round: the four compare-and-swaps are in flight together (each is a DRAM-latency round trip into a
     // table no cache holds); a lane whose slot was taken walks on alone. Only this warp touches the table, the CAS settles
     // collisions between its own lanes.
+#if APA_CAS4
     const unsigned long long EMPTY64 = (unsigned long long)HT_EMPTY << 32;
     for (I s0 = 0; s0 < ns; s0 += 128) {
         unsigned long long want[4], got[4];
@@ -518,6 +658,27 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     }
     __syncwarp();
 
+#else
+    const unsigned long long EMPTY64 = (unsigned long long)HT_EMPTY << 32;
+    for (I s0 = 0; s0 < ns; s0 += 32) {
+        I sd = s0 + lane;
+        if (sd < ns) {
+            const uint2 w = extract32(ap, sd * GK);  // planes are stored negated
+            const uint32_t key = (~w.x & kmask) | ((~w.y & kmask) << GK);
+            const uint32_t hsh = key * KMER_MUL;
+            atomicOr(&bm[bloom_word(hsh)], bloom_bits(hsh));
+            uint32_t slot = hsh >> (32 - log_t);
+            unsigned long long want = ((unsigned long long)(uint32_t)sd << 32) | key;  // uint2{key, seed}
+            for (;;) {
+                unsigned long long old = atomicCAS((unsigned long long*)&tab[slot], EMPTY64, want);
+                if (old == EMPTY64) break;
+                slot = (slot + 1) & (tsize - 1);
+            }
+        }
+    }
+    __syncwarp();
+
+#endif
     // smallest seed > `after` whose k-mer is `key` (INT32_MAX if none); n_out = number of seeds with that k-mer
     auto probe = [&](uint32_t key, I after, int& n_out) -> I {
         uint32_t slot = (key * KMER_MUL) >> (32 - log_t);

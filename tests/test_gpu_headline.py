@@ -88,6 +88,7 @@ def test_config3_waves_gpu(apa, oracle, engine, monkeypatch):
     batch.free_pool(pool)
     batch.free()
     monkeypatch.setenv("APA_BUDGET_BYTES", str(5 << 30))
+    monkeypatch.setenv("APA_RAW", "1")  # (an engine with >= 12 host threads to itself would host-pack a batch this large)
     a_pin, b_pin = apa.pinned_copy(a_all), apa.pinned_copy(b_all)
     costs, pool, off, ln, st = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, 1, True)
     assert st["waves"] >= 2 and st["pass_warps_per_pair"] == 8 and st["upload_mode"] == 3, (st, st0)
