@@ -30,11 +30,20 @@
 #ifndef APA_NM_LAZY
 #define APA_NM_LAZY 0      // next_match_per_diag uninitialised behind a segment bitmap (less DRAM traffic, measured 2.2 ms slower: off)
 #endif
-#ifndef APA_BLOOM8
-#define APA_BLOOM8 0       // blocked Bloom filter (2 bits per key in one word) + seed table at load factor <= 0.63 (measured 1.7 ms slower: off)
+#ifndef APA_TAB_DENSE
+#define APA_TAB_DENSE 0    // seed table at load factor <= 0.63 instead of <= 0.5
+#endif
+#ifndef APA_BLOOM2
+#define APA_BLOOM2 1       // blocked Bloom filter: two bits per key inside one 32-bit word, instead of one bit
+#endif
+#ifndef APA_BLOOM_LOG
+#define APA_BLOOM_LOG 2    // filter bits per table slot = 2^APA_BLOOM_LOG
 #endif
 #ifndef APA_CAS4
-#define APA_CAS4 0         // four seed insertions in flight per lane (measured 2.4 ms slower under the 56-register cap: off)
+#define APA_CAS4 0         // four seed insertions in flight per lane
+#endif
+#ifndef APA_PROBE2
+#define APA_PROBE2 1       // two table probes in flight per lane in the window scan
 #endif
 
 namespace APA_NS {
@@ -570,15 +579,13 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     // front of it: a blocked Bloom filter, two bits per key inside one 32-bit word, 4 bits of filter per table slot (8 KB at
     // n = 100 k: the filters of all resident warps, ~45 MB, stay in the 126 MB L2; about 5 % of unrelated windows pass).
     int log_t = 5;
-#if APA_BLOOM8
-    while ((5ll << log_t) < 8ll * ns) log_t++;  // 2^log_t >= 1.6 ns
-    const uint32_t tsize = 1u << log_t;
-    const int log_bw = log_t + 2 - 5;  // filter words
-#else  // round-1 sizes: table >= 2 ns slots, one-bit filter of 4 bits per slot
-    while ((1 << log_t) < 2 * ns) log_t++;
-    const uint32_t tsize = 1u << log_t;
-    const int log_bw = log_t + 2 - 5;
+#if APA_TAB_DENSE
+    while ((5ll << log_t) < 8ll * ns) log_t++;  // 2^log_t >= 1.6 ns: load factor 0.31 .. 0.63
+#else
+    while ((1 << log_t) < 2 * ns) log_t++;      // 2^log_t >= 2 ns: load factor 0.25 .. 0.5
 #endif
+    const uint32_t tsize = 1u << log_t;
+    const int log_bw = log_t + APA_BLOOM_LOG - 5;  // filter words: 2^APA_BLOOM_LOG bits per table slot
     const uint32_t bm_words = 1u << log_bw;
     uint32_t off_tab = arena_alloc(cx, tsize * 8u);
     uint32_t off_bm = arena_alloc(cx, bm_words * 4u);
@@ -620,7 +627,7 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     const uint32_t kmask = (1u << GK) - 1u;
     // filter word and the two bits of a key: word from the top bits of the hash, bit positions from the next 5 + 5
     auto bloom_word = [&](uint32_t hsh) -> uint32_t { return hsh >> (32 - log_bw); };
-#if APA_BLOOM8
+#if APA_BLOOM2
     auto bloom_bits = [&](uint32_t hsh) -> uint32_t { return (1u << ((hsh >> 5) & 31u)) | (1u << (hsh & 31u)); };
 #else
     auto bloom_bits = [&](uint32_t hsh) -> uint32_t { return 1u << ((hsh >> (32 - log_bw - 5)) & 31u); };
@@ -629,31 +636,36 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     // table no cache holds); a lane whose slot was taken walks on alone. Only this warp touches the table, the CAS settles
     // collisions between its own lanes.
 #if APA_CAS4
+    // Four seeds per lane and round, their compare-and-swaps in flight together (each is a DRAM-latency round trip into a table
+    // no cache holds). Only the four results stay in registers: a lane whose slot was taken recomputes the key and walks on
+    // alone. Only this warp touches the table; the CAS settles collisions between its own lanes.
     const unsigned long long EMPTY64 = (unsigned long long)HT_EMPTY << 32;
+    auto seed_key = [&](I sd) -> uint32_t {
+        const uint2 w = extract32(ap, sd * GK);  // planes are stored negated
+        return (~w.x & kmask) | ((~w.y & kmask) << GK);
+    };
     for (I s0 = 0; s0 < ns; s0 += 128) {
-        unsigned long long want[4], got[4];
-        uint32_t slot[4];
+        unsigned long long got[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const I sd = s0 + 32 * u + lane;
             got[u] = EMPTY64;
             if (sd < ns) {
-                const uint2 w = extract32(ap, sd * GK);  // planes are stored negated
-                const uint32_t key = (~w.x & kmask) | ((~w.y & kmask) << GK);
+                const uint32_t key = seed_key(sd);
                 const uint32_t hsh = key * KMER_MUL;
                 atomicOr(&bm[bloom_word(hsh)], bloom_bits(hsh));
-                slot[u] = hsh >> (32 - log_t);
-                want[u] = ((unsigned long long)(uint32_t)sd << 32) | key;  // uint2{key, seed}
+                got[u] = atomicCAS((unsigned long long*)&tab[hsh >> (32 - log_t)], EMPTY64, ((unsigned long long)(uint32_t)sd << 32) | key);
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
-            if (s0 + 32 * u + lane < ns) got[u] = atomicCAS((unsigned long long*)&tab[slot[u]], EMPTY64, want[u]);
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            while (got[u] != EMPTY64) {
-                slot[u] = (slot[u] + 1) & (tsize - 1);
-                got[u] = atomicCAS((unsigned long long*)&tab[slot[u]], EMPTY64, want[u]);
+            if (got[u] != EMPTY64) {
+                const I sd = s0 + 32 * u + lane;
+                const uint32_t key = seed_key(sd);
+                uint32_t slot = (key * KMER_MUL) >> (32 - log_t);
+                do {
+                    slot = (slot + 1) & (tsize - 1);
+                } while (atomicCAS((unsigned long long*)&tab[slot], EMPTY64, ((unsigned long long)(uint32_t)sd << 32) | key) != EMPTY64);
             }
     }
     __syncwarp();
@@ -679,22 +691,25 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
     __syncwarp();
 
 #endif
-    // smallest seed > `after` whose k-mer is `key` (INT32_MAX if none); n_out = number of seeds with that k-mer
-    auto probe = [&](uint32_t key, I after, int& n_out) -> I {
-        uint32_t slot = (key * KMER_MUL) >> (32 - log_t);
+    // smallest seed > `after` whose k-mer is `key` (INT32_MAX if none); n_out = number of seeds with that k-mer.
+    // probe_from continues from a slot whose entry `e` the caller has already loaded.
+    auto probe_from = [&](uint32_t key, uint32_t slot, uint2 e, I after, int& n_out) -> I {
         I best = INT32_MAX;
         int c = 0;
-        for (;;) {
-            const uint2 e = tab[slot];
-            if (e.y == HT_EMPTY) break;
+        while (e.y != HT_EMPTY) {
             if (e.x == key) {
                 c++;
                 if ((I)e.y > after && (I)e.y < best) best = (I)e.y;
             }
             slot = (slot + 1) & (tsize - 1);
+            e = tab[slot];
         }
         n_out = c;
         return best;
+    };
+    auto probe = [&](uint32_t key, I after, int& n_out) -> I {
+        const uint32_t slot = (key * KMER_MUL) >> (32 - log_t);
+        return probe_from(key, slot, tab[slot], after, n_out);
     };
 
     // ---- all windows of b, right to left (b_qgrams_rev, qgrams.rs:81-97), 1024 per round: lane l owns the 32 windows
@@ -723,25 +738,52 @@ __device__ bool gcsh_build(PairCtx& cx, WarpSmem& sm, GcshH& H) {
         }
         int nh = 0;
         uint2 st0 = make_uint2(0u, 0u), st1 = make_uint2(0u, 0u);
+        auto stage_hit = [&](int sft, I seed0, int c) {  // the first two hits of a lane stay in registers (1.7 hits per lane and round on average)
+            const uint2 rec = make_uint2((uint32_t)(wbase + sft), (uint32_t)seed0 | (c > 1 ? STAGE_MULTI : 0u));
+            if (nh == 0)
+                st0 = rec;
+            else if (nh == 1)
+                st1 = rec;
+            else
+                stage[lane * 32 + nh] = rec;
+            nh++;
+        };
+        auto window_key = [&](int sft) -> uint32_t {
+            return (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GK);
+        };
+#if APA_PROBE2
+        // two survivors per lane and iteration: both first table entries are loaded before either chain is followed
+        while (__any_sync(FULL, surv != 0u)) {
+            if (surv) {
+                const int sa = 31 - __clz(surv);  // highest j first
+                surv &= ~(1u << sa);
+                const int sb = surv ? 31 - __clz(surv) : -1;
+                if (sb >= 0) surv &= ~(1u << sb);
+                const uint32_t ka = window_key(sa), kb = window_key(sb < 0 ? 0 : sb);
+                const uint32_t slot_a = (ka * KMER_MUL) >> (32 - log_t), slot_b = (kb * KMER_MUL) >> (32 - log_t);
+                const uint2 ea = tab[slot_a];
+                uint2 eb = make_uint2(0u, HT_EMPTY);
+                if (sb >= 0) eb = tab[slot_b];
+                int c;
+                I seed0 = probe_from(ka, slot_a, ea, -1, c);
+                if (c > 0) stage_hit(sa, seed0, c);
+                if (sb >= 0) {
+                    seed0 = probe_from(kb, slot_b, eb, -1, c);
+                    if (c > 0) stage_hit(sb, seed0, c);
+                }
+            }
+        }
+#else
         while (__any_sync(FULL, surv != 0u)) {
             if (surv) {
                 const int sft = 31 - __clz(surv);  // highest j first
                 surv &= ~(1u << sft);
-                const uint32_t key = (__funnelshift_r(w0x, w1x, sft) & kmask) | ((__funnelshift_r(w0y, w1y, sft) & kmask) << GK);
                 int c;
-                const I seed0 = probe(key, -1, c);
-                if (c > 0) {  // the first two hits of a lane stay in registers (1.7 hits per lane and round on average)
-                    const uint2 rec = make_uint2((uint32_t)(wbase + sft), (uint32_t)seed0 | (c > 1 ? STAGE_MULTI : 0u));
-                    if (nh == 0)
-                        st0 = rec;
-                    else if (nh == 1)
-                        st1 = rec;
-                    else
-                        stage[lane * 32 + nh] = rec;
-                    nh++;
-                }
+                const I seed0 = probe(window_key(sft), -1, c);
+                if (c > 0) stage_hit(sft, seed0, c);
             }
         }
+#endif
         __syncwarp();
         unsigned has = __ballot_sync(FULL, nh > 0);
         while (has) {
