@@ -132,6 +132,7 @@ def load_library():
     L.apa_debug_band_log_params.argtypes = [C.c_void_p, pp, C.c_int, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64]
     L.apa_batch_download_pair_stats.argtypes = [C.c_void_p, C.c_void_p, vp]
     L.apa_search.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, C.c_float, vp]
+    L.apa_search_trace.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, C.c_float, C.c_uint64, C.c_char_p, C.c_uint64, vp]
     L.apa_free.argtypes = [C.c_void_p]
     L.apa_pinned_alloc.restype = C.c_void_p
     L.apa_pinned_alloc.argtypes = [C.c_uint64]
@@ -316,6 +317,17 @@ class Engine:
         tb = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(1, np.uint8)
         _check(self._L.apa_search(self._h, pb.ctypes.data, len(pattern), tb.ctypes.data, len(text), float(unmatched_cost), out.ctypes.data))
         return out
+
+    def search_trace(self, pattern: bytes, text: bytes, unmatched_cost: float, idx: int):
+        """SearchResult::trace(idx) (pa-bitpacking/src/search.rs:135-230): (cigar text, (start_i, start_j), (end_i, end_j), cost)."""
+        cap = 2 * (len(pattern) + len(text)) + 16
+        buf = C.create_string_buffer(cap)
+        pos = np.zeros(5, dtype=np.int32)
+        pb = np.frombuffer(pattern, dtype=np.uint8) if pattern else np.zeros(1, np.uint8)
+        tb = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(1, np.uint8)
+        _check(self._L.apa_search_trace(self._h, pb.ctypes.data, len(pattern), tb.ctypes.data, len(text), float(unmatched_cost), int(idx),
+                                        buf, cap, pos.ctypes.data))
+        return buf.value.decode(), (int(pos[0]), int(pos[1])), (int(pos[2]), int(pos[3])), int(pos[4])
 
     def block_compute(self, a: bytes, b: bytes, v=None):
         """pa_bitpacking::simd::compute on the GPU with +1 top deltas. Returns (bottom_sum, h_out, v_out)."""
@@ -514,6 +526,11 @@ class AstarPa2:
 def search(pattern: bytes, text: bytes, unmatched_cost: float = 0.0, device=0):
     """pa_bitpacking::search (pa-bitpacking/src/search.rs:46): see Engine.search."""
     return _engine(device).search(pattern, text, unmatched_cost)
+
+
+def search_trace(pattern: bytes, text: bytes, unmatched_cost: float, idx: int, device=0):
+    """SearchResult::trace (pa-bitpacking/src/search.rs:135-230): see Engine.search_trace."""
+    return _engine(device).search_trace(pattern, text, unmatched_cost, idx)
 
 
 def astarpa2_simple(a: bytes, b: bytes):

@@ -439,18 +439,40 @@ __global__ void __launch_bounds__(256) apa_pack_kernel(BatchDev bd, int* bad) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// pa_bitpacking::search on one warp (pa-bitpacking/src/search.rs:46-118, simd/scatter_profile.rs): the text runs along the columns
-// in slabs of 256, the (short) pattern along the rows. Top deltas are 0 (a match may start anywhere in the text), so every
-// chunk takes its incoming deltas from sm.hrow (zeroed for the first chunk) and leaves its bottom deltas there; what the last
-// chunk leaves is the bottom row of the slab. The equality words are the pattern's match masks (wildcards N * Y R and the
-// all-matching padding rows, profile.rs:39-66), which the per-lane table of the block DP takes as they are.
-__global__ void apa_search_kernel(const uint8_t* __restrict__ text, int nt, const uint4* __restrict__ pmask, int nhw, uint2* v,
-                                  int8_t* __restrict__ hdelta) {
-    __shared__ WarpSmem sm;
+// pa_bitpacking::search (pa-bitpacking/src/search.rs:46-118, simd/scatter_profile.rs): the text runs along the columns in slabs
+// of 256, the (short) pattern along the rows. Top deltas are 0 (a match may start anywhere in the text), so every chunk takes
+// its incoming deltas from sm.hrow (zeroed for the first chunk) and leaves its bottom deltas there; what the last chunk leaves
+// is the bottom row of the slab. The equality words are the pattern's match masks (wildcards N * Y R and the all-matching
+// padding rows, profile.rs:39-66), which the per-lane table of the block DP takes as they are.
+//
+// One warp per TEXT SEGMENT. A cell (i, j) costs at most j (start in the top row above it), so an optimal path to it spans at
+// most 2 j <= 2 rows columns: a warp that starts `warm` = 2 * rows columns before its segment from all-(+1) vertical deltas
+// (an upper bound of the true column) has exact values from its segment's first column on. The same argument is what
+// SearchResult::trace uses for its window (search.rs:141-186). Segment s covers columns [s * seg_len, (s + 1) * seg_len);
+// hdelta is written for those columns only; the warp of the last segment leaves the final column in vfin.
+// FILL: single segment starting at column 0 of `text` with v0 as given; every column's V is stored: fillvals[(c + 1) * nhw + hw]
+// (column 0 of fillvals = v0), for SearchResult::trace.
+template <bool FILL>
+__global__ void __launch_bounds__(128) apa_search_kernel(const uint8_t* __restrict__ text, int nt, const uint4* __restrict__ pmask, int nhw,
+                                                       const uint2* __restrict__ v0, uint2* __restrict__ vwork, uint2* __restrict__ vfin,
+                                                       int8_t* __restrict__ hdelta, int seg_len, int warm, uint2* __restrict__ fillvals) {
+    __shared__ WarpSmem smem[4];
+    WarpSmem& sm = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const long long seg_start = (long long)seg * seg_len;
+    if (seg_start >= nt && !(seg == 0)) return;
+    const int seg_end = (int)min((long long)nt, seg_start + seg_len);
+    const int c_begin = (int)max(0ll, seg_start - warm);
+    uint2* v = vwork + (size_t)seg * nhw;
+    for (int hw = lane; hw < nhw; hw += 32) {
+        v[hw] = c_begin == 0 ? v0[hw] : make_uint2(~0u, 0u);
+        if (FILL) fillvals[hw] = v0[hw];
+    }
+    __syncwarp();
     const int nchunks = (nhw + 31) / 32;
-    for (int c0 = 0; c0 < nt; c0 += BLOCK_W) {
-        const int nc = min(BLOCK_W, nt - c0);
+    for (int c0 = c_begin; c0 < seg_end; c0 += BLOCK_W) {
+        const int nc = min(BLOCK_W, seg_end - c0);
         for (int k = lane; k < BLOCK_W + 4; k += 32) sm.achar[k] = k < nc ? (uint8_t)((text[c0 + k] >> 1) & 3u) : (uint8_t)0;  // A0 C1 T2 G3
         for (int k = lane; k < BLOCK_W; k += 32) sm.hrow[k] = 0;
         __syncwarp();
@@ -469,16 +491,100 @@ __global__ void apa_search_kernel(const uint8_t* __restrict__ text, int nt, cons
             sm.etab[1 * 32 + lane] = pm.y;
             sm.etab[2 * 32 + lane] = pm.z;
             sm.etab[3 * 32 + lane] = pm.w;
-            dp_chunk<false, false, true, true>(sm, nc, nrow, 0u, 0u, vp, vm, nullptr, nhw);
+            dp_chunk<FILL, false, true, true>(sm, nc, nrow, 0u, 0u, vp, vm, FILL ? fillvals + (size_t)(c0 + 1) * nhw + hw : nullptr, nhw);
             __syncwarp();
             if (is_row) v[hw] = make_uint2(vp, vm);
         }
         for (int k = lane; k < nc; k += 32) {
-            const uint32_t x = sm.hrow[k];
-            hdelta[c0 + k] = (int8_t)((int)(x & 1u) - (int)(x >> 1));
+            if (hdelta && c0 + k >= seg_start) {
+                const uint32_t x = sm.hrow[k];
+                hdelta[c0 + k] = (int8_t)((int)(x & 1u) - (int)(x >> 1));
+            }
         }
         __syncwarp();
     }
+    if (seg_end == nt)
+        for (int hw = lane; hw < nhw; hw += 32) vfin[hw] = v[hw];
+}
+
+// SearchResult::trace walk (search.rs:188-229) on the filled window: columns [start, end] of the text = fill columns 0 .. end - start,
+// from (end, pj) with cost `target` back to column `start` or row 0. One warp: V::value_to is a strided popcount sum + shuffle
+// reduction, everything else is warp-uniform. out: [0] status (0 walked, 1 the window's cost at the end position exceeds the
+// target: re-fill a wider window, 2 cheaper than the target / stuck: a reference panic), [1] number of elements, [2] start i,
+// [3] start j, [4] cost found at the end position. elems: CIGAR elements newest first, (op << 30) | count.
+__global__ void apa_search_trace_kernel(const uint8_t* __restrict__ text, const uint4* __restrict__ pmask, int nhw, const uint2* __restrict__ fillvals,
+                                        int start, int end, int pj, int target, uint32_t* __restrict__ elems, uint32_t elem_cap, int* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    auto value_to = [&](int i, int j) -> int {  // encoding.rs:54-63 on 32-row half-words
+        const uint2* col = fillvals + (size_t)(i - start) * nhw;
+        int sum = 0;
+        for (int hw = lane; 32 * hw < j; hw += 32) {
+            const uint2 pm = col[hw];
+            const int bits = j - 32 * hw;
+            const uint32_t mask = bits >= 32 ? ~0u : ((1u << bits) - 1u);
+            sum += __popc(pm.x & mask) - __popc(pm.y & mask);
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
+        return sum;
+    };
+    auto is_match = [&](int i, int j) -> bool {  // ScatterProfile::is_match, profile.rs:72-74
+        const uint4 pm = pmask[j >> 5];
+        const uint32_t c = (text[i] >> 1) & 3u;
+        const uint32_t w = c == 0 ? pm.x : (c == 1 ? pm.y : (c == 2 ? pm.z : pm.w));
+        return (w >> (j & 31)) & 1u;
+    };
+    const int cost_end = value_to(end, pj);
+    if (lane == 0) out[4] = cost_end;
+    if (cost_end != target) {
+        if (lane == 0) out[0] = cost_end > target ? 1 : 2, out[1] = 0;
+        return;
+    }
+    int pi = end, g = target;
+    uint32_t n_el = 0, pend_op = 0, pend_cnt = 0;
+    int status = 0;
+    auto push = [&](uint32_t op, uint32_t cnt) {
+        if (pend_cnt && pend_op == op) {
+            pend_cnt += cnt;
+            return;
+        }
+        if (pend_cnt) {
+            if (n_el < elem_cap && lane == 0) elems[n_el] = cig_pack(pend_op, pend_cnt);
+            n_el++;
+        }
+        pend_op = op, pend_cnt = cnt;
+    };
+    while (pi > start && pj > 0) {
+        uint32_t cnt = 0;
+        while (pi > start && pj > 0 && is_match(pi - 1, pj - 1)) cnt++, pi--, pj--;
+        if (cnt > 0) {
+            push(OP_MATCH, cnt);
+            continue;
+        }
+        if (value_to(pi - 1, pj) == g - 1) {
+            g--, pi--;
+            push(OP_DEL, 1);
+            continue;
+        }
+        if (value_to(pi, pj - 1) == g - 1) {
+            g--, pj--;
+            push(OP_INS, 1);
+            continue;
+        }
+        if (value_to(pi - 1, pj - 1) == g - 1) {
+            g--, pi--, pj--;
+            push(OP_SUB, 1);
+            continue;
+        }
+        status = 2;  // "Bad trace! Got stuck"
+        break;
+    }
+    if (pend_cnt) {
+        if (n_el < elem_cap && lane == 0) elems[n_el] = cig_pack(pend_op, pend_cnt);
+        n_el++;
+    }
+    if (status == 0 && !(pi == 0 || g == 0)) status = 2;  // assert!(pos.0 == 0 || g == 0), search.rs:226
+    if (lane == 0) out[0] = status, out[1] = (int)n_el, out[2] = pi, out[3] = pj;
 }
 
 struct apa_engine;
@@ -996,7 +1102,16 @@ static int upload_planes(apa_engine* e, apa_batch* b, bool streaming) {
         }
         p0 = p1;
     }
-    pk.start(pack_threads());
+    // small batches (the single-pair drop-in calls) are packed by the calling thread: spawning workers costs more than the work
+    const bool inline_pack = b->total_a + b->total_b < (2u << 20);
+    if (inline_pack) {
+        for (const PackTask& tk : pk.tasks) {
+            if (apa_pack_planes_host(tk.seq, tk.len, tk.hw_begin, tk.hw_end, tk.out)) pk.bad.store(1);
+            pk.remaining[tk.chunk].fetch_sub(1, std::memory_order_release);
+        }
+    } else {
+        pk.start(pack_threads());
+    }
     cudaStream_t cs = streaming ? e->copy_stream : e->stream;
     p0 = 0;
     for (size_t c = 0; c < n_chunks; c++) {
@@ -1554,15 +1669,20 @@ static int64_t band_log_impl(apa_engine* e, int preset, const apa_params* params
 }
 
 // ------------------------------------------------------------------------------------------------ pa_bitpacking::search
-extern "C" int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t np, const uint8_t* text, uint64_t nt, float unmatched_cost,
-                          int32_t* out) {
-    if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
+// Host side of search / trace: the pattern's match masks, the start column v0 (search.rs:58-66) and input validation.
+struct SearchSetup {
+    uint64_t nwords = 0, nhw = 0, padding = 0;
+    std::vector<uint32_t> pmask, v0;  // per half-word: 4 mask words (A C T G) / (p, m)
+};
+static int search_setup(const uint8_t* pattern, uint64_t np, const uint8_t* text, uint64_t nt, float unmatched_cost, SearchSetup& S) {
     if (!(unmatched_cost >= 0.0f && unmatched_cost <= 1.0f)) return set_err(APA_ERR_BAD_INPUT, "unmatched_cost must be in [0, 1]");
     if (nt >= (1ull << 31) - 1024 || np >= (1ull << 24)) return set_err(APA_ERR_TOO_LARGE, "search: text < 2^31, pattern < 2^24");
-    CUDA_TRY(cudaSetDevice(e->device));
     // ScatterProfile::build (profile.rs:28-66): per 32 rows of the pattern, the rows matching A / C / T / G.
-    const uint64_t nwords = (np + 63) / 64, nhw = nwords * 2;
-    std::vector<uint32_t> pmask(nhw * 4, 0u), v0(nhw * 2, 0u);
+    S.nwords = (np + 63) / 64;
+    S.nhw = S.nwords * 2;
+    S.padding = S.nwords * 64 - np;
+    S.pmask.assign(S.nhw * 4, 0u);
+    S.v0.assign(S.nhw * 2, 0u);
     for (uint64_t j = 0; j < np; j++) {
         uint32_t m4 = 0;  // bit i: matches base i (A0 C1 T2 G3)
         switch (pattern[j]) {
@@ -1576,10 +1696,10 @@ extern "C" int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t np, co
             default: return set_err(APA_ERR_BAD_INPUT, "search: unknown pattern base (ACGT, N, *, Y, R)");
         }
         for (int i = 0; i < 4; i++)
-            if (m4 >> i & 1) pmask[(j / 32) * 4 + i] |= 1u << (j % 32);
+            if (m4 >> i & 1) S.pmask[(j / 32) * 4 + i] |= 1u << (j % 32);
     }
-    for (uint64_t j = np; j < nwords * 64; j++)
-        for (int i = 0; i < 4; i++) pmask[(j / 32) * 4 + i] |= 1u << (j % 32);  // padding rows match everything
+    for (uint64_t j = np; j < S.nwords * 64; j++)
+        for (int i = 0; i < 4; i++) S.pmask[(j / 32) * 4 + i] |= 1u << (j % 32);  // padding rows match everything
     for (uint64_t i = 0; i < nt; i++) {
         const uint8_t c = text[i] & 0xDF;  // acgtACGT only (profile.rs:31-38)
         if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return set_err(APA_ERR_BAD_INPUT, "search: text byte outside acgtACGT");
@@ -1588,39 +1708,31 @@ extern "C" int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t np, co
         for (uint64_t i = 0;; i++) {
             const uint64_t idx = (uint64_t)std::ceil((float)i / unmatched_cost);
             if (idx >= np) break;
-            v0[(idx / 32) * 2] |= 1u << (idx % 32);
+            S.v0[(idx / 32) * 2] |= 1u << (idx % 32);
         }
     }
-    std::vector<uint32_t> vfin(v0);
-    std::vector<int8_t> hd(std::max<uint64_t>(nt, 1), 0);
-    if (nt > 0 && nhw > 0) {
-        uint8_t* d_text = nullptr;
-        uint4* d_pmask = nullptr;
-        uint2* d_v = nullptr;
-        int8_t* d_h = nullptr;
-        cudaStream_t st = e->stream;
-        cudaError_t ce = cudaMalloc(&d_text, nt);
-        if (ce == cudaSuccess) ce = cudaMalloc(&d_pmask, nhw * 16);
-        if (ce == cudaSuccess) ce = cudaMalloc(&d_v, nhw * 8);
-        if (ce == cudaSuccess) ce = cudaMalloc(&d_h, nt);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_text, text, nt, cudaMemcpyHostToDevice, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_pmask, pmask.data(), nhw * 16, cudaMemcpyHostToDevice, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_v, v0.data(), nhw * 8, cudaMemcpyHostToDevice, st);
-        if (ce == cudaSuccess) {
-            apa_search_kernel<<<1, 32, 0, st>>>(d_text, (int)nt, d_pmask, (int)nhw, d_v, d_h);
-            ce = cudaGetLastError();
-        }
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(vfin.data(), d_v, nhw * 8, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(hd.data(), d_h, nt, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-        cudaFree(d_text);
-        cudaFree(d_pmask);
-        cudaFree(d_v);
-        cudaFree(d_h);
-        if (ce != cudaSuccess) return set_err(APA_ERR_CUDA, std::string("apa_search: ") + cudaGetErrorString(ce));
+    return APA_OK;
+}
+// Device buffers of a search call come from the engine's cache (no cudaMalloc / cudaFree per call once it is warm).
+struct SearchBufs {
+    apa_engine* e;
+    std::vector<void*> ptrs;
+    ~SearchBufs() {
+        for (void* p : ptrs) eng_release(e, p);
     }
-    // Output assembly (search.rs:72-104): bottom row, then up the right column; the first `padding` values are skipped
-    // because the pattern was rounded up to a multiple of 64 rows.
+    template <class T>
+    cudaError_t get(T** out, size_t bytes) {
+        void* p = nullptr;
+        cudaError_t ce = eng_alloc(e, &p, std::max<size_t>(bytes, 16));
+        if (ce == cudaSuccess) ptrs.push_back(p);
+        *out = (T*)p;
+        return ce;
+    }
+};
+// The `out` vector of pa_bitpacking::search from the final column and the bottom deltas (search.rs:72-104): bottom row, then up
+// the right column; the first `padding` values are skipped because the pattern was rounded up to a multiple of 64 rows.
+static int search_assemble(const SearchSetup& S, uint64_t np, uint64_t nt, const std::vector<uint32_t>& vfin, const std::vector<int8_t>& hd,
+                           int32_t* out) {
     auto word = [&](const std::vector<uint32_t>& vv, uint64_t w, int pm) -> uint64_t {
         return (uint64_t)vv[(2 * w) * 2 + pm] | ((uint64_t)vv[(2 * w + 1) * 2 + pm] << 32);
     };
@@ -1631,31 +1743,163 @@ extern "C" int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t np, co
         const uint64_t mask = ~((1ull << (64 - j)) - 1ull);  // V::value_of_suffix, encoding.rs:33-38 (0 < j <= 64)
         return __builtin_popcountll(word(vv, w, 0) & mask) - __builtin_popcountll(word(vv, w, 1) & mask);
     };
-    const uint64_t padding = nwords * 64 - np;
     int b = 0;
-    for (uint64_t w = 0; w < nwords; w++) b += value(v0, w);
+    for (uint64_t w = 0; w < S.nwords; w++) b += value(S.v0, w);
     uint64_t n_out = 0, skipped = 0;
     out[n_out++] = b;
     for (uint64_t i = 0; i < nt; i++) {
         b += hd[i];
-        if (skipped < padding)
+        if (skipped < S.padding)
             skipped++;
         else
             out[n_out++] = b;
     }
-    for (uint64_t w = nwords; w-- > 0;) {
+    for (uint64_t w = S.nwords; w-- > 0;) {
         for (int j = 1; j <= 64; j++) {
-            const int val = b - suffix(vfin, w, j) + suffix(v0, w, j);
-            if (skipped < padding)
+            const int val = b - suffix(vfin, w, j) + suffix(S.v0, w, j);
+            if (skipped < S.padding)
                 skipped++;
             else
                 out[n_out++] = val;
         }
         b -= value(vfin, w);
-        b += value(v0, w);
+        b += value(S.v0, w);
     }
     if (n_out != np + nt + 1) return set_err(APA_ERR_INTERNAL, "search: output length");
     return APA_OK;
+}
+
+extern "C" int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t np, const uint8_t* text, uint64_t nt, float unmatched_cost,
+                          int32_t* out) {
+    if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
+    SearchSetup S;
+    int rc = search_setup(pattern, np, text, nt, unmatched_cost, S);
+    if (rc != APA_OK) return rc;
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<uint32_t> vfin(S.v0);
+    std::vector<int8_t> hd(std::max<uint64_t>(nt, 1), 0);
+    if (nt > 0 && S.nhw > 0) {
+        // text segments, one warp each: long enough that the 2 * rows warm-up columns stay a small share, short enough to fill the GPU
+        const int nhw = (int)S.nhw;
+        const int warm = 2 * 32 * nhw;
+        const long long min_seg = std::max<long long>(1024, 8ll * warm);
+        const long long want_segs = (long long)e->sm_count * 16;
+        long long seg_len = std::max<long long>(min_seg, ((long long)nt + want_segs - 1) / want_segs);
+        seg_len = (seg_len + BLOCK_W - 1) / BLOCK_W * BLOCK_W;
+        const long long n_segs = ((long long)nt + seg_len - 1) / seg_len;
+        SearchBufs B{e, {}};
+        uint8_t* d_text;
+        uint4* d_pmask;
+        uint2 *d_v0, *d_vwork, *d_vfin;
+        int8_t* d_h;
+        cudaStream_t st = e->stream;
+        CUDA_TRY(B.get(&d_text, nt));
+        CUDA_TRY(B.get(&d_pmask, S.nhw * 16));
+        CUDA_TRY(B.get(&d_v0, S.nhw * 8));
+        CUDA_TRY(B.get(&d_vwork, (size_t)n_segs * S.nhw * 8));
+        CUDA_TRY(B.get(&d_vfin, S.nhw * 8));
+        CUDA_TRY(B.get(&d_h, nt));
+        CUDA_TRY(cudaMemcpyAsync(d_text, text, nt, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_pmask, S.pmask.data(), S.nhw * 16, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_v0, S.v0.data(), S.nhw * 8, cudaMemcpyHostToDevice, st));
+        apa_search_kernel<false><<<(unsigned)((n_segs + 3) / 4), 128, 0, st>>>(d_text, (int)nt, d_pmask, nhw, d_v0, d_vwork, d_vfin, d_h, (int)seg_len,
+                                                                               warm, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(vfin.data(), d_vfin, S.nhw * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hd.data(), d_h, nt, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return search_assemble(S, np, nt, vfin, hd, out);
+}
+
+// SearchResult::trace(idx) (search.rs:135-230): the alignment that ends at out[idx]. The window of the text that can hold it
+// (2 |pattern| columns, doubled while the cost found at the end position exceeds the target) is re-filled on the GPU with every
+// column kept (apa_search_kernel<true>), and walked back on the GPU (apa_search_trace_kernel); the host formats the CIGAR text.
+// cigar_out: NUL-terminated text (pa_types::Cigar::to_string: count omitted when 1), at most cigar_cap bytes; pos_out: start.i,
+// start.j (where the walk stopped: poss[0] of the reference), end.i, end.j, cost.
+extern "C" int apa_search_trace(apa_engine* e, const uint8_t* pattern, uint64_t np, const uint8_t* text, uint64_t nt, float unmatched_cost,
+                                uint64_t idx, char* cigar_out, uint64_t cigar_cap, int32_t* pos_out) {
+    if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
+    if (idx > np + nt) return set_err(APA_ERR_BAD_INPUT, "search trace: idx out of range");  // assert, search.rs:122
+    std::vector<int32_t> out(np + nt + 1);
+    int rc = apa_search(e, pattern, np, text, nt, unmatched_cost, out.data());
+    if (rc != APA_OK) return rc;
+    SearchSetup S;
+    rc = search_setup(pattern, np, text, nt, unmatched_cost, S);
+    if (rc != APA_OK) return rc;
+    // idx_to_pos (search.rs:121-132) and the target cost (search.rs:137-140: the right column's values carry the unmatched rows)
+    const int64_t pi = idx <= nt ? (int64_t)idx : (int64_t)nt, pj = idx <= nt ? (int64_t)np : (int64_t)(np - (idx - nt));
+    int target = out[idx];
+    if ((uint64_t)pi == nt) {  // V::value_from(&v0, pos.1): rows pj .. of the start column
+        for (uint64_t j = (uint64_t)pj; j < S.nwords * 64; j++)
+            target -= (int)((S.v0[(j / 32) * 2] >> (j % 32)) & 1u) - (int)((S.v0[(j / 32) * 2 + 1] >> (j % 32)) & 1u);
+    }
+    pos_out[2] = (int32_t)pi, pos_out[3] = (int32_t)pj, pos_out[4] = target;
+    if (S.nhw == 0) {  // empty pattern: nothing to walk
+        if (cigar_cap < 1) return set_err(APA_ERR_TOO_LARGE, "search trace: cigar buffer too small");
+        cigar_out[0] = 0;
+        pos_out[0] = (int32_t)pi, pos_out[1] = 0;
+        return APA_OK;
+    }
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const int nhw = (int)S.nhw;
+    const uint64_t end = (uint64_t)pi;
+    uint64_t width = 2 * np;
+    std::vector<uint32_t> ones(S.nhw * 2, 0u);
+    for (uint64_t h = 0; h < S.nhw; h++) ones[2 * h] = ~0u;
+    for (;;) {
+        const uint64_t start = end > width ? end - width : 0;
+        const uint64_t ncol = end - start;
+        if ((ncol + 1) * S.nhw * 8 > (8ull << 30)) return set_err(APA_ERR_TOO_LARGE, "search trace: window too large");
+        SearchBufs B{e, {}};
+        uint8_t* d_text;
+        uint4* d_pmask;
+        uint2 *d_v0, *d_vwork, *d_vfin, *d_fill;
+        uint32_t* d_elems;
+        int* d_out;
+        const uint32_t elem_cap = (uint32_t)std::min<uint64_t>(ncol + np + 16, 1u << 30);
+        CUDA_TRY(B.get(&d_text, nt + 1));
+        CUDA_TRY(B.get(&d_pmask, S.nhw * 16));
+        CUDA_TRY(B.get(&d_v0, S.nhw * 8));
+        CUDA_TRY(B.get(&d_vwork, S.nhw * 8 * 4));
+        CUDA_TRY(B.get(&d_vfin, S.nhw * 8));
+        CUDA_TRY(B.get(&d_fill, (ncol + 1) * S.nhw * 8));
+        CUDA_TRY(B.get(&d_elems, (size_t)elem_cap * 4));
+        CUDA_TRY(B.get(&d_out, 8 * 4));
+        if (nt) CUDA_TRY(cudaMemcpyAsync(d_text, text, nt, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_pmask, S.pmask.data(), S.nhw * 16, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_v0, start == 0 ? S.v0.data() : ones.data(), S.nhw * 8, cudaMemcpyHostToDevice, st));
+        const int seg_len = (int)((std::max<uint64_t>(ncol, 1) + BLOCK_W - 1) / BLOCK_W * BLOCK_W);
+        apa_search_kernel<true><<<1, 128, 0, st>>>(d_text + start, (int)ncol, d_pmask, nhw, d_v0, d_vwork, d_vfin, nullptr, seg_len, 0, d_fill);
+        CUDA_TRY(cudaGetLastError());
+        apa_search_trace_kernel<<<1, 32, 0, st>>>(d_text, d_pmask, nhw, d_fill, (int)start, (int)end, (int)pj, target, d_elems, elem_cap, d_out);
+        CUDA_TRY(cudaGetLastError());
+        int h_out[8] = {0};
+        CUDA_TRY(cudaMemcpyAsync(h_out, d_out, 5 * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_out[0] == 1) {  // cost > target_cost: the window cut the path off
+            if (start == 0) return set_err(APA_ERR_INTERNAL, "search trace: target cost not reached with the whole text");
+            width *= 2;
+            continue;
+        }
+        if (h_out[0] != 0) return set_err(APA_ERR_INTERNAL, "search trace: a reference panic path was reached (search.rs:176-226)");
+        const uint32_t n_el = (uint32_t)h_out[1];
+        if (n_el > elem_cap) return set_err(APA_ERR_INTERNAL, "search trace: element buffer");
+        std::vector<uint32_t> el(n_el);
+        if (n_el) CUDA_TRY(cudaMemcpy(el.data(), d_elems, (size_t)n_el * 4, cudaMemcpyDeviceToHost));
+        std::string txt;
+        static const char opc[4] = {'=', 'X', 'D', 'I'};
+        for (uint32_t k = n_el; k-- > 0;) {  // cigar.reverse()
+            const uint32_t cnt = el[k] & 0x3fffffffu;
+            if (cnt != 1) txt += std::to_string(cnt);
+            txt += opc[el[k] >> 30];
+        }
+        if (txt.size() + 1 > cigar_cap) return set_err(APA_ERR_TOO_LARGE, "search trace: cigar buffer too small");
+        memcpy(cigar_out, txt.c_str(), txt.size() + 1);
+        pos_out[0] = h_out[2], pos_out[1] = h_out[3];
+        return APA_OK;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ INT32 issue-rate probe

@@ -170,9 +170,19 @@ int64_t apa_debug_band_log(apa_engine* e, int preset, int trace, const uint8_t* 
  * wildcards N, *, Y = C|T, R = A|G) in a long text (acgtACGT). A match may start anywhere in the text and anywhere in the
  * pattern; unmatched pattern rows cost `unmatched_cost` each (0..1, realised as one +1 row every 1/unmatched_cost rows).
  * out receives pattern_len + text_len + 1 costs: along the bottom row, then up the right column (search.rs:36-45). The DP
- * runs on the GPU (the block-DP step with zero top deltas and the pattern's match masks as equality words). */
+ * runs on the GPU (the block-DP step with zero top deltas and the pattern's match masks as equality words), one warp per text
+ * segment: a cell of row j costs at most j, so a warp that starts 2 * rows columns ahead of its segment from an upper bound of
+ * the column is exact inside the segment. */
 int apa_search(apa_engine* e, const uint8_t* pattern, uint64_t pattern_len, const uint8_t* text, uint64_t text_len,
                float unmatched_cost, int32_t* out);
+
+/* SearchResult::trace(idx) of pa_bitpacking::search (pa-bitpacking/src/search.rs:135-230): the alignment of the pattern that ends at
+ * out[idx] (idx <= text_len: bottom row, column idx; beyond: up the right column). The text window that can hold it is re-filled
+ * and walked back on the GPU. cigar_out receives the NUL-terminated CIGAR text ('=' match, 'X' substitution, 'D' a text base
+ * skipped, 'I' a pattern base skipped; count omitted when 1), pos_out[5] = {start.i, start.j, end.i, end.j, cost} with i the
+ * text column and j the pattern row; start is where the walk stopped (the window's left edge or the top row). */
+int apa_search_trace(apa_engine* e, const uint8_t* pattern, uint64_t pattern_len, const uint8_t* text, uint64_t text_len,
+                     float unmatched_cost, uint64_t idx, char* cigar_out, uint64_t cigar_cap, int32_t* pos_out);
 
 /* INT32 issue-rate probe (bench.py's roofline denominator for the block DP, SURVEY 8d "must be measured"): lane-operations
  * per second with every SM full of warps running dependent chains of out[0] LOP3, out[1] SHF, out[2] IADD3 (three-input add),

@@ -296,6 +296,21 @@ int64_t oracle_bp_compute(const uint8_t* a, size_t na, const uint8_t* b, size_t 
     return s;
 }
 
+// SearchResult::trace(idx) (search.rs:135-230): CIGAR text into cigar_out (NUL-terminated, cap bytes), pos_out = {start.i, start.j,
+// end.i, end.j, cost}. Returns strlen, -1 on a reference panic, -2 when cap is too small.
+int64_t oracle_search_trace(const uint8_t* pattern, size_t np, const uint8_t* text, size_t nt, float unmatched_cost, uint64_t idx,
+                            char* cigar_out, size_t cap, int32_t* pos_out) {
+    try {
+        SearchTrace tr = search_trace(pattern, np, text, nt, unmatched_cost, (size_t)idx);
+        if (tr.cigar.size() + 1 > cap) return -2;
+        memcpy(cigar_out, tr.cigar.c_str(), tr.cigar.size() + 1);
+        pos_out[0] = tr.start.i, pos_out[1] = tr.start.j, pos_out[2] = tr.end.i, pos_out[3] = tr.end.j, pos_out[4] = tr.cost;
+        return (int64_t)tr.cigar.size();
+    } catch (const RefPanic&) {
+        return -1;
+    }
+}
+
 // The reference's micro-benchmark of the block kernel (pa-bitpacking/benches/nw/main.rs:139-159): `reps` evaluations of the
 // a[na] x b[mb] rectangle with all-(+1) input deltas, profile built once. Returns the last bottom-delta sum (keeps the loop live).
 int64_t oracle_bp_compute_bench(const uint8_t* a, size_t na, const uint8_t* b, size_t mb, int reps) {

@@ -120,4 +120,96 @@ inline std::vector<Cost> search(const uint8_t* pattern, size_t np, const uint8_t
     return out;
 }
 
+// SearchResult::trace (search.rs:135-230): the alignment ending at out[idx]. The text window [end - width, end) is re-filled with
+// every V column kept (width = 2 |pattern|, doubled until the cost at the end position equals the target: a window that starts
+// past column 0 starts from all +1 deltas, an upper bound), then walked back greedily: matches first, then Del (a text base),
+// Ins (a pattern base), Sub. Returns the CIGAR text; start receives the position the walk stopped at (poss[0] of the reference).
+struct SearchTrace {
+    std::string cigar;
+    Pos start, end;
+    Cost cost;
+};
+inline Cost v_value_to(const std::vector<V>& v, I j) {  // encoding.rs:54-63
+    Cost s = 0;
+    for (I w = 0; w < j / 64; w++) s += v[w].value();
+    if (j % 64 != 0) s += v[j / 64].value_of_prefix(j % 64);
+    return s;
+}
+inline Cost v_value_from(const std::vector<V>& v, I j) {  // encoding.rs:64-73
+    Cost s = 0;
+    if (j % 64 != 0) s += v[j / 64].value_of_suffix(64 - j % 64);
+    for (size_t w = (size_t)((j + 63) / 64); w < v.size(); w++) s += v[w].value();
+    return s;
+}
+inline SearchTrace search_trace(const uint8_t* pattern, size_t np, const uint8_t* text, size_t nt, float unmatched_cost, size_t idx) {
+    const std::vector<Cost> out = search(pattern, np, text, nt, unmatched_cost);
+    if (idx >= out.size()) throw RefPanic("trace: idx out of range");  // search.rs:122
+    std::vector<uint8_t> t;
+    std::vector<ScatterB> p;
+    scatter_build(text, nt, pattern, np, t, p);
+    std::vector<V> v0(p.size(), V::zero());
+    if (unmatched_cost > 0.0f) {
+        for (size_t i = 0;; i++) {
+            size_t k = (size_t)std::ceil((float)i / unmatched_cost);
+            if (k >= np) break;
+            v0[k / 64].p |= 1ull << (k % 64);
+        }
+    }
+    Pos pos = idx <= nt ? Pos{(I)idx, (I)np} : Pos{(I)nt, (I)(np - (idx - nt))};  // idx_to_pos, search.rs:121-132
+    Cost target = out[idx];
+    if ((size_t)pos.i == nt) target -= v_value_from(v0, pos.j);
+    size_t width = 2 * np;
+    const size_t end = (size_t)pos.i;
+    size_t start;
+    std::vector<std::vector<V>> fill;
+    for (;;) {
+        start = end > width ? end - width : 0;
+        std::vector<H> h(end - start + 1, H::zero());
+        std::vector<V> v = start == 0 ? v0 : std::vector<V>(v0.size(), V::one());
+        fill.assign(h.size(), {});
+        fill[0] = v;
+        for (size_t i = start; i < end; i++) {
+            for (size_t j = 0; j < p.size(); j++) scatter_compute_block(h[i - start + 1], v[j], t[i], p[j]);
+            fill[i - start + 1] = v;
+        }
+        const Cost cost = v_value_to(v, pos.j);
+        if (cost < target) throw RefPanic("trace: found a path cheaper than the target");  // assert, search.rs:176-179
+        if (cost == target) break;
+        if (start == 0) throw RefPanic("trace: target cost not reached with the whole text");
+        width *= 2;
+    }
+    auto cost_at = [&](I i, I j) { return v_value_to(fill[(size_t)i - start], j); };
+    auto is_match = [&](I i, I j) { return ((p[(size_t)j / 64].m[t[(size_t)i]] >> ((size_t)j % 64)) & 1ull) != 0; };  // profile.rs:72-74
+    Cigar cigar;
+    const Pos endpos = pos;
+    Cost g = target;
+    while (pos.i > (I)start && pos.j > 0) {
+        I cnt = 0;
+        while (pos.i > (I)start && pos.j > 0 && is_match(pos.i - 1, pos.j - 1)) cnt++, pos.i--, pos.j--;
+        if (cnt > 0) {
+            cigar.push_elem(CigarElem{OpMatch, cnt});
+            continue;
+        }
+        if (cost_at(pos.i - 1, pos.j) == g - 1) {
+            g--, pos.i--;
+            cigar.push_elem(CigarElem{OpDel, 1});
+            continue;
+        }
+        if (cost_at(pos.i, pos.j - 1) == g - 1) {
+            g--, pos.j--;
+            cigar.push_elem(CigarElem{OpIns, 1});
+            continue;
+        }
+        if (cost_at(pos.i - 1, pos.j - 1) == g - 1) {
+            g--, pos.i--, pos.j--;
+            cigar.push_elem(CigarElem{OpSub, 1});
+            continue;
+        }
+        throw RefPanic("Bad trace! Got stuck");
+    }
+    if (!(pos.i == 0 || g == 0)) throw RefPanic("trace: assert pos.0 == 0 || g == 0");  // search.rs:226
+    cigar.reverse();
+    return SearchTrace{cigar.to_string(), pos, endpos, target};
+}
+
 }  // namespace oracle

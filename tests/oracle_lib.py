@@ -59,6 +59,8 @@ def lib():
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_search.restype = C.c_int64
         L.oracle_search.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_float, C.c_void_p]
+        L.oracle_search_trace.restype = C.c_int64
+        L.oracle_search_trace.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_float, C.c_uint64, C.c_char_p, C.c_size_t, C.c_void_p]
         L.oracle_hardware_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -148,3 +150,14 @@ def search(pattern: bytes, text: bytes, unmatched_cost: float = 0.0):
     if w < 0:
         raise OraclePanic("panic in search")
     return out[:w].tolist()
+
+
+def search_trace(pattern: bytes, text: bytes, unmatched_cost: float, idx: int):
+    """SearchResult::trace(idx) (pa-bitpacking/src/search.rs:135-230): (cigar text, (start_i, start_j), (end_i, end_j), cost)."""
+    cap = 2 * (len(pattern) + len(text)) + 16
+    buf = C.create_string_buffer(cap)
+    pos = np.zeros(5, dtype=np.int32)
+    w = lib().oracle_search_trace(pattern, len(pattern), text, len(text), unmatched_cost, idx, buf, cap, pos.ctypes.data)
+    if w < 0:
+        raise OraclePanic("panic in search trace")
+    return buf.value.decode(), (int(pos[0]), int(pos[1])), (int(pos[2]), int(pos[3])), int(pos[4])

@@ -419,6 +419,48 @@ def test_search_gpu(apa, oracle):
     for bad in ((b"AX", b"ACGT", 0.0), (b"AC", b"ACGN", 0.0), (b"AC", b"ACGT", 2.0)):
         with pytest.raises(apa.AstarPaError):
             apa.search(*bad)
+    # many text segments (one warp each, 2 * rows warm-up columns): short and multi-chunk patterns on a long text
+    for n_p, n_t, u in [(33, 3000000, 0.0), (200, 2000000, 0.3), (1500, 1200000, 0.0)]:
+        p = bytes(rng.choice(b"ACGTACGTACGTNYR") for _ in range(n_p))
+        t = bytes(rng.choice(b"ACGT") for _ in range(n_t))
+        assert apa.search(p, t, u).tolist() == oracle.search(p, t, u), (n_p, n_t, u)
+
+
+def test_search_trace_gpu(apa, oracle):
+    # SearchResult::trace (pa-bitpacking/src/search.rs:135-230) on the GPU against the oracle's literal restatement: planted
+    # occurrences with errors, ends along the bottom row and up the right column, windows that have to be doubled, patterns whose
+    # length is and is not a multiple of 64, every unmatched_cost class. Where the reference would panic, the call fails.
+    import random
+    rng = random.Random(5)
+    assert oracle.search_trace(b"AC", b"CTTACTTA", 0.0, 5)[0] == "2="
+    checked = 0
+    for n_p, n_t in [(2, 8), (20, 300), (64, 1000), (65, 1000), (128, 5000), (200, 700), (1000, 9000), (2100, 20000)]:
+        for u in (0.0, 0.5, 1.0):
+            t = bytearray(rng.choice(b"ACGT") for _ in range(n_t))
+            p = bytearray(rng.choice(b"ACGT") for _ in range(n_p))
+            if n_t > 2 * n_p:  # plant the pattern with a few edits
+                at = rng.randrange(0, n_t - n_p)
+                t[at:at + n_p] = p
+                for _ in range(max(1, n_p // 25)):
+                    t[at + rng.randrange(n_p)] = rng.choice(b"ACGT")
+            if n_p >= 20:
+                p[3] = ord("N")
+            p, t = bytes(p), bytes(t)
+            out = oracle.search(p, t, u)
+            bottom = out[:n_t + 1]
+            idxs = {bottom.index(min(bottom[1:])) if n_t else 0, n_t, n_t // 2, n_t + n_p, n_t + n_p // 2, 1, rng.randrange(len(out))}
+            for idx in sorted(idxs):
+                try:
+                    want = oracle.search_trace(p, t, u, idx)
+                except oracle.OraclePanic:
+                    with pytest.raises(apa.AstarPaError):
+                        apa.search_trace(p, t, u, idx)
+                    continue
+                assert apa.search_trace(p, t, u, idx) == want, (n_p, n_t, u, idx)
+                checked += 1
+    assert checked > 100
+    with pytest.raises(apa.AstarPaError):
+        apa.search_trace(b"ACGT", b"ACGTACGT", 0.0, 100)
 
 
 @pytest.mark.parametrize("preset", GENERAL_PRESETS)

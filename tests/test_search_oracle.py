@@ -66,3 +66,35 @@ def test_search_panics_like_the_reference(oracle):
         oracle.search(b"AX", b"ACGT", 0.0)
     with pytest.raises(oracle.OraclePanic):
         oracle.search(b"AC", b"ACGT", 1.5)
+
+
+def test_search_trace_oracle_properties(oracle):
+    # SearchResult::trace (search.rs:135-230) restated: the doc-test's occurrence, and for random planted occurrences the CIGAR
+    # replayed over text[start.i:end.i] x pattern[start.j:end.j] costs exactly out[idx] (unmatched_cost = 0: free start in the top
+    # row and in the left column), uses every base of both slices, and '=' / 'X' agree with the bases.
+    import random
+    import re
+    assert oracle.search_trace(b"AC", b"CTTACTTA", 0.0, 5) == ("2=", (3, 0), (5, 2), 0)
+    rng = random.Random(11)
+    for n_p, n_t in [(12, 200), (64, 900), (100, 3000), (700, 5000)]:
+        t = bytearray(rng.choice(b"ACGT") for _ in range(n_t))
+        p = bytes(rng.choice(b"ACGT") for _ in range(n_p))
+        at = rng.randrange(0, n_t - n_p)
+        t[at:at + n_p] = p
+        for _ in range(n_p // 20):
+            t[at + rng.randrange(n_p)] = rng.choice(b"ACGT")
+        t = bytes(t)
+        out = oracle.search(p, t, 0.0)
+        for idx in (out.index(min(out[1:n_t + 1]), 1), n_t // 3, n_t, n_t + n_p // 2):
+            cigar, (si, sj), (ei, ej), cost = oracle.search_trace(p, t, 0.0, idx)
+            i, j, c = si, sj, 0
+            for cnt, op in re.findall(r"(\d*)([=XID])", cigar):
+                for _ in range(int(cnt or 1)):
+                    if op in "=X":
+                        assert (t[i] == p[j]) == (op == "="), (idx, i, j)
+                        i, j, c = i + 1, j + 1, c + (op == "X")
+                    elif op == "D":
+                        i, c = i + 1, c + 1
+                    else:
+                        j, c = j + 1, c + 1
+            assert (i, j) == (ei, ej) and c == cost == out[idx] and (si == 0 or sj == 0), (n_p, idx, cigar[:40])
