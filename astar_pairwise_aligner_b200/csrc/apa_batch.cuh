@@ -29,7 +29,10 @@ struct BatchDev {
     int preset;
     int trace;
     uint32_t q0;        // phase-split path: first work-order position of this wave (arena slot = q - q0)
-    const volatile uint32_t* ready;  // streaming upload: number of pairs (in work order) whose bases are in HBM; nullptr = all
+    // Streaming upload: chunk_state[c] = 0 while upload chunk c is on its way, 1 once its packed planes are in HBM, 2 once its raw
+    // bases are (the kernel then packs them: device-side K0); pair_chunk[q] = chunk of work-order position q. nullptr = all there.
+    const volatile uint32_t* chunk_state;
+    const uint16_t* pair_chunk;
     long long* pair_stats;  // 8 per pair: apa_pair_stats (f_max_tries, h0, num_matches, h_calls, computed_cells, dt blocks, fill tries, -)
     // Device-side K0: when non-null, the raw bases as uploaded (byte offsets a_off / b_off); the kernel that opens a pair packs
     // them into aprof / bprof first (dev_pack_planes). Null: the planes were packed before the launch.

@@ -29,6 +29,12 @@ namespace APA_NS {
 #ifndef APA_DP_V2
 #define APA_DP_V2 1
 #endif
+// APA_TMA_STAGE=1: the planes of a for a block (64 bytes) reach shared memory by a TMA bulk copy (cp.async.bulk + mbarrier)
+// instead of one coalesced load - the measurement north_star's "staged through shared memory via TMA" asks for. Measured on
+// B200 (profiles/README.md, round 2): no gain - the operand is 64 bytes per 256 x 700 cells; kept as a switch, off.
+#ifndef APA_TMA_STAGE
+#define APA_TMA_STAGE 0
+#endif
 
 constexpr int DP_UNROLL = APA_DP_UNROLL;  // steady-state steps per loop iteration of dp_chunk
 
@@ -46,8 +52,23 @@ struct WarpSmem {
     uint2 amask[BLOCK_W];   // per column of the current block: (0 - rank bit0, 0 - rank bit1) of a[i]  (profile.rs:117-121)
 #endif
     uint8_t hrow[BLOCK_W];  // bottom horizontal deltas of the previous chunk: bit0 = +1, bit1 = -1
+#if APA_TMA_STAGE
+    alignas(16) uint2 astage[8];      // landing zone of the bulk copy of a block's planes of a (8 half-words = 256 columns)
+    alignas(8) unsigned long long mbar;  // its completion barrier
+    uint32_t mbar_phase, mbar_ready;
+#endif
     alignas(8) int32_t dt_i[2][96];  // (8-byte aligned: the build kernel keeps its uint2 plane windows here) DT-trace fronts of the current and previous level: column reached on diagonal d at [d + 48]
 };
+
+// APA_TMA_STAGE: shared memory is not initialised at launch; every kernel resets its warps' barrier flag before the first block.
+__device__ __forceinline__ void tma_stage_reset(WarpSmem& sm) {
+#if APA_TMA_STAGE
+    if ((threadIdx.x & 31) == 0) sm.mbar_ready = 0u;
+    __syncwarp();
+#else
+    (void)sm;
+#endif
+}
 
 // Constants as operands the assembler cannot fold: (h << 1) | carry is issued as IMAD h, c[2], carry and the table
 // address as IMAD c, c[128], base on the FMA pipe instead of shifts / LEAs on the ALU pipe.
@@ -82,6 +103,32 @@ __device__ __forceinline__ void myers_step_eq(uint32_t eq, uint32_t& vp, uint32_
 __device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restrict__ aprof, I col_s, int ncols, int lane) {
     const int hw0 = col_s >> 5;
     const int nw = (ncols >> 2) + 1;  // one word past the last column: the steady loop of dp_chunk fetches one column ahead
+#if APA_TMA_STAGE && !APA_GENERAL
+    {   // TMA bulk copy of the block's plane words into sm.astage, completion on sm.mbar (one phase per block)
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.mbar);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.astage[0]);
+        const uint32_t bytes = (uint32_t)(((ncols + 63) >> 6) * 16);  // whole 16-byte units: two half-words each (planes are padded)
+        if (lane == 0) {
+            if (sm.mbar_ready != 0x600DBA44u) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                sm.mbar_ready = 0x600DBA44u;
+                sm.mbar_phase = 0u;
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(aprof + hw0), "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+        __syncwarp();
+        const uint32_t phase = sm.mbar_phase;
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+        __syncwarp();
+        if (lane == 0) sm.mbar_phase = phase ^ 1u;
+    }
+#endif
     for (int w = lane; w < nw; w += 32) {
         uint32_t word = 0u;
         if (4 * w < ncols) {
@@ -90,7 +137,11 @@ __device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restric
             const int sh = 0;
             (void)hw0;
 #else
+#if APA_TMA_STAGE
+            const uint2 pl = sm.astage[w >> 3];
+#else
             const uint2 pl = aprof[hw0 + (w >> 3)];
+#endif
             const int sh = (w & 7) * 4;
 #endif
             const uint32_t n0 = (~pl.x >> sh) & 15u, n1 = (~pl.y >> sh) & 15u;

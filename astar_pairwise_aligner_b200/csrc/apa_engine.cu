@@ -43,31 +43,28 @@ static int set_err(int code, const std::string& msg) {
 #include "apa_batch.cuh"
 
 
-// Streaming upload: wait until pair number q of the work order has landed in HBM. The wait is bounded (about 20 s without
-// the counter moving past q) so that a copy that never comes - a failed upload, a profiler that serialises the launch ahead
-// of the copies - ends in ST_ASSERT for the pair instead of a hung GPU. The fence orders the loads of the pair's bases after
-// the observation of the counter.
-__device__ __forceinline__ bool wait_ready(const BatchDev& bd, unsigned long long q) {
-    if (!bd.ready) return true;
+// Streaming upload: wait until the upload chunk of work-order position q has landed in HBM. Returns 1 when the pair's packed
+// planes are there, 2 when its raw bases are (the caller packs them), 0 when nothing came: the wait is bounded (about 20 s)
+// so that a copy that never comes - a failed upload, a profiler that serialises the launch ahead of the copies - ends in
+// ST_ASSERT for the pair instead of a hung GPU. The fence orders the loads of the pair's bases after the observation.
+__device__ __forceinline__ int wait_ready(const BatchDev& bd, unsigned long long q) {
+    if (!bd.chunk_state) return bd.raw_a ? 2 : 1;
     const int lane = threadIdx.x & 31;
-    int ok = 1;
+    uint32_t st = 0;
     if (lane == 0) {
+        const volatile uint32_t* flag = bd.chunk_state + bd.pair_chunk[q];
         unsigned long long spins = 0;
-        while (*bd.ready <= (uint32_t)q) {
+        while ((st = *flag) == 0u) {
             __nanosleep(500);
-            if (++spins > 40000000ull) {
-                ok = 0;
-                break;
-            }
+            if (++spins > 40000000ull) break;
         }
         __threadfence();
     }
-    ok = __shfl_sync(FULL, ok, 0);
-    return ok != 0;
+    return (int)__shfl_sync(FULL, st, 0);
 }
 // Device-side K0 for the pair a warp is about to align (BatchDev::raw_a / raw_b): returns true on a byte outside ACGT.
-__device__ __forceinline__ bool pack_pair(const BatchDev& bd, uint32_t p, I n, I m) {
-    if (!bd.raw_a) return false;
+__device__ __forceinline__ bool pack_pair(const BatchDev& bd, uint32_t p, I n, I m, int mode) {
+    if (mode != 2) return false;
     const int nhw_a = (int)(bd.ap_off[p + 1] - bd.ap_off[p]), nhw_b = (int)(bd.bp_off[p + 1] - bd.bp_off[p]);
     bool bad = dev_pack_planes(bd.raw_a + bd.a_off[p], n, bd.aprof + bd.ap_off[p], nhw_a);
     bad |= dev_pack_planes(bd.raw_b + bd.b_off[p], m, bd.bprof + bd.bp_off[p], nhw_b);
@@ -91,7 +88,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         if (lane == 0) q = atomicAdd(bd.queue, 1ull);
         q = __shfl_sync(FULL, q, 0);
         if (q >= bd.n_order) break;
-        const bool landed = wait_ready(bd, q);  // streaming upload: this pair's bases are in HBM
+        const int landed = wait_ready(bd, q);  // streaming upload: this pair's bases are in HBM (1 planes, 2 raw, 0 never came)
         const uint32_t p = bd.order[q];
 
         PairCtx cx;
@@ -119,7 +116,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.dbg_n = 0;
         if (meta_bytes + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
         if (!landed) cx.status = ST_ASSERT;
-        else if (pack_pair(bd, p, cx.n, cx.m)) cx.status = ST_BAD_INPUT;
+        else if (pack_pair(bd, p, cx.n, cx.m, landed)) cx.status = ST_BAD_INPUT;
 
         Cost cost = -1;
         long long cig_off = -1, cig_len = 0;
@@ -225,7 +222,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
         if (lane == 0) q = atomicAdd(bd.queue + 24 + PHASE, 1ull) + bd.q0;
         q = __shfl_sync(FULL, q, 0);
         if (q >= bd.n_order) break;
-        bool landed = true;
+        int landed = 1;
         if (PHASE == 0) landed = wait_ready(bd, q);  // later phases run after the build kernel, which saw every pair land
         const uint32_t p = bd.order[q];
         uint8_t* arena = bd.arena + (size_t)(q - bd.q0) * bd.arena_size;
@@ -256,7 +253,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             cx.dbg_n = 0;
             if (cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
             if (!landed) cx.status = ST_ASSERT;
-            else if (pack_pair(bd, p, cx.n, cx.m)) cx.status = ST_BAD_INPUT;
+            else if (pack_pair(bd, p, cx.n, cx.m, landed)) cx.status = ST_BAD_INPUT;
             GcshH hh;
             if (cx.status == ST_PENDING && bd.preset == APA_PRESET_FULL) gcsh_build(cx, sm, hh);
             __syncwarp();
@@ -348,6 +345,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
 #define APA_PHASE_KERNEL(NAME, PHASE, MINB)                                                     \
     __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) NAME(BatchDev bd) {             \
         __shared__ WarpSmem smem[WARPS_PER_CTA];                                                \
+        tma_stage_reset(smem[threadIdx.x >> 5]);                                                \
         apa_phase_body<PHASE>(bd, smem[threadIdx.x >> 5]);                                      \
     }
 APA_PHASE_KERNEL(apa_phase_build_kernel, 0, 10)
@@ -365,6 +363,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) apa_phase_pass_coop_kernel(Bat
     __shared__ CoopSmem<W> cs;
     const int wid = threadIdx.x >> 5;
     if (wid == 0) {
+        tma_stage_reset(cs.lead);
         apa_phase_body<1>(bd, cs);
         coop_release_workers<W>(cs);
     } else {
@@ -390,14 +389,17 @@ static int phase_regs(int phase) {  // default register budget per phase, overri
 // whole waves, and the variant follows from the slots needed per SM.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) apa_align_kernel_r64(BatchDev bd) {
     __shared__ WarpSmem smem[WARPS_PER_CTA];
+    tma_stage_reset(smem[threadIdx.x >> 5]);
     apa_align_body(bd, smem);
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 10) apa_align_kernel_r48(BatchDev bd) {
     __shared__ WarpSmem smem[WARPS_PER_CTA];
+    tma_stage_reset(smem[threadIdx.x >> 5]);
     apa_align_body(bd, smem);
 }
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 12) apa_align_kernel_r40(BatchDev bd) {
     __shared__ WarpSmem smem[WARPS_PER_CTA];
+    tma_stage_reset(smem[threadIdx.x >> 5]);
     apa_align_body(bd, smem);
 }
 
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 12) apa_align_kernel_r40(B
 // path (HMode::None only), so h_in must be all +1; h_out is reconstructed column by column for the KAT.
 __global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof, int nhw, uint2* v, int32_t* cum, uint2* fillvals) {
     __shared__ WarpSmem sm;
+    tma_stage_reset(sm);
     const int lane = threadIdx.x & 31;
     BlkView prev;
     prev.js = 0;
@@ -595,9 +598,11 @@ struct apa_engine {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // streaming uploads overlap the persistent kernel
-    uint32_t* d_ready = nullptr;
-    uint32_t* h_ready = nullptr;  // pinned: cumulative pair counts per upload chunk
+    cudaStream_t copy_stream = nullptr;   // streaming uploads overlap the persistent kernel: raw bases (DMA only)
+    cudaStream_t copy_stream2 = nullptr;  // ... and host-packed planes, issued by the packing threads
+    cudaEvent_t ev_ring[4] = {};          // pacing of the raw copies (two chunks in flight)
+    uint32_t* d_ready = nullptr;  // [0, 256): per-chunk upload state (BatchDev::chunk_state), [300]: bad-input flag of apa_pack_kernel
+    uint32_t* h_ready = nullptr;  // pinned constants the state flags are copied from: h_ready[1] = 1, h_ready[2] = 2
     uint32_t* h_stage = nullptr;  // pinned staging for the packed planes (grow-only)
     size_t h_stage_cap = 0;
     cudaEvent_t ev[6] = {};
@@ -624,6 +629,8 @@ struct apa_batch {
     int64_t *d_cig_off = nullptr, *d_cig_len = nullptr;
     long long* d_pair_stats = nullptr;  // 8 per pair (apa_pair_stats)
     uint32_t* d_order = nullptr;
+    uint16_t* d_pair_chunk = nullptr;  // upload chunk of every work-order position (streaming upload)
+    uint32_t chunks_raw = 0;           // chunks of the last streamed upload that went as raw bases
     char* d_pool = nullptr;
     uint64_t pool_cap = 0;
     // streaming upload (apa_align_batch): bases are copied chunk by chunk while the kernel already runs
@@ -707,8 +714,11 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     eng->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc(&eng->d_ready, 64));
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream2, cudaStreamNonBlocking));
+    for (auto& ev : eng->ev_ring) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&eng->d_ready, 2048));
     CUDA_TRY(cudaHostAlloc((void**)&eng->h_ready, 256 * sizeof(uint32_t), cudaHostAllocDefault));
+    for (uint32_t k = 0; k < 256; k++) eng->h_ready[k] = k;
     for (auto& ev : eng->ev) CUDA_TRY(cudaEventCreate(&ev));
     for (auto& ev : eng->evp) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMalloc(&eng->d_queue, 32 * sizeof(unsigned long long)));
@@ -742,6 +752,9 @@ extern "C" void apa_engine_destroy(apa_engine* e) {
         if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->copy_stream2) cudaStreamDestroy(e->copy_stream2);
+    for (auto& ev : e->ev_ring)
+        if (ev) cudaEventDestroy(ev);
     if (e->d_ready) cudaFree(e->d_ready);
     if (e->h_ready) cudaFreeHost(e->h_ready);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -819,6 +832,7 @@ extern "C" void apa_batch_free(apa_engine* e, apa_batch* b) {
     eng_release(e, b->d_cig_len);
     eng_release(e, b->d_pair_stats);
     eng_release(e, b->d_order);
+    eng_release(e, b->d_pair_chunk);
     eng_release(e, b->d_pool);
     delete b;
 }
@@ -882,6 +896,7 @@ static int pack_threads() {
 
 static int upload_planes(apa_engine* e, apa_batch* b, bool streaming);
 static int upload_raw(apa_engine* e, apa_batch* b, bool streaming, cudaStream_t cs);
+static int stream_upload(apa_engine* e, apa_batch* b, int mode);
 static void fill_batch_dev(apa_engine* e, apa_batch* b, BatchDev& bd);
 
 // Frees a half-built batch on every early return of batch_prepare (CUDA_TRY returns from the middle of the function).
@@ -950,11 +965,6 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     b->h_a_off0 = a_off[0];
     b->h_b_off0 = b_off[0];
     b->raw = host_pinned(a_all ? a_all + a_off[0] : nullptr) && host_pinned(b_all ? b_all + b_off[0] : nullptr);
-    // A streamed batch moves 4x fewer bytes over PCIe when host threads pack it first. Measured on B200 (10 000 pairs, n = 100 k):
-    // 113 ms per step host-packed on 16 threads against 123 ms raw (2 GB at ~40 GB/s arrive later than the build kernel needs
-    // them) - but with 4 threads per engine (8 ranks sharing 32 hardware threads) host packing takes 240 ms. So raw is the rule
-    // and host packing the exception for an engine that has at least 12 host threads to itself.
-    if (b->raw && defer_data && pack_threads() >= 12 && b->total_a + b->total_b >= (64ull << 20)) b->raw = false;
     if (const char* ev = getenv("APA_RAW")) b->raw = atoi(ev) != 0;
     // Offsets rebased to the first pair (only lengths matter on the device).
     std::vector<int64_t> ao(b->a_off), bo(b->b_off);
@@ -1001,10 +1011,23 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     CUDA_TRY(eng_alloc(e, (void**)&b->d_cig_len, std::max<uint64_t>(n_pairs, 1) * 8));
     CUDA_TRY(eng_alloc(e, (void**)&b->d_pair_stats, std::max<uint64_t>(n_pairs, 1) * 64));
     CUDA_TRY(eng_alloc(e, (void**)&b->d_order, std::max<uint64_t>(n_pairs, 1) * 8));  // [0,n): work order, [n,2n): retry list
+    const bool streamed = defer_data && b->chunk_pair_end.size() >= 2;
     if (b->raw) {
         CUDA_TRY(eng_alloc(e, (void**)&b->d_araw, b->total_a + 64));
         CUDA_TRY(eng_alloc(e, (void**)&b->d_braw, b->total_b + 64));
-    } else {
+    }
+    if (streamed) {
+        std::vector<uint16_t> pc(n_pairs);
+        uint32_t q0 = 0;
+        for (size_t c = 0; c < b->chunk_pair_end.size(); c++) {
+            for (uint32_t q = q0; q < b->chunk_pair_end[c]; q++) pc[q] = (uint16_t)c;
+            q0 = b->chunk_pair_end[c];
+        }
+        CUDA_TRY(eng_alloc(e, (void**)&b->d_pair_chunk, n_pairs * 2));
+        CUDA_TRY(cudaMemcpyAsync(b->d_pair_chunk, pc.data(), n_pairs * 2, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // pc goes out of scope
+    }
+    if (!b->raw || streamed) {
         // pinned staging for the packed planes: [aprof | bprof]
         const size_t stage_words = (size_t)(hwa + hw) * 2 + 16;
         if (e->h_stage_cap < stage_words) {
@@ -1021,7 +1044,7 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     CUDA_TRY(cudaMemcpyAsync(b->d_ap_off, b->ap_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_pairs) CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), n_pairs * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    b->stats.h2d_bytes = (b->raw ? b->total_a + b->total_b : (hwa + hw) * 8) + 4 * (n_pairs + 1) * 8 + n_pairs * 4;
+    b->stats.h2d_bytes = (b->raw ? b->total_a + b->total_b : (hwa + hw) * 8) + 4 * (n_pairs + 1) * 8 + n_pairs * 4;  // streamed: recounted
     if (!defer_data) {
         int rc;
         if (b->raw) {  // raw bases by DMA, packed by apa_pack_kernel; the raw copy is not kept
@@ -1029,7 +1052,7 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
             if (rc == APA_OK && n_pairs) {
                 BatchDev bd{};
                 fill_batch_dev(e, b, bd);
-                int* d_bad = (int*)(e->d_ready + 8);
+                int* d_bad = (int*)(e->d_ready + 300);
                 CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, st));
                 const unsigned gx = (unsigned)std::min<uint64_t>(n_pairs, 4096);
                 const unsigned gy = n_pairs >= 4ull * e->sm_count ? 1u : (unsigned)((4ull * e->sm_count + n_pairs - 1) / n_pairs);
@@ -1058,28 +1081,31 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     return APA_OK;
 }
 
-// Raw bases from page-locked host memory to HBM, chunk by chunk, on stream cs. With streaming every chunk is followed by
-// the ready counter the running kernel polls. Nothing here blocks the host: all copies are asynchronous DMA.
-static int upload_raw(apa_engine* e, apa_batch* b, bool streaming, cudaStream_t cs) {
-    const size_t n_chunks = b->chunk_pair_end.size();
-    uint32_t p0 = 0;
-    for (size_t c = 0; c < n_chunks; c++) {
-        const uint32_t p1 = b->chunk_pair_end[c];
-        const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
-        if (a1 > a0) CUDA_TRY(cudaMemcpyAsync(b->d_araw + a0, b->h_a + b->h_a_off0 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, cs));
-        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(b->d_braw + b0, b->h_b + b->h_b_off0 + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
-        if (streaming) {
-            e->h_ready[c] = p1;
-            CUDA_TRY(cudaMemcpyAsync(e->d_ready, &e->h_ready[c], 4, cudaMemcpyHostToDevice, cs));
-        }
-        p0 = p1;
-    }
+// Plain (not streamed) upload of raw bases from page-locked host memory: asynchronous DMA on stream cs.
+static int upload_raw(apa_engine* e, apa_batch* b, bool /*streaming*/, cudaStream_t cs) {
+    (void)e;
+    if (b->total_a) CUDA_TRY(cudaMemcpyAsync(b->d_araw, b->h_a + b->h_a_off0, b->total_a, cudaMemcpyHostToDevice, cs));
+    if (b->total_b) CUDA_TRY(cudaMemcpyAsync(b->d_braw, b->h_b + b->h_b_off0, b->total_b, cudaMemcpyHostToDevice, cs));
     return APA_OK;
 }
 
-// Pack the bases on host threads into the pinned staging buffer and copy the planes to HBM, chunk by chunk. With
-// streaming the copies go to the copy stream and each chunk is followed by the ready counter the running kernel polls.
-static int upload_planes(apa_engine* e, apa_batch* b, bool streaming) {
+// Pack the pairs [p0, p1) on the calling thread into the pinned staging buffer ([aprof | bprof], device layout).
+static bool pack_pairs_host(apa_engine* e, apa_batch* b, uint32_t p0, uint32_t p1) {
+    uint32_t* stage_a = e->h_stage;
+    uint32_t* stage_b = e->h_stage + (size_t)b->total_hw_a * 2;
+    bool bad = false;
+    for (uint32_t p = p0; p < p1; p++) {
+        const int64_t n = b->a_off[p + 1] - b->a_off[p], m = b->b_off[p + 1] - b->b_off[p];
+        const int64_t nhw_a = b->ap_off[p + 1] - b->ap_off[p], nhw_b = b->bp_off[p + 1] - b->bp_off[p];
+        bad |= apa_pack_planes_host(b->h_a + b->h_a_off0 + b->a_off[p], n, 0, nhw_a, stage_a + (size_t)b->ap_off[p] * 2) != 0;
+        bad |= apa_pack_planes_host(b->h_b + b->h_b_off0 + b->b_off[p], m, 0, nhw_b, stage_b + (size_t)b->bp_off[p] * 2) != 0;
+    }
+    return bad;
+}
+
+// Plain (not streamed) upload of host-packed planes: host threads pack the bases into the pinned staging buffer (long
+// sequences in segments), one copy per chunk on the engine's stream.
+static int upload_planes(apa_engine* e, apa_batch* b, bool /*streaming*/) {
     const size_t n_chunks = b->chunk_pair_end.size();
     if (n_chunks == 0) return APA_OK;
     auto tp0 = std::chrono::steady_clock::now();
@@ -1112,7 +1138,7 @@ static int upload_planes(apa_engine* e, apa_batch* b, bool streaming) {
     } else {
         pk.start(pack_threads());
     }
-    cudaStream_t cs = streaming ? e->copy_stream : e->stream;
+    cudaStream_t cs = e->stream;
     p0 = 0;
     for (size_t c = 0; c < n_chunks; c++) {
         const uint32_t p1 = b->chunk_pair_end[c];
@@ -1120,16 +1146,91 @@ static int upload_planes(apa_engine* e, apa_batch* b, bool streaming) {
         const int64_t a0 = b->ap_off[p0], a1 = b->ap_off[p1], b0 = b->bp_off[p0], b1 = b->bp_off[p1];
         if (a1 > a0) CUDA_TRY(cudaMemcpyAsync(b->d_aprof + a0, stage_a + (size_t)a0 * 2, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cs));
         if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(b->d_bprof + b0, stage_b + (size_t)b0 * 2, (size_t)(b1 - b0) * 8, cudaMemcpyHostToDevice, cs));
-        if (streaming) {
-            e->h_ready[c] = p1;
-            CUDA_TRY(cudaMemcpyAsync(e->d_ready, &e->h_ready[c], 4, cudaMemcpyHostToDevice, cs));
-        }
         p0 = p1;
     }
     pk.join();
     CUDA_TRY(cudaStreamSynchronize(cs));
     b->pack_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
     if (pk.bad.load()) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT (the reference panics here: pa-bitpacking/src/profile.rs:113)");
+    return APA_OK;
+}
+
+// Streamed upload under the running build kernel, from both ends of the batch at once. The kernel takes the pairs in chunk
+// order. The copy engines send RAW bases of the chunks from the front (pure DMA from page-locked memory, two chunks in flight;
+// the kernel packs them: device-side K0), while the host threads pack chunks from the BACK - the ones the kernel needs last -
+// into 2-bit planes (4x fewer bytes over PCIe) and send those; the two meet wherever the box's PCIe rate and free host cores
+// put the balance (1 GPU with 16 cores: mostly packed; 8 ranks sharing the cores: mostly raw). Every chunk is followed, on the
+// stream that carried it, by its state word (1 planes / 2 raw) that the kernel polls. Pageable inputs cannot be read by DMA:
+// the host threads then pack all chunks, front first. mode: 0 both, 1 raw only, 2 packed only.
+static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
+    const uint32_t n_chunks = (uint32_t)b->chunk_pair_end.size();
+    auto tp0 = std::chrono::steady_clock::now();
+    std::mutex mu;
+    uint32_t front = 0, back = n_chunks;  // unclaimed chunks: [front, back)
+    auto claim = [&](bool from_back, uint32_t& c) -> bool {
+        std::lock_guard<std::mutex> lk(mu);
+        if (front >= back) return false;
+        c = from_back ? --back : front++;
+        return true;
+    };
+    auto chunk_pairs = [&](uint32_t c, uint32_t& p0, uint32_t& p1) {
+        p0 = c ? b->chunk_pair_end[c - 1] : 0u;
+        p1 = b->chunk_pair_end[c];
+    };
+    std::atomic<int> bad{0}, cuda_fail{0};
+    std::atomic<uint64_t> bytes{0};
+    const bool dma = mode != 2, pack = mode != 1;
+    uint32_t* stage_a = e->h_stage;
+    uint32_t* stage_b = e->h_stage + (size_t)b->total_hw_a * 2;
+    std::vector<std::thread> workers;
+    if (pack)
+        for (int t = 0; t < pack_threads(); t++)
+            workers.emplace_back([&]() {
+                if (cudaSetDevice(e->device) != cudaSuccess) {
+                    cuda_fail.store(1);
+                    return;
+                }
+                uint32_t c;
+                while (claim(/*from_back=*/dma, c)) {
+                    uint32_t p0, p1;
+                    chunk_pairs(c, p0, p1);
+                    if (pack_pairs_host(e, b, p0, p1)) bad.store(1);  // the chunk is still sent: the kernel must not wait forever
+                    const int64_t a0 = b->ap_off[p0], a1 = b->ap_off[p1], b0 = b->bp_off[p0], b1 = b->bp_off[p1];
+                    cudaError_t ce = cudaSuccess;
+                    if (a1 > a0) ce = cudaMemcpyAsync(b->d_aprof + a0, stage_a + (size_t)a0 * 2, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, e->copy_stream2);
+                    if (ce == cudaSuccess && b1 > b0)
+                        ce = cudaMemcpyAsync(b->d_bprof + b0, stage_b + (size_t)b0 * 2, (size_t)(b1 - b0) * 8, cudaMemcpyHostToDevice, e->copy_stream2);
+                    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->d_ready + c, &e->h_ready[1], 4, cudaMemcpyHostToDevice, e->copy_stream2);
+                    if (ce != cudaSuccess) cuda_fail.store(1);
+                    bytes.fetch_add((uint64_t)(a1 - a0 + b1 - b0) * 8);
+                }
+            });
+    uint32_t n_raw = 0;
+    cudaError_t ce_main = cudaSuccess;
+    if (dma) {
+        uint32_t c;
+        while (ce_main == cudaSuccess && claim(/*from_back=*/false, c)) {
+            if (n_raw >= 2) ce_main = cudaEventSynchronize(e->ev_ring[(n_raw - 2) & 3]);  // two raw chunks in flight
+            uint32_t p0, p1;
+            chunk_pairs(c, p0, p1);
+            const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
+            if (ce_main == cudaSuccess && a1 > a0)
+                ce_main = cudaMemcpyAsync(b->d_araw + a0, b->h_a + b->h_a_off0 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream);
+            if (ce_main == cudaSuccess && b1 > b0)
+                ce_main = cudaMemcpyAsync(b->d_braw + b0, b->h_b + b->h_b_off0 + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, e->copy_stream);
+            if (ce_main == cudaSuccess) ce_main = cudaMemcpyAsync(e->d_ready + c, &e->h_ready[2], 4, cudaMemcpyHostToDevice, e->copy_stream);
+            if (ce_main == cudaSuccess) ce_main = cudaEventRecord(e->ev_ring[n_raw & 3], e->copy_stream);
+            bytes.fetch_add((uint64_t)(a1 - a0 + b1 - b0));
+            n_raw++;
+        }
+    }
+    for (auto& t : workers) t.join();
+    b->chunks_raw = n_raw;
+    b->stats.h2d_bytes = bytes.load() + 4 * (b->n_pairs + 1) * 8 + b->n_pairs * 6;
+    b->pack_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+    if (ce_main != cudaSuccess || cuda_fail.load())
+        return set_err(APA_ERR_CUDA, std::string("streamed upload: ") + cudaGetErrorString(ce_main != cudaSuccess ? ce_main : cudaGetLastError()));
+    if (bad.load()) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT (the reference panics here: pa-bitpacking/src/profile.rs:113)");
     return APA_OK;
 }
 
@@ -1355,30 +1456,27 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             bd.order = b->d_order + b->n_pairs;
             CUDA_TRY(cudaMemsetAsync(e->d_queue, 0, sizeof(unsigned long long), st));
         }
-        // The bases of a deferred batch (apa_align_batch) reach HBM here. A batch of several upload chunks streams: the
-        // persistent kernel starts on the first chunk while the later ones are still on their way (H2D overlaps compute).
-        // One chunk, waves, the general kernel and retries take the plain upload: nothing to overlap with. Raw (page-locked)
-        // inputs are copied by DMA alone and packed by the kernel that opens each pair; the host never blocks, so every copy is
-        // queued before the kernel is launched (a serialising profiler can then not dead-lock the ready wait). Pageable inputs
-        // are packed by host threads, chunk by chunk, after the launch.
+        // The bases of a deferred batch (apa_align_batch) reach HBM here. A batch of several upload chunks streams under the
+        // running kernel (stream_upload: raw bases by DMA from the front, host-packed planes from the back); one chunk, waves,
+        // the general kernel and retries take the plain upload first: nothing to overlap with.
         const bool first_upload = stream_data && attempt == 0 && !b->chunk_pair_end.empty();
-        bool streaming = first_upload && !gp && b->chunk_pair_end.size() >= 2 && !(split && wave_n < n_work);
+        const bool streaming = first_upload && !gp && b->chunk_pair_end.size() >= 2 && !(split && wave_n < n_work) && b->d_pair_chunk;
+        int stream_mode = b->raw ? 0 : 2;  // page-locked inputs: both ends; pageable: host-packed only
+        if (const char* ev = getenv("APA_RAW")) stream_mode = atoi(ev) != 0 ? (b->raw ? 1 : 2) : 2;
         if (first_upload && !streaming) {
             int rc = b->raw ? upload_raw(e, b, /*streaming=*/false, st) : upload_planes(e, b, /*streaming=*/false);
             if (rc != APA_OK) return rc;
         }
-        bd.ready = streaming ? e->d_ready : nullptr;
+        bd.chunk_state = streaming ? e->d_ready : nullptr;
+        bd.pair_chunk = b->d_pair_chunk;
+        if (attempt > 0) bd.raw_a = bd.raw_b = nullptr;  // a retried pair was packed when it was first opened: its planes are in HBM
         if (streaming) {
-            CUDA_TRY(cudaMemsetAsync(e->d_ready, 0, 4, st));
-            CUDA_TRY(cudaStreamSynchronize(st));  // offsets, order, zeroed queue are in place before anything overlaps
-            if (b->raw) {
-                int rc = upload_raw(e, b, /*streaming=*/true, e->copy_stream);
-                if (rc != APA_OK) return rc;
-            }
+            CUDA_TRY(cudaMemsetAsync(e->d_ready, 0, 256 * 4, st));
+            CUDA_TRY(cudaStreamSynchronize(st));  // offsets, order, zeroed queue and chunk states are in place before anything overlaps
         }
-        const bool host_streaming = streaming && !b->raw;  // host threads pack while the build kernel already runs
+        const bool host_streaming = streaming;  // the host feeds the chunks while the build kernel already runs
         if (attempt == 0) {
-            b->stats.upload_mode = !first_upload ? 0u : (b->raw ? (streaming ? 4u : 3u) : (streaming ? 2u : 1u));
+            b->stats.upload_mode = !first_upload ? 0u : (streaming ? (stream_mode == 0 ? 5u : (stream_mode == 1 ? 4u : 2u)) : (b->raw ? 3u : 1u));
             b->stats.upload_chunks = first_upload ? (uint32_t)b->chunk_pair_end.size() : 0u;
             b->stats.pass_warps_per_pair = split ? (uint32_t)coop_w : 0u;
             b->stats.waves = split ? (uint32_t)((n_work + wave_n - 1) / wave_n) : 0u;
@@ -1445,13 +1543,15 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         if (!split) b->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
         if (host_streaming) {
-            // host threads pack the bases while the persistent kernel already consumes the chunks that have landed
-            int rc = upload_planes(e, b, /*streaming=*/true);
+            // the chunks travel while the persistent kernel already consumes the ones that have landed
+            int rc = stream_upload(e, b, stream_mode);
+            b->stats.upload_chunks_raw = b->chunks_raw;
             if (rc != APA_OK) {
-                // let the kernel drain (the ready counter must reach n_pairs), then report
-                e->h_ready[255] = (uint32_t)b->n_pairs;
-                cudaMemcpyAsync(e->d_ready, &e->h_ready[255], 4, cudaMemcpyHostToDevice, e->copy_stream);
+                // let the kernel drain (every chunk state must become non-zero; chunks that were claimed have been sent), then report
+                std::vector<uint32_t> ones(256, 1u);
                 cudaStreamSynchronize(e->copy_stream);
+                cudaStreamSynchronize(e->copy_stream2);
+                cudaMemcpy(e->d_ready, ones.data(), 256 * 4, cudaMemcpyHostToDevice);
                 cudaStreamSynchronize(st);
                 return rc;
             }
@@ -1459,7 +1559,10 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (streaming) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));  // the caller's buffers are no longer being read
+        if (streaming) {  // the caller's buffers are no longer being read
+            CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+            CUDA_TRY(cudaStreamSynchronize(e->copy_stream2));
+        }
         if (split) CUDA_TRY(add_phase_ms());
         pending.clear();
         for (uint64_t p = 0; p < b->n_pairs; p++)

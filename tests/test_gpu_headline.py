@@ -32,7 +32,8 @@ def test_headline_shape_one_warp_per_pair_gpu(apa, oracle, engine, preset, monke
     # 2 000 pairs of n = 100 000 at e = 5 % (400 MB of bases): more pairs than the cooperative kernel takes (1 184), more
     # bases than one upload chunk. All costs and CIGARs against the oracle, through (1) the resident path bench.py times as
     # `value`, (2) apa_align_batch from pageable memory (host-packed planes streamed under the running kernel), (3)
-    # apa_align_batch from page-locked memory (raw bases streamed, device-side K0) - the `e2e` path of bench.py.
+    # apa_align_batch from page-locked memory: raw bases only (device-side K0 for every pair), and the default - raw chunks by
+    # DMA from the front, host-packed chunks from the back - which is the `e2e` path of bench.py.
     n_pairs = 2000
     a_all, a_off, b_all, b_off = apa.generate_batch(n_pairs, 100000, 0.05, 0, 31415)
     want_costs, want_digests = _oracle_batch(oracle, a_all, a_off, b_all, b_off, preset)
@@ -64,6 +65,12 @@ def test_headline_shape_one_warp_per_pair_gpu(apa, oracle, engine, preset, monke
     costs, pool, off, ln, st = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, preset, True)
     assert st["upload_mode"] == 4 and st["upload_chunks"] >= 8 and st["pass_warps_per_pair"] == 1, st
     _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "pinned, raw streamed")
+    engine.free_pool(pool)
+    # the default for page-locked inputs: streamed from both ends (raw chunks by DMA from the front, host-packed from the back)
+    monkeypatch.delenv("APA_RAW")
+    costs, pool, off, ln, st = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, preset, True)
+    assert st["upload_mode"] == 5 and st["upload_chunks"] >= 8 and 1 <= st["upload_chunks_raw"] <= st["upload_chunks"], st
+    _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "pinned, streamed from both ends")
     engine.free_pool(pool)
     # cost-only run of the same batch
     c2, pool2, _, _, _ = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, preset, False)
@@ -239,3 +246,21 @@ def test_sharded_two_ranks_gpu(apa, tmp_path):
     for p, (o, er) in zip(procs, outs):
         assert p.returncode == 0, er[-3000:]
     assert "GPU_SHARD_OK 120" in outs[0][0]
+
+
+def test_streamed_upload_with_arena_retries_gpu(apa, oracle, engine, monkeypatch):
+    # A streamed batch (several upload chunks, both ends) whose pairs overflow a deliberately small arena: the retried pairs
+    # find their planes in HBM (packed on the host or by the kernel that first opened them) and must not be packed again from
+    # raw bases that never travelled.
+    n_pairs = 700
+    a_all, a_off, b_all, b_off = apa.generate_batch(n_pairs, 100000, 0.05, 0, 99)
+    want_costs, want_digests = _oracle_batch(oracle, a_all, a_off, b_all, b_off, 1)
+    a_pin, b_pin = apa.pinned_copy(a_all), apa.pinned_copy(b_all)
+    monkeypatch.setenv("APA_ARENA_BYTES", str(1 << 20))
+    costs, pool, off, ln, st = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, 1, True)
+    assert st["upload_mode"] == 5 and st["retries"] > 0, st
+    _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "streamed + retries")
+    engine.free_pool(pool)
+    L = apa.load_library()
+    L.apa_pinned_free(a_pin.ctypes.data)
+    L.apa_pinned_free(b_pin.ctypes.data)
