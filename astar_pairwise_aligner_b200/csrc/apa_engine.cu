@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -715,7 +716,7 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream2, cudaStreamNonBlocking));
-    for (auto& ev : eng->ev_ring) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : eng->ev_ring) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
     CUDA_TRY(cudaMalloc(&eng->d_ready, 2048));
     CUDA_TRY(cudaHostAlloc((void**)&eng->h_ready, 256 * sizeof(uint32_t), cudaHostAllocDefault));
     for (uint32_t k = 0; k < 256; k++) eng->h_ready[k] = k;
@@ -1165,23 +1166,65 @@ static int upload_planes(apa_engine* e, apa_batch* b, bool /*streaming*/) {
 static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
     const uint32_t n_chunks = (uint32_t)b->chunk_pair_end.size();
     auto tp0 = std::chrono::steady_clock::now();
+    const bool dma = mode != 2, pack = mode != 1;
     std::mutex mu;
     uint32_t front = 0, back = n_chunks;  // unclaimed chunks: [front, back)
-    auto claim = [&](bool from_back, uint32_t& c) -> bool {
-        std::lock_guard<std::mutex> lk(mu);
-        if (front >= back) return false;
-        c = from_back ? --back : front++;
-        return true;
+    // The packing threads share ONE chunk at a time, pair by pair, so that a chunk is ready after (pack time of a chunk) /
+    // (threads) - the same order of time the copy engines need for one - and the two ends meet without one side idling.
+    struct PackChunk {
+        uint32_t c, p0, p1, next;
+        std::atomic<uint32_t> done{0};
     };
+    std::vector<std::unique_ptr<PackChunk>> pack_chunks;  // stable addresses: stragglers finish a chunk after the next one opened
+    PackChunk* cur = nullptr;
     auto chunk_pairs = [&](uint32_t c, uint32_t& p0, uint32_t& p1) {
         p0 = c ? b->chunk_pair_end[c - 1] : 0u;
         p1 = b->chunk_pair_end[c];
     };
+    auto claim_pair = [&](PackChunk*& pc, uint32_t& p) -> bool {  // next pair of the shared chunk, opening a new chunk when it is used up
+        std::lock_guard<std::mutex> lk(mu);
+        while (!cur || cur->next >= cur->p1) {
+            if (front >= back) return false;
+            const uint32_t c = dma ? --back : front++;  // next to the copy engines: from the back; alone: in the kernel's order
+            pack_chunks.emplace_back(new PackChunk());
+            cur = pack_chunks.back().get();
+            cur->c = c;
+            chunk_pairs(c, cur->p0, cur->p1);
+            cur->next = cur->p0;
+            if (cur->p0 == cur->p1) cur->done.store(0);  // (chunks are never empty: batch_prepare closes a chunk on a pair)
+        }
+        pc = cur;
+        p = cur->next++;
+        return true;
+    };
+    auto claim_front = [&](uint32_t& c) -> bool {
+        std::lock_guard<std::mutex> lk(mu);
+        if (front >= back) return false;
+        c = front++;
+        return true;
+    };
     std::atomic<int> bad{0}, cuda_fail{0};
     std::atomic<uint64_t> bytes{0};
-    const bool dma = mode != 2, pack = mode != 1;
     uint32_t* stage_a = e->h_stage;
     uint32_t* stage_b = e->h_stage + (size_t)b->total_hw_a * 2;
+    uint32_t n_raw = 0;
+    cudaError_t ce_main = cudaSuccess;
+    auto send_raw = [&](uint32_t c) {
+        if (n_raw >= 2) ce_main = cudaEventSynchronize(e->ev_ring[(n_raw - 2) & 3]);  // two raw chunks in flight
+        uint32_t p0, p1;
+        chunk_pairs(c, p0, p1);
+        const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
+        if (ce_main == cudaSuccess && a1 > a0)
+            ce_main = cudaMemcpyAsync(b->d_araw + a0, b->h_a + b->h_a_off0 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream);
+        if (ce_main == cudaSuccess && b1 > b0)
+            ce_main = cudaMemcpyAsync(b->d_braw + b0, b->h_b + b->h_b_off0 + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, e->copy_stream);
+        if (ce_main == cudaSuccess) ce_main = cudaMemcpyAsync(e->d_ready + c, &e->h_ready[2], 4, cudaMemcpyHostToDevice, e->copy_stream);
+        if (ce_main == cudaSuccess) ce_main = cudaEventRecord(e->ev_ring[n_raw & 3], e->copy_stream);
+        bytes.fetch_add((uint64_t)(a1 - a0 + b1 - b0));
+        n_raw++;
+    };
+    uint32_t c;
+    if (dma && claim_front(c)) send_raw(c);  // the first chunk is on its way before the packing threads exist
     std::vector<std::thread> workers;
     if (pack)
         for (int t = 0; t < pack_threads(); t++)
@@ -1190,40 +1233,24 @@ static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
                     cuda_fail.store(1);
                     return;
                 }
-                uint32_t c;
-                while (claim(/*from_back=*/dma, c)) {
-                    uint32_t p0, p1;
-                    chunk_pairs(c, p0, p1);
-                    if (pack_pairs_host(e, b, p0, p1)) bad.store(1);  // the chunk is still sent: the kernel must not wait forever
-                    const int64_t a0 = b->ap_off[p0], a1 = b->ap_off[p1], b0 = b->bp_off[p0], b1 = b->bp_off[p1];
+                PackChunk* pc;
+                uint32_t p;
+                while (claim_pair(pc, p)) {
+                    if (pack_pairs_host(e, b, p, p + 1)) bad.store(1);  // the chunk is still sent: the kernel must not wait forever
+                    if (pc->done.fetch_add(1, std::memory_order_acq_rel) + 1 != pc->p1 - pc->p0) continue;
+                    // the last pair of the chunk: send its planes and its state word
+                    const int64_t a0 = b->ap_off[pc->p0], a1 = b->ap_off[pc->p1], b0 = b->bp_off[pc->p0], b1 = b->bp_off[pc->p1];
                     cudaError_t ce = cudaSuccess;
                     if (a1 > a0) ce = cudaMemcpyAsync(b->d_aprof + a0, stage_a + (size_t)a0 * 2, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, e->copy_stream2);
                     if (ce == cudaSuccess && b1 > b0)
                         ce = cudaMemcpyAsync(b->d_bprof + b0, stage_b + (size_t)b0 * 2, (size_t)(b1 - b0) * 8, cudaMemcpyHostToDevice, e->copy_stream2);
-                    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->d_ready + c, &e->h_ready[1], 4, cudaMemcpyHostToDevice, e->copy_stream2);
+                    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->d_ready + pc->c, &e->h_ready[1], 4, cudaMemcpyHostToDevice, e->copy_stream2);
                     if (ce != cudaSuccess) cuda_fail.store(1);
                     bytes.fetch_add((uint64_t)(a1 - a0 + b1 - b0) * 8);
                 }
             });
-    uint32_t n_raw = 0;
-    cudaError_t ce_main = cudaSuccess;
-    if (dma) {
-        uint32_t c;
-        while (ce_main == cudaSuccess && claim(/*from_back=*/false, c)) {
-            if (n_raw >= 2) ce_main = cudaEventSynchronize(e->ev_ring[(n_raw - 2) & 3]);  // two raw chunks in flight
-            uint32_t p0, p1;
-            chunk_pairs(c, p0, p1);
-            const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
-            if (ce_main == cudaSuccess && a1 > a0)
-                ce_main = cudaMemcpyAsync(b->d_araw + a0, b->h_a + b->h_a_off0 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream);
-            if (ce_main == cudaSuccess && b1 > b0)
-                ce_main = cudaMemcpyAsync(b->d_braw + b0, b->h_b + b->h_b_off0 + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, e->copy_stream);
-            if (ce_main == cudaSuccess) ce_main = cudaMemcpyAsync(e->d_ready + c, &e->h_ready[2], 4, cudaMemcpyHostToDevice, e->copy_stream);
-            if (ce_main == cudaSuccess) ce_main = cudaEventRecord(e->ev_ring[n_raw & 3], e->copy_stream);
-            bytes.fetch_add((uint64_t)(a1 - a0 + b1 - b0));
-            n_raw++;
-        }
-    }
+    if (dma)
+        while (ce_main == cudaSuccess && claim_front(c)) send_raw(c);
     for (auto& t : workers) t.join();
     b->chunks_raw = n_raw;
     b->stats.h2d_bytes = bytes.load() + 4 * (b->n_pairs + 1) * 8 + b->n_pairs * 6;
