@@ -43,7 +43,7 @@ struct DpCounters {  // statistics of the block DP (bench.py: lane_utilisation =
     unsigned long long issue_steps;  // lane-steps issued: 32 lanes x anti-diagonals swept, ramps and idle lanes included
 };
 
-struct WarpSmem {
+struct alignas(16) WarpSmem {  // (also the 1 040-byte landing zone of dev_pack_planes, before anything else of a pair is live)
 #if APA_DP_V2
     uint32_t etab[4 * 32];   // etab[c * 32 + lane]: BitProfile::eq of base c against the 32 rows of b this lane owns
     uint8_t achar[BLOCK_W + 4];  // per column of the current block: rank of a[i] (A0 C1 G2 T3, profile.rs:113); +4: zero

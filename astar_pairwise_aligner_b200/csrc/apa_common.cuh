@@ -129,31 +129,64 @@ __device__ __forceinline__ uint32_t rank_acgt(uint32_t c) {
 __device__ __forceinline__ bool is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
 // K0 on the device: BitProfile::build (pa-bitpacking/src/profile.rs:112-133) for one sequence, by one warp (or by the warps
-// of a grid, each taking every `stride`-th group of 32 half-words starting at `first`). raw: the bases as uploaded (any
-// alignment; read with ld.global.cg - the bytes may have been written by a copy engine while this kernel was already running,
-// and L1 is not coherent with those writes); prof: nhw plane words (negated rank bits of A0 C1 G2 T3 per 32 bases, zero past
-// the end of the sequence, padding half-words included). Returns true (warp-uniform) if a byte outside ACGT was seen: the
-// reference panics there (profile.rs:113).
-__device__ __forceinline__ bool dev_pack_planes(const uint8_t* __restrict__ raw, I len, uint2* __restrict__ prof, int nhw, int first = 0,
-                                                int stride = 1) {
+// of a grid, each taking every `stride`-th group of 32 half-words starting at `first`). raw: the bases as uploaded, any
+// alignment; prof: nhw plane words (negated rank bits of A0 C1 G2 T3 per 32 bases, zero past the end of the sequence, padding
+// half-words included). A group of 1 024 bases is fetched with 16-byte loads from the enclosing aligned words (ld.global.cg:
+// the bytes may have been written by a copy engine while this kernel was already running, and L1 is not coherent with those
+// writes) into `sbuf` (>= 1 040 bytes of this warp's shared memory, 16-byte aligned), then every lane turns the 32 bytes of
+// its half-word into two plane words: 2-bit code (c >> 1) & 3 per byte, rank = code ^ (code >> 1), the four rank bits of a
+// 32-bit word gathered by one multiply. Returns true (warp-uniform) if a byte outside ACGT was seen: the reference panics there
+// (profile.rs:113).
+__device__ __forceinline__ bool dev_pack_planes(const uint8_t* __restrict__ raw, I len, uint2* __restrict__ prof, int nhw, uint32_t* sbuf,
+                                                int first = 0, int stride = 1) {
     const int lane = threadIdx.x & 31;
+    const unsigned long long addr = (unsigned long long)raw;
+    const uint32_t sh = (uint32_t)(addr & 15ull);
+    const uint4* src = (const uint4*)(addr - sh);
+    uint4* sb4 = (uint4*)sbuf;
     bool bad = false;
     for (int g = first; 32 * g < nhw; g += stride) {
-        // this warp packs half-words [32 g, 32 g + 32): one ballot pair per half-word, lane t of the result keeps half-word t
-        uint32_t keep0 = 0u, keep1 = 0u;
-        const int hw_end = min(32, nhw - 32 * g);
-#pragma unroll 4
-        for (int t = 0; t < hw_end; t++) {
-            const I pos = (I)((32 * g + t) * 32 + lane);
-            const bool in = pos < len;
-            const uint32_t c = in ? (uint32_t)__ldcg(raw + pos) : (uint32_t)'T';  // rank 3: both negated planes 0
-            const uint32_t r = rank_acgt(c);
-            const uint32_t p0 = __ballot_sync(FULL, !(r & 1u));
-            const uint32_t p1 = __ballot_sync(FULL, !(r & 2u));
-            bad |= in && !is_acgt(c);
-            if (lane == t) keep0 = p0, keep1 = p1;
+        // bytes [1024 g, 1024 g + 1024) of the sequence = aligned 16-byte words 64 g .. 64 g + 64 (the last one only when sh > 0);
+        // nothing past the end of the sequence is fetched (it may belong to a chunk that has not landed, or to no buffer at all)
+        const long long last_word = ((long long)sh + len + 15) >> 4;  // exclusive
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int k = lane + 32 * r;
+            const long long w = 64ll * g + k;
+            if (k < 65 && w < last_word) sb4[k] = __ldcg(src + w);
         }
-        if (lane < hw_end) prof[32 * g + lane] = make_uint2(keep0, keep1);
+        __syncwarp();
+        const int hw = 32 * g + lane;
+        if (hw < nhw) {
+            const I p0 = (I)hw * 32;
+            const int nvalid = max(0, min(32, len - p0));
+            uint32_t b0 = 0u, b1 = 0u, diff = 0u;
+            if (nvalid > 0) {
+                const uint32_t o = sh + 32u * (uint32_t)lane;
+                const uint32_t* w32 = sbuf + (o >> 2);
+                const uint32_t s8 = (o & 3u) * 8u;
+                uint32_t lo = w32[0];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t hi = w32[j + 1];
+                    const uint32_t x = __funnelshift_r(lo, hi, s8);  // bases 4 j .. 4 j + 3 of this half-word
+                    lo = hi;
+                    const uint32_t code = (x >> 1) & 0x03030303u;                  // A0 C1 T2 G3 per byte
+                    const uint32_t rk = code ^ ((code >> 1) & 0x01010101u);        // A0 C1 G2 T3
+                    b0 |= ((((rk & 0x01010101u) * 0x01020408u) >> 24) & 15u) << (4 * j);
+                    b1 |= (((((rk >> 1) & 0x01010101u) * 0x01020408u) >> 24) & 15u) << (4 * j);
+                    // the byte each code stands for, against the byte that is there (bytes past the end are not judged)
+                    const uint32_t sel = (code & 3u) | ((code >> 4) & 0x30u) | ((code >> 8) & 0x300u) | ((code >> 12) & 0x3000u);
+                    const int nb = min(4, nvalid - 4 * j);
+                    const uint32_t bm = nb >= 4 ? ~0u : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+                    diff |= (__byte_perm(0x47544341u, 0u, sel) ^ x) & bm;
+                }
+            }
+            const uint32_t vm = nvalid >= 32 ? ~0u : ((1u << nvalid) - 1u);
+            prof[hw] = make_uint2(~b0 & vm, ~b1 & vm);
+            bad |= diff != 0u;
+        }
+        __syncwarp();  // sbuf is overwritten by the next group
     }
     return __any_sync(FULL, bad);
 }

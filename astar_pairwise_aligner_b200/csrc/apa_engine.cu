@@ -64,11 +64,12 @@ __device__ __forceinline__ int wait_ready(const BatchDev& bd, unsigned long long
     return (int)__shfl_sync(FULL, st, 0);
 }
 // Device-side K0 for the pair a warp is about to align (BatchDev::raw_a / raw_b): returns true on a byte outside ACGT.
-__device__ __forceinline__ bool pack_pair(const BatchDev& bd, uint32_t p, I n, I m, int mode) {
+__device__ __forceinline__ bool pack_pair(const BatchDev& bd, uint32_t p, I n, I m, int mode, WarpSmem& sm) {
     if (mode != 2) return false;
+    static_assert(sizeof(WarpSmem) >= 1040, "dev_pack_planes lands 65 16-byte words in the warp's shared memory");
     const int nhw_a = (int)(bd.ap_off[p + 1] - bd.ap_off[p]), nhw_b = (int)(bd.bp_off[p + 1] - bd.bp_off[p]);
-    bool bad = dev_pack_planes(bd.raw_a + bd.a_off[p], n, bd.aprof + bd.ap_off[p], nhw_a);
-    bad |= dev_pack_planes(bd.raw_b + bd.b_off[p], m, bd.bprof + bd.bp_off[p], nhw_b);
+    bool bad = dev_pack_planes(bd.raw_a + bd.a_off[p], n, bd.aprof + bd.ap_off[p], nhw_a, (uint32_t*)&sm);
+    bad |= dev_pack_planes(bd.raw_b + bd.b_off[p], m, bd.bprof + bd.bp_off[p], nhw_b, (uint32_t*)&sm);
     __syncwarp();
     return bad;
 }
@@ -117,7 +118,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.dbg_n = 0;
         if (meta_bytes + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
         if (!landed) cx.status = ST_ASSERT;
-        else if (pack_pair(bd, p, cx.n, cx.m, landed)) cx.status = ST_BAD_INPUT;
+        else if (pack_pair(bd, p, cx.n, cx.m, landed, sm)) cx.status = ST_BAD_INPUT;
 
         Cost cost = -1;
         long long cig_off = -1, cig_len = 0;
@@ -254,7 +255,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             cx.dbg_n = 0;
             if (cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
             if (!landed) cx.status = ST_ASSERT;
-            else if (pack_pair(bd, p, cx.n, cx.m, landed)) cx.status = ST_BAD_INPUT;
+            else if (pack_pair(bd, p, cx.n, cx.m, landed, sm)) cx.status = ST_BAD_INPUT;
             GcshH hh;
             if (cx.status == ST_PENDING && bd.preset == APA_PRESET_FULL) gcsh_build(cx, sm, hh);
             __syncwarp();
@@ -432,12 +433,14 @@ __global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof,
 // gridDim.x-th pair, its warps (and those of the gridDim.y CTAs sharing the pair) every (8 gridDim.y)-th group of 32 half-words
 // of a, then of b. *bad is set when a byte outside ACGT was seen.
 __global__ void __launch_bounds__(256) apa_pack_kernel(BatchDev bd, int* bad) {
+    __shared__ uint4 land[8][66];
     const int wid = threadIdx.x >> 5, first = blockIdx.y * 8 + wid, stride = gridDim.y * 8;
+    uint32_t* sbuf = (uint32_t*)land[wid];
     bool any_bad = false;
     for (uint64_t p = blockIdx.x; p < bd.n_pairs; p += gridDim.x) {
         const I n = (I)(bd.a_off[p + 1] - bd.a_off[p]), m = (I)(bd.b_off[p + 1] - bd.b_off[p]);
-        any_bad |= dev_pack_planes(bd.raw_a + bd.a_off[p], n, bd.aprof + bd.ap_off[p], (int)(bd.ap_off[p + 1] - bd.ap_off[p]), first, stride);
-        any_bad |= dev_pack_planes(bd.raw_b + bd.b_off[p], m, bd.bprof + bd.bp_off[p], (int)(bd.bp_off[p + 1] - bd.bp_off[p]), first, stride);
+        any_bad |= dev_pack_planes(bd.raw_a + bd.a_off[p], n, bd.aprof + bd.ap_off[p], (int)(bd.ap_off[p + 1] - bd.ap_off[p]), sbuf, first, stride);
+        any_bad |= dev_pack_planes(bd.raw_b + bd.b_off[p], m, bd.bprof + bd.bp_off[p], (int)(bd.bp_off[p + 1] - bd.bp_off[p]), sbuf, first, stride);
     }
     if (any_bad && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
 }
@@ -1251,7 +1254,17 @@ static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
             });
     if (dma)
         while (ce_main == cudaSuccess && claim_front(c)) send_raw(c);
+    const double ms_dma_issued = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
     for (auto& t : workers) t.join();
+    if (getenv("APA_DEBUG_TIMING")) {
+        const double ms_packed = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+        cudaStreamSynchronize(e->copy_stream);
+        const double ms_raw_landed = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+        cudaStreamSynchronize(e->copy_stream2);
+        const double ms_all_landed = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+        fprintf(stderr, "[stream_upload] %u chunks: %u raw (last issued at %.1f ms, landed by %.1f ms), %zu packed by %d threads (done at %.1f ms, landed by %.1f ms)\n",
+                n_chunks, n_raw, ms_dma_issued, ms_raw_landed, pack_chunks.size(), pack ? pack_threads() : 0, ms_packed, ms_all_landed);
+    }
     b->chunks_raw = n_raw;
     b->stats.h2d_bytes = bytes.load() + 4 * (b->n_pairs + 1) * 8 + b->n_pairs * 6;
     b->pack_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();

@@ -256,7 +256,7 @@ def test_streamed_upload_with_arena_retries_gpu(apa, oracle, engine, monkeypatch
     a_all, a_off, b_all, b_off = apa.generate_batch(n_pairs, 100000, 0.05, 0, 99)
     want_costs, want_digests = _oracle_batch(oracle, a_all, a_off, b_all, b_off, 1)
     a_pin, b_pin = apa.pinned_copy(a_all), apa.pinned_copy(b_all)
-    monkeypatch.setenv("APA_ARENA_BYTES", str(1 << 20))
+    monkeypatch.setenv("APA_ARENA_BYTES", "500000")
     costs, pool, off, ln, st = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, 1, True)
     assert st["upload_mode"] == 5 and st["retries"] > 0, st
     _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "streamed + retries")
