@@ -1159,19 +1159,21 @@ static int upload_planes(apa_engine* e, apa_batch* b, bool /*streaming*/) {
     return APA_OK;
 }
 
-// Streamed upload under the running build kernel, from both ends of the batch at once. The kernel takes the pairs in chunk
-// order. The copy engines send RAW bases of the chunks from the front (pure DMA from page-locked memory, two chunks in flight;
-// the kernel packs them: device-side K0), while the host threads pack chunks from the BACK - the ones the kernel needs last -
-// into 2-bit planes (4x fewer bytes over PCIe) and send those; the two meet wherever the box's PCIe rate and free host cores
-// put the balance (1 GPU with 16 cores: mostly packed; 8 ranks sharing the cores: mostly raw). Every chunk is followed, on the
-// stream that carried it, by its state word (1 planes / 2 raw) that the kernel polls. Pageable inputs cannot be read by DMA:
-// the host threads then pack all chunks, front first. mode: 0 both, 1 raw only, 2 packed only.
+// Streamed upload under the running build kernel by two producers that both take the next chunk in the kernel's order: the
+// copy engines send RAW bases (pure DMA from page-locked memory, two chunks in flight; the kernel packs them: device-side K0),
+// the host threads pack a chunk into 2-bit planes (4x fewer bytes over PCIe) and send those. Who takes how many follows from
+// the box: 1 GPU with 16 cores to itself packs ~2/3 of the chunks, 8 ranks sharing the cores send most of them raw. Every
+// chunk is followed, on the stream that carried it, by its state word (1 planes / 2 raw) that the kernel polls. (Measured
+// dead end: packing threads working from the BACK of the batch finish the upload as early, but the kernel - which wants a
+// pair for every resident warp at once - then only sees the front grow at the raw DMA rate: 115 ms per step against 106.)
+// Pageable inputs cannot be read by DMA: the host threads pack all chunks. mode: 0 both, 1 raw only, 2 packed only.
 static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
     const uint32_t n_chunks = (uint32_t)b->chunk_pair_end.size();
     auto tp0 = std::chrono::steady_clock::now();
     const bool dma = mode != 2, pack = mode != 1;
     std::mutex mu;
-    uint32_t front = 0, back = n_chunks;  // unclaimed chunks: [front, back)
+    uint32_t front = 0;
+    const uint32_t back = n_chunks;  // unclaimed chunks: [front, back)
     // The packing threads share ONE chunk at a time, pair by pair, so that a chunk is ready after (pack time of a chunk) /
     // (threads) - the same order of time the copy engines need for one - and the two ends meet without one side idling.
     struct PackChunk {
@@ -1188,7 +1190,7 @@ static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
         std::lock_guard<std::mutex> lk(mu);
         while (!cur || cur->next >= cur->p1) {
             if (front >= back) return false;
-            const uint32_t c = dma ? --back : front++;  // next to the copy engines: from the back; alone: in the kernel's order
+            const uint32_t c = front++;  // like the copy engines: the next chunk in the kernel's order
             pack_chunks.emplace_back(new PackChunk());
             cur = pack_chunks.back().get();
             cur->c = c;
@@ -2172,8 +2174,8 @@ extern "C" int apa_pack_planes_device(apa_engine* e, const uint8_t* seq, uint64_
     const int64_t offs[6] = {3, 3 + (int64_t)len, 0, 0, 0, (int64_t)nhw};  // a_off[2] | b_off[2] (empty b) | plane offsets[2]
     CUDA_TRY(cudaMemcpy(d_off, offs, sizeof offs, cudaMemcpyHostToDevice));
     if (len) CUDA_TRY(cudaMemcpy(d_raw + 3, seq, len, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(d_prof, 0xff, nhw * 8));
-    CUDA_TRY(cudaMemset(d_bad, 0, 4));
+    CUDA_TRY(cudaMemsetAsync(d_prof, 0xff, nhw * 8, e->stream));  // (on the kernel's stream: e->stream does not wait for the legacy stream)
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, e->stream));
     BatchDev bd{};
     bd.n_pairs = 1;
     bd.a_off = d_off;

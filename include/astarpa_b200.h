@@ -53,8 +53,7 @@ typedef struct apa_batch_stats {
      * pass_warps_per_pair: 1 = apa_phase_pass_kernel (one warp per pair), 4 / 8 = apa_phase_pass_coop_kernel, 0 = fused or general kernel;
      * upload_mode: 0 resident batch (apa_batch_upload), 1 host-packed planes, plain copy, 2 host-packed planes streamed under
      * the running kernel, 3 raw bases by DMA + device-side K0, plain copy, 4 raw bases streamed under the running kernel,
-     * 5 streamed from both ends (raw chunks by DMA from the front, host-packed chunks from the back: upload_chunks_raw of
-     * upload_chunks went raw); upload_chunks: H2D chunks of the bases; waves: arena waves of the phase-split path (1 = all at once). */
+     * 5 streamed by both producers (raw chunks by DMA, host-packed chunks: upload_chunks_raw of upload_chunks went raw); upload_chunks: H2D chunks of the bases; waves: arena waves of the phase-split path (1 = all at once). */
     uint32_t pass_warps_per_pair, upload_mode, upload_chunks, waves;
     uint64_t dp_issue_steps; /* 32-row lane-steps ISSUED by the block DP: 32 lanes x anti-diagonals swept by every chunk (ramps, idle lanes
                                 and the feeder lane included); dp_word_steps / dp_issue_steps = lane utilisation */
@@ -95,9 +94,9 @@ void apa_pinned_free(void* p);
 
 /* Host buffers in, host buffers out: upload + run + download in one call (the end-to-end path). Batches of more than one
  * upload chunk (~32 MB of bases) stream: the kernels start on the first chunk while later chunks are still in flight.
- * Page-locked inputs (apa_pinned_alloc, cudaHostAlloc, cudaHostRegister) stream from both ends: the copy engines send raw bytes
- * of the chunks from the front, packed to 2-bit planes on the device (K0 = BitProfile::build, pa-bitpacking/src/profile.rs:112-133,
- * inside the kernel that opens each pair), while host threads pack chunks from the back (4x fewer PCIe bytes); the split follows
+ * Page-locked inputs (apa_pinned_alloc, cudaHostAlloc, cudaHostRegister) are fed by two producers taking the next chunk in turn:
+ * the copy engines send raw bytes, packed to 2-bit planes on the device (K0 = BitProfile::build, pa-bitpacking/src/profile.rs:112-133,
+ * inside the kernel that opens each pair), host threads pack chunks themselves (4x fewer PCIe bytes); the split follows
  * the PCIe rate and the host cores the engine finds. Pageable inputs are packed by host threads into a pinned staging buffer. */
 int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off,
                     const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool, int64_t* cigar_off,

@@ -33,7 +33,7 @@ def test_headline_shape_one_warp_per_pair_gpu(apa, oracle, engine, preset, monke
     # bases than one upload chunk. All costs and CIGARs against the oracle, through (1) the resident path bench.py times as
     # `value`, (2) apa_align_batch from pageable memory (host-packed planes streamed under the running kernel), (3)
     # apa_align_batch from page-locked memory: raw bases only (device-side K0 for every pair), and the default - raw chunks by
-    # DMA from the front, host-packed chunks from the back - which is the `e2e` path of bench.py.
+    # DMA, host-packed chunks by the host threads - which is the `e2e` path of bench.py.
     n_pairs = 2000
     a_all, a_off, b_all, b_off = apa.generate_batch(n_pairs, 100000, 0.05, 0, 31415)
     want_costs, want_digests = _oracle_batch(oracle, a_all, a_off, b_all, b_off, preset)
@@ -66,11 +66,11 @@ def test_headline_shape_one_warp_per_pair_gpu(apa, oracle, engine, preset, monke
     assert st["upload_mode"] == 4 and st["upload_chunks"] >= 8 and st["pass_warps_per_pair"] == 1, st
     _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "pinned, raw streamed")
     engine.free_pool(pool)
-    # the default for page-locked inputs: streamed from both ends (raw chunks by DMA from the front, host-packed from the back)
+    # the default for page-locked inputs: streamed by both producers (raw chunks by DMA, host-packed chunks)
     monkeypatch.delenv("APA_RAW")
     costs, pool, off, ln, st = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, preset, True)
     assert st["upload_mode"] == 5 and st["upload_chunks"] >= 8 and 1 <= st["upload_chunks_raw"] <= st["upload_chunks"], st
-    _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "pinned, streamed from both ends")
+    _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "pinned, both producers")
     engine.free_pool(pool)
     # cost-only run of the same batch
     c2, pool2, _, _, _ = engine.align_batch_raw(a_pin, a_off, b_pin, b_off, preset, False)
@@ -249,7 +249,7 @@ def test_sharded_two_ranks_gpu(apa, tmp_path):
 
 
 def test_streamed_upload_with_arena_retries_gpu(apa, oracle, engine, monkeypatch):
-    # A streamed batch (several upload chunks, both ends) whose pairs overflow a deliberately small arena: the retried pairs
+    # A streamed batch (several upload chunks, both producers) whose pairs overflow a deliberately small arena: the retried pairs
     # find their planes in HBM (packed on the host or by the kernel that first opened them) and must not be packed again from
     # raw bases that never travelled.
     n_pairs = 700
