@@ -153,6 +153,14 @@ def load_library():
     return L
 
 
+def bind_to_device_numa(device):
+    """apa_bind_host_thread_to_device: keep this thread (and what it spawns / first touches) on the GPU's NUMA node.
+    Returns the number of CPUs bound to (0 = unchanged)."""
+    L = load_library()
+    L.apa_bind_host_thread_to_device.argtypes = [C.c_int]
+    return int(L.apa_bind_host_thread_to_device(int(device)))
+
+
 def _check(rc):
     if rc != 0:
         raise AstarPaError(f"libastarpa_c error {rc}: {load_library().apa_last_error().decode()}")

@@ -688,6 +688,46 @@ static void eng_release(apa_engine* e, void* p) {
 
 extern "C" const char* apa_last_error(void) { return g_last_error.c_str(); }
 
+// One process per GPU: keep the calling thread (and the packing threads it will spawn, and the page-locked buffers it will
+// first touch) on the CPUs of the NUMA node the GPU hangs off, so that neither the DMA reads of the bases nor the packed planes
+// cross the socket interconnect. Reads /sys/bus/pci/devices/<bus id>/local_cpulist; CPUs outside the caller's current affinity
+// mask (cgroup cpuset) are ignored, and nothing changes when none is left. Returns the number of CPUs bound to, 0 when nothing
+// was changed, < 0 on error.
+#include <sched.h>
+extern "C" int apa_bind_host_thread_to_device(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return set_err(APA_ERR_NO_DEVICE, "cudaDeviceGetPCIBusId failed");
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return 0;
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!got) return 0;
+    cpu_set_t cur, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return 0;
+    int n = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-15,64-79"
+        int lo = 0, hi = 0;
+        if (sscanf(tok, "%d-%d", &lo, &hi) == 2) {
+        } else if (sscanf(tok, "%d", &lo) == 1) {
+            hi = lo;
+        } else {
+            continue;
+        }
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &cur)) {
+                CPU_SET(c, &want);
+                n++;
+            }
+    }
+    if (n == 0 || n == CPU_COUNT(&cur)) return 0;
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return 0;
+    return n;
+}
+
 extern "C" int apa_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -895,6 +935,8 @@ static int pack_threads() {
         const unsigned ranks = (unsigned)std::max(1, atoi(ev));
         n = std::max(2u, std::min(n, (hc ? hc : 4u) / ranks));
     }
+    cpu_set_t cur;  // a thread bound to part of the box (apa_bind_host_thread_to_device) does not start more workers than it has CPUs
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0 && CPU_COUNT(&cur) > 0) n = std::min<unsigned>(n, (unsigned)CPU_COUNT(&cur));
     return (int)n;
 }
 

@@ -250,6 +250,9 @@ def main():
     else:
         a_all, a_off, b_all, b_off = make_batch(A, args, rank)
     n_local = len(a_off) - 1
+    # one process per GPU: this rank's threads and page-locked buffers stay on the GPU's NUMA node (APA_BENCH_NUMA=0 turns it off)
+    cpus_before = os.sched_getaffinity(0)
+    numa_cpus = A.bind_to_device_numa(local_rank) if os.environ.get("APA_BENCH_NUMA", "1") != "0" else 0
     eng = A.Engine(local_rank)
     eff_cells = float(np.sum((a_off[1:] - a_off[:-1]).astype(np.float64) * (b_off[1:] - b_off[:-1])))
     total_bp = float(a_off[-1])
@@ -354,6 +357,7 @@ def main():
         "contour_probe_rounds_per_query": (st["score_probes"] / st["score_calls"]) if st["score_calls"] else None,
         # block DP: useful 32-row lane-steps / lane-steps issued (32 lanes x steps of every chunk sweep, ramps included)
         "lane_utilisation": (wsteps_all / isteps_all) if isteps_all else None,
+        "host": {"numa_bound_cpus_rank0": numa_cpus, "cpus_visible": len(os.sched_getaffinity(0))},
         "path": {"pass_warps_per_pair": st["pass_warps_per_pair"], "waves": st["waves"], "e2e_upload_mode": s2["upload_mode"] if s2 else None,
                  "e2e_upload_chunks": s2["upload_chunks"] if s2 else None},
         "kernels": [{"name": k, "ms_per_launch": t, "share_of_step": t / ms_step if ms_step else None,
@@ -375,6 +379,7 @@ def main():
         out["phase_cycles"] = dict(zip(["heuristic_build", "block_dp", "passes_total", "trace_total", "dt_trace", "cigar_text", "h_queries",
                                         "prune_update"], [int(x) for x in st["phase_cycles"]]))
     if world == 1:
+        os.sched_setaffinity(0, cpus_before)  # the CPU baseline gets every CPU this process may use
         out["cpu_baseline"] = cpu_leg(args, a_all, a_off, b_all, b_off, preset_id, trace, args.cpu_sample)
         # in-run parity: the GPU results of this very batch against the oracle's, on every pair of the CPU sample
         o_costs, o_digests = cpu_leg.sample_results

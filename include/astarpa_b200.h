@@ -64,6 +64,10 @@ const char* apa_last_error(void);
 int apa_device_count(void);
 
 int apa_engine_create(int device, apa_engine** out);
+/* One process (or thread) per GPU: bind the calling thread - and with it the packing threads the engine spawns from it and the
+ * page-locked buffers it touches first - to the CPUs of the GPU's NUMA node (sysfs local_cpulist of the device, intersected
+ * with the caller's current affinity mask). Returns the number of CPUs bound to, 0 if nothing was changed, < 0 on error. */
+int apa_bind_host_thread_to_device(int device);
 void apa_engine_destroy(apa_engine* e);
 
 /* Host -> HBM: copies the concatenated sequences (a_off/b_off have n_pairs+1 entries) and validates ACGT. */
