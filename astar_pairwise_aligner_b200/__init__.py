@@ -138,6 +138,10 @@ def load_library():
     L.apa_pinned_alloc.argtypes = [C.c_uint64]
     L.apa_pinned_free.argtypes = [C.c_void_p]
     L.apa_align_batch_multi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(C.c_void_p), vp, vp, vp]
+    L.apa_packed_layout.argtypes = [C.c_uint64, vp, vp]
+    L.apa_pack_sequences.argtypes = [C.c_uint64, vp, vp, vp, vp, C.c_int]
+    L.apa_align_batch_packed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(C.c_void_p), vp, vp,
+                                         C.POINTER(BatchStats)]
     L.apa_int32_peak.argtypes = [C.c_void_p, vp]
     L.apa_pack_planes_device.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.apa_block_compute.argtypes = [C.c_void_p, vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.POINTER(C.c_int64)]
@@ -232,6 +236,23 @@ def generate_batch(n_pairs, n, e, model=0, seed0=31415, threads=None):
     return a_all[:n_pairs * n], a_off, b_all[:int(b_off[-1])], b_off
 
 
+def pack_sequences(seq_all, seq_off, threads=None, pinned=True):
+    """apa_pack_sequences: the 2-bit plane form of a set of sequences (the engine's own layout, see include/astarpa_b200.h).
+    Returns (planes uint32 array [2 per half-word], lengths int64 array); planes live in page-locked memory when pinned."""
+    L = load_library()
+    seq_all = np.ascontiguousarray(seq_all, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    n = len(seq_off) - 1
+    lens = np.ascontiguousarray(seq_off[1:] - seq_off[:-1], dtype=np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    _check(L.apa_packed_layout(n, lens.ctypes.data, off.ctypes.data))
+    words = max(int(off[-1]) * 2, 1)
+    planes = pinned_copy(np.zeros(words, dtype=np.uint32)) if pinned else np.zeros(words, dtype=np.uint32)
+    _check(L.apa_pack_sequences(n, seq_all.ctypes.data if seq_all.size else None, seq_off.ctypes.data, planes.ctypes.data, off.ctypes.data,
+                                threads or (os.cpu_count() or 1)))
+    return planes, lens
+
+
 def pinned_copy(arr):
     """Copy a numpy array into page-locked host memory; returns a numpy view (keep it alive; never freed)."""
     L = load_library()
@@ -292,6 +313,20 @@ class Engine:
         else:
             _check(self._L.apa_align_batch(self._h, preset, int(trace), n, ap, a_off.ctypes.data, bp, b_off.ctypes.data,
                                            costs.ctypes.data, C.byref(pool), off.ctypes.data, ln.ctypes.data, C.byref(st)))
+        return costs[:n], pool, off[:n], ln[:n], st.as_dict()
+
+    def align_batch_packed(self, a_planes, a_len, b_planes, b_len, preset=PRESET_FULL, trace=True):
+        """apa_align_batch_packed: as align_batch_raw, on sequences already packed by pack_sequences (2-bit planes)."""
+        n = len(a_len)
+        a_len = np.ascontiguousarray(a_len, dtype=np.int64)
+        b_len = np.ascontiguousarray(b_len, dtype=np.int64)
+        costs = np.zeros(max(n, 1), dtype=np.int64)
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        ln = np.zeros(max(n, 1), dtype=np.int64)
+        pool = C.c_void_p()
+        st = BatchStats()
+        _check(self._L.apa_align_batch_packed(self._h, preset, int(trace), n, a_planes.ctypes.data, a_len.ctypes.data, b_planes.ctypes.data,
+                                              b_len.ctypes.data, costs.ctypes.data, C.byref(pool), off.ctypes.data, ln.ctypes.data, C.byref(st)))
         return costs[:n], pool, off[:n], ln[:n], st.as_dict()
 
     def free_pool(self, pool):

@@ -639,6 +639,7 @@ struct apa_batch {
     uint64_t pool_cap = 0;
     // streaming upload (apa_align_batch): bases are copied chunk by chunk while the kernel already runs
     const uint8_t *h_a = nullptr, *h_b = nullptr;
+    const uint32_t *h_ap = nullptr, *h_bp = nullptr;  // packed (2-bit plane) input of apa_align_batch_packed, in the device layout
     int64_t h_a_off0 = 0, h_b_off0 = 0;
     double pack_ms = 0;
     std::vector<uint32_t> chunk_end;  // pairs (in work order) available after each chunk
@@ -943,6 +944,7 @@ static int pack_threads() {
 static int upload_planes(apa_engine* e, apa_batch* b, bool streaming);
 static int upload_raw(apa_engine* e, apa_batch* b, bool streaming, cudaStream_t cs);
 static int stream_upload(apa_engine* e, apa_batch* b, int mode);
+static int upload_packed(apa_engine* e, apa_batch* b, cudaStream_t cs);
 static void fill_batch_dev(apa_engine* e, apa_batch* b, BatchDev& bd);
 
 // Frees a half-built batch on every early return of batch_prepare (CUDA_TRY returns from the middle of the function).
@@ -973,7 +975,8 @@ static bool host_pinned(const void* p) {
 }
 
 static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, const int64_t* a_off, const uint8_t* b_all,
-                         const int64_t* b_off, bool defer_data, apa_batch** out) {
+                         const int64_t* b_off, bool defer_data, apa_batch** out, const uint32_t* a_planes = nullptr,
+                         const uint32_t* b_planes = nullptr) {
     *out = nullptr;
     if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
     CUDA_TRY(cudaSetDevice(e->device));
@@ -1010,7 +1013,9 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     b->h_b = b_all;
     b->h_a_off0 = a_off[0];
     b->h_b_off0 = b_off[0];
-    b->raw = host_pinned(a_all ? a_all + a_off[0] : nullptr) && host_pinned(b_all ? b_all + b_off[0] : nullptr);
+    b->h_ap = a_planes;
+    b->h_bp = b_planes;
+    b->raw = !a_planes && host_pinned(a_all ? a_all + a_off[0] : nullptr) && host_pinned(b_all ? b_all + b_off[0] : nullptr);
     if (const char* ev = getenv("APA_RAW")) b->raw = atoi(ev) != 0;
     // Offsets rebased to the first pair (only lengths matter on the device).
     std::vector<int64_t> ao(b->a_off), bo(b->b_off);
@@ -1073,7 +1078,7 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
         CUDA_TRY(cudaMemcpyAsync(b->d_pair_chunk, pc.data(), n_pairs * 2, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));  // pc goes out of scope
     }
-    if (!b->raw || streamed) {
+    if ((!b->raw || streamed) && !a_planes) {
         // pinned staging for the packed planes: [aprof | bprof]
         const size_t stage_words = (size_t)(hwa + hw) * 2 + 16;
         if (e->h_stage_cap < stage_words) {
@@ -1124,6 +1129,14 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
     b->stats.h2d_ms = ms;
     *out = guard.release();
+    return APA_OK;
+}
+
+// Plain (not streamed) upload of caller-packed planes (apa_align_batch_packed): the arrays are already in the device layout.
+static int upload_packed(apa_engine* e, apa_batch* b, cudaStream_t cs) {
+    (void)e;
+    if (b->total_hw_a) CUDA_TRY(cudaMemcpyAsync(b->d_aprof, b->h_ap, (size_t)b->total_hw_a * 8, cudaMemcpyHostToDevice, cs));
+    if (b->total_hw) CUDA_TRY(cudaMemcpyAsync(b->d_bprof, b->h_bp, (size_t)b->total_hw * 8, cudaMemcpyHostToDevice, cs));
     return APA_OK;
 }
 
@@ -1212,7 +1225,8 @@ static int upload_planes(apa_engine* e, apa_batch* b, bool /*streaming*/) {
 static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
     const uint32_t n_chunks = (uint32_t)b->chunk_pair_end.size();
     auto tp0 = std::chrono::steady_clock::now();
-    const bool dma = mode != 2, pack = mode != 1;
+    const bool planes_in = mode == 3;  // caller-packed planes: DMA only, nothing to pack on either side
+    const bool dma = mode != 2, pack = mode != 1 && !planes_in;
     std::mutex mu;
     uint32_t front = 0;
     const uint32_t back = n_chunks;  // unclaimed chunks: [front, back)
@@ -1260,6 +1274,18 @@ static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
         if (n_raw >= 2) ce_main = cudaEventSynchronize(e->ev_ring[(n_raw - 2) & 3]);  // two raw chunks in flight
         uint32_t p0, p1;
         chunk_pairs(c, p0, p1);
+        if (planes_in) {
+            const int64_t a0 = b->ap_off[p0], a1 = b->ap_off[p1], b0 = b->bp_off[p0], b1 = b->bp_off[p1];
+            if (ce_main == cudaSuccess && a1 > a0)
+                ce_main = cudaMemcpyAsync(b->d_aprof + a0, b->h_ap + (size_t)a0 * 2, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, e->copy_stream);
+            if (ce_main == cudaSuccess && b1 > b0)
+                ce_main = cudaMemcpyAsync(b->d_bprof + b0, b->h_bp + (size_t)b0 * 2, (size_t)(b1 - b0) * 8, cudaMemcpyHostToDevice, e->copy_stream);
+            if (ce_main == cudaSuccess) ce_main = cudaMemcpyAsync(e->d_ready + c, &e->h_ready[1], 4, cudaMemcpyHostToDevice, e->copy_stream);
+            if (ce_main == cudaSuccess) ce_main = cudaEventRecord(e->ev_ring[n_raw & 3], e->copy_stream);
+            bytes.fetch_add((uint64_t)(a1 - a0 + b1 - b0) * 8);
+            n_raw++;
+            return;
+        }
         const int64_t a0 = b->a_off[p0], a1 = b->a_off[p1], b0 = b->b_off[p0], b1 = b->b_off[p1];
         if (ce_main == cudaSuccess && a1 > a0)
             ce_main = cudaMemcpyAsync(b->d_araw + a0, b->h_a + b->h_a_off0 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream);
@@ -1309,7 +1335,7 @@ static int stream_upload(apa_engine* e, apa_batch* b, int mode) {
         fprintf(stderr, "[stream_upload] %u chunks: %u raw (last issued at %.1f ms, landed by %.1f ms), %zu packed by %d threads (done at %.1f ms, landed by %.1f ms)\n",
                 n_chunks, n_raw, ms_dma_issued, ms_raw_landed, pack_chunks.size(), pack ? pack_threads() : 0, ms_packed, ms_all_landed);
     }
-    b->chunks_raw = n_raw;
+    b->chunks_raw = planes_in ? 0u : n_raw;
     b->stats.h2d_bytes = bytes.load() + 4 * (b->n_pairs + 1) * 8 + b->n_pairs * 6;
     b->pack_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
     if (ce_main != cudaSuccess || cuda_fail.load())
@@ -1545,10 +1571,11 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         // the general kernel and retries take the plain upload first: nothing to overlap with.
         const bool first_upload = stream_data && attempt == 0 && !b->chunk_pair_end.empty();
         const bool streaming = first_upload && !gp && b->chunk_pair_end.size() >= 2 && !(split && wave_n < n_work) && b->d_pair_chunk;
-        int stream_mode = b->raw ? 0 : 2;  // page-locked inputs: both ends; pageable: host-packed only
+        int stream_mode = b->raw ? 0 : 2;  // page-locked inputs: both producers; pageable: host-packed only
         if (const char* ev = getenv("APA_RAW")) stream_mode = atoi(ev) != 0 ? (b->raw ? 1 : 2) : 2;
+        if (b->h_ap) stream_mode = 3;  // caller-packed planes
         if (first_upload && !streaming) {
-            int rc = b->raw ? upload_raw(e, b, /*streaming=*/false, st) : upload_planes(e, b, /*streaming=*/false);
+            int rc = b->h_ap ? upload_packed(e, b, st) : (b->raw ? upload_raw(e, b, /*streaming=*/false, st) : upload_planes(e, b, /*streaming=*/false));
             if (rc != APA_OK) return rc;
         }
         bd.chunk_state = streaming ? e->d_ready : nullptr;
@@ -1560,7 +1587,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         }
         const bool host_streaming = streaming;  // the host feeds the chunks while the build kernel already runs
         if (attempt == 0) {
-            b->stats.upload_mode = !first_upload ? 0u : (streaming ? (stream_mode == 0 ? 5u : (stream_mode == 1 ? 4u : 2u)) : (b->raw ? 3u : 1u));
+            b->stats.upload_mode = !first_upload ? 0u : (b->h_ap ? (streaming ? 7u : 6u) : (streaming ? (stream_mode == 0 ? 5u : (stream_mode == 1 ? 4u : 2u)) : (b->raw ? 3u : 1u)));
             b->stats.upload_chunks = first_upload ? (uint32_t)b->chunk_pair_end.size() : 0u;
             b->stats.pass_warps_per_pair = split ? (uint32_t)coop_w : 0u;
             b->stats.waves = split ? (uint32_t)((n_work + wave_n - 1) / wave_n) : 0u;
@@ -1769,6 +1796,54 @@ extern "C" int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_
         fprintf(stderr, "[apa_align_batch] prepare %.1f ms, run %.1f ms (pack+h2d %.1f ms), download %.1f ms\n", ms(t0, t1), ms(t1, t2),
                 b ? b->pack_ms : 0.0, ms(t2, t3));
     }
+    if (rc == APA_OK && stats) *stats = b->stats;
+    apa_batch_free(e, b);
+    return rc;
+}
+
+// ---- packed (2-bit) input
+static uint64_t packed_halfwords(int64_t len) { return (uint64_t)(((len + 63) / 64) * 2 + 2 + 15) & ~(uint64_t)15; }
+extern "C" int apa_packed_layout(uint64_t n, const int64_t* len, int64_t* off_out) {
+    uint64_t hw = 0;
+    for (uint64_t p = 0; p < n; p++) {
+        if (len[p] < 0 || len[p] >= (1ll << 31) - 1024) return set_err(APA_ERR_TOO_LARGE, "sequence length must be < 2^31 (I = i32)");
+        off_out[p] = (int64_t)hw;
+        hw += packed_halfwords(len[p]);
+    }
+    off_out[n] = (int64_t)hw;
+    return APA_OK;
+}
+extern "C" int apa_pack_sequences(uint64_t n, const uint8_t* seq_all, const int64_t* seq_off, uint32_t* planes_out, const int64_t* off, int n_threads) {
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint64_t p = next.fetch_add(1);
+            if (p >= n) break;
+            if (apa_pack_planes_host(seq_all + seq_off[p], seq_off[p + 1] - seq_off[p], 0, off[p + 1] - off[p], planes_out + (size_t)off[p] * 2)) bad.store(1);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < std::max(1, n_threads); t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (bad.load()) return set_err(APA_ERR_BAD_INPUT, "input byte outside ACGT (the reference panics here: pa-bitpacking/src/profile.rs:113)");
+    return APA_OK;
+}
+extern "C" int apa_align_batch_packed(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint32_t* a_planes, const int64_t* a_len,
+                                      const uint32_t* b_planes, const int64_t* b_len, int64_t* costs, char** cigar_pool, int64_t* cigar_off,
+                                      int64_t* cigar_len, apa_batch_stats* stats) {
+    if (n_pairs && (!a_planes || !b_planes || !a_len || !b_len)) return set_err(APA_ERR_BAD_INPUT, "apa_align_batch_packed: null input");
+    std::vector<int64_t> a_off(n_pairs + 1, 0), b_off(n_pairs + 1, 0);
+    for (uint64_t p = 0; p < n_pairs; p++) {
+        a_off[p + 1] = a_off[p] + a_len[p];
+        b_off[p + 1] = b_off[p] + b_len[p];
+    }
+    apa_batch* b = nullptr;
+    static const uint32_t none[2] = {0u, 0u};  // an empty batch still says "packed input"
+    int rc = batch_prepare(e, n_pairs, nullptr, a_off.data(), nullptr, b_off.data(), true, &b, a_planes ? a_planes : none, b_planes ? b_planes : none);
+    if (rc == APA_OK) rc = batch_run(e, b, preset, trace, true);
+    if (rc == APA_OK) rc = apa_batch_download(e, b, costs, cigar_pool, cigar_off, cigar_len);
     if (rc == APA_OK && stats) *stats = b->stats;
     apa_batch_free(e, b);
     return rc;

@@ -303,8 +303,26 @@ def main():
     clocks = sampler.stop()
     e2e_step = float(np.mean(e2e_ms)) if e2e_ms else float('nan')
 
+    # ---- the same end to end with the bases already in 2-bit planes on the host (apa_align_batch_packed): what a pipeline that
+    # keeps its reads packed sees; 4x fewer bytes through host memory and PCIe. Packing (apa_pack_sequences) is outside the timed region.
+    a_pl, a_len = A.pack_sequences(a_all, a_off)
+    b_pl, b_len = A.pack_sequences(b_all, b_off)
+    pk_ms, pk_h2d = [], 0
+    for it in range(2 + min(e2e_steps, 5)):
+        barrier()
+        t1 = time.perf_counter()
+        c3, pool3, off3, ln3, s3 = eng.align_batch_packed(a_pl, a_len, b_pl, b_len, preset_id, trace)
+        dt = (time.perf_counter() - t1) * 1e3
+        pk_h2d = s3["h2d_bytes"]
+        if it >= 2:
+            pk_ms.append(dt)
+        if it == 0:
+            assert (c3 == costs).all() and (not trace or (A.cigar_digests(pool3, off3, ln3) == digests).all()), "packed-input results differ"
+        eng.free_pool(pool3)
+    pk_step = float(np.mean(pk_ms))
+
     # ---- reduce over ranks: max time, sum of work
-    agg = np.array([ms_step, e2e_step, *(phase_ms / args.steps)], dtype=np.float64)
+    agg = np.array([ms_step, e2e_step, *(phase_ms / args.steps), pk_step], dtype=np.float64)
     work = np.array([eff_cells, float(st["computed_cells"]), total_bp, float(st["dp_word_steps"]), float(a_off[-1] + b_off[-1]),
                      float(st["dp_issue_steps"]), float(n_local)], dtype=np.float64)
     if dist is not None:
@@ -320,6 +338,7 @@ def main():
         return
     ms_step, e2e_step = float(agg[0]), float(agg[1])
     k_ms = [float(x) for x in agg[2:5]]
+    pk_step = float(agg[5])
     eff_all, comp_all, bp_all, wsteps_all, bases_all, isteps_all, pairs_all = work
     value = eff_all / (ms_step / 1e3) / 1e9
     hbm_peak, peak_src, sm_max = peaks()
@@ -373,6 +392,8 @@ def main():
                      "int32_peak_detail": int_peak_meas},
         "e2e": {"value": eff_all / (e2e_step / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": e2e_step, "steps": len(e2e_ms), "api": "apa_align_batch_multi (host page-locked buffers in, host buffers out)"},
+        "e2e_packed_input": {"value": eff_all / (pk_step / 1e3) / 1e9, "unit": UNIT, "ms_per_step": pk_step, "h2d_bytes_per_step": int(pk_h2d),
+                             "api": "apa_align_batch_packed (2-bit planes in page-locked host memory in, host buffers out; packing not timed)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if any(st["phase_cycles"]):  # only with a TIMERS=1 build

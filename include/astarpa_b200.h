@@ -53,7 +53,8 @@ typedef struct apa_batch_stats {
      * pass_warps_per_pair: 1 = apa_phase_pass_kernel (one warp per pair), 4 / 8 = apa_phase_pass_coop_kernel, 0 = fused or general kernel;
      * upload_mode: 0 resident batch (apa_batch_upload), 1 host-packed planes, plain copy, 2 host-packed planes streamed under
      * the running kernel, 3 raw bases by DMA + device-side K0, plain copy, 4 raw bases streamed under the running kernel,
-     * 5 streamed by both producers (raw chunks by DMA, host-packed chunks: upload_chunks_raw of upload_chunks went raw); upload_chunks: H2D chunks of the bases; waves: arena waves of the phase-split path (1 = all at once). */
+     * 5 streamed by both producers (raw chunks by DMA, host-packed chunks: upload_chunks_raw of upload_chunks went raw),
+     * 6 / 7 caller-packed planes (apa_align_batch_packed), plain / streamed; upload_chunks: H2D chunks of the bases; waves: arena waves of the phase-split path (1 = all at once). */
     uint32_t pass_warps_per_pair, upload_mode, upload_chunks, waves;
     uint64_t dp_issue_steps; /* 32-row lane-steps ISSUED by the block DP: 32 lanes x anti-diagonals swept by every chunk (ramps, idle lanes
                                 and the feeder lane included); dp_word_steps / dp_issue_steps = lane utilisation */
@@ -112,6 +113,19 @@ int apa_align_batch(apa_engine* e, int preset, int trace, uint64_t n_pairs, cons
 int apa_align_batch_multi(const int* devices, int n_devices, int preset, int trace, uint64_t n_pairs, const uint8_t* a_all,
                           const int64_t* a_off, const uint8_t* b_all, const int64_t* b_off, int64_t* costs, char** cigar_pool,
                           int64_t* cigar_off, int64_t* cigar_len, apa_batch_stats* stats);
+/* Packed (2-bit) input: for pipelines that keep their reads packed, and for boxes where ASCII bases through host memory are
+ * the limit (8 GPUs x 2 GB of bases per step). A packed sequence set is the engine's own plane layout: sequence p occupies the
+ * half-words [off[p], off[p + 1]) (apa_packed_layout: ceil(len / 64) * 2 + 2 half-words rounded up to a multiple of 16); a
+ * half-word is two u32, (plane0, plane1) = the NEGATED rank bits (A0 C1 G2 T3) of 32 consecutive bases, zero past the end of
+ * the sequence (BitProfile::build, pa-bitpacking/src/profile.rs:124-131). apa_pack_sequences fills such an array on host threads
+ * (validating ACGT); apa_align_batch_packed is apa_align_batch on such arrays: the planes go to HBM by DMA alone. */
+int apa_packed_layout(uint64_t n, const int64_t* len, int64_t* off_out /* n + 1 entries, in half-words */);
+int apa_pack_sequences(uint64_t n, const uint8_t* seq_all, const int64_t* seq_off /* n + 1 */, uint32_t* planes_out,
+                       const int64_t* off /* from apa_packed_layout */, int n_threads);
+int apa_align_batch_packed(apa_engine* e, int preset, int trace, uint64_t n_pairs, const uint32_t* a_planes, const int64_t* a_len,
+                           const uint32_t* b_planes, const int64_t* b_len, int64_t* costs, char** cigar_pool, int64_t* cigar_off,
+                           int64_t* cigar_len, apa_batch_stats* stats);
+
 /* K0 on its own (tests): BitProfile::build of one sequence on the device, layout as in the engine - per 32 bases one
  * (plane0, plane1) pair of u32 with the NEGATED rank bits of A0 C1 G2 T3, ceil(len / 64) * 2 + 2 half-words rounded up to
  * a multiple of 16, zero past the end. out receives 2 u32 per half-word; *n_halfwords the count. Returns APA_ERR_BAD_INPUT for

@@ -264,3 +264,32 @@ def test_streamed_upload_with_arena_retries_gpu(apa, oracle, engine, monkeypatch
     L = apa.load_library()
     L.apa_pinned_free(a_pin.ctypes.data)
     L.apa_pinned_free(b_pin.ctypes.data)
+
+
+@pytest.mark.parametrize("preset", [0, 1])
+def test_packed_input_gpu(apa, oracle, engine, preset):
+    # apa_align_batch_packed: sequences packed to 2-bit planes by the caller (apa_pack_sequences, the engine's own layout), small
+    # batch (plain copy) and a streamed one; equal to the ASCII entry pair by pair, and to the oracle.
+    rng = np.random.default_rng(41)
+    pairs = [apa.generate_pair(int(rng.integers(0, 4000)), float(rng.choice([0.0, 0.05, 0.2])), int(rng.integers(0, 4)),
+                               int(rng.integers(1 << 40))) for _ in range(120)] + [(b"", b""), (b"ACGT", b""), (b"", b"TTGCA")]
+    a_all, a_off, b_all, b_off = apa._concat(pairs)
+    ap, al = apa.pack_sequences(a_all, a_off)
+    bp, bl = apa.pack_sequences(b_all, b_off)
+    costs, pool, off, ln, st = engine.align_batch_packed(ap, al, bp, bl, preset, True)
+    assert st["upload_mode"] == 6, st
+    for k, (a, b) in enumerate(pairs):
+        oc, ocg, _ = oracle.align(a, b, preset, True)
+        assert int(costs[k]) == oc and C.string_at(pool.value + int(off[k]), int(ln[k])).decode() == ocg, k
+    engine.free_pool(pool)
+    with pytest.raises(apa.AstarPaError):
+        apa.pack_sequences(np.frombuffer(b"ACGTNACG", dtype=np.uint8), np.array([0, 8]))
+    # streamed: 700 pairs of n = 100 000 (140 MB of bases = 4 chunks)
+    a_all, a_off, b_all, b_off = apa.generate_batch(700, 100000, 0.05, 0, 777)
+    want_costs, want_digests = _oracle_batch(oracle, a_all, a_off, b_all, b_off, preset)
+    ap, al = apa.pack_sequences(a_all, a_off)
+    bp, bl = apa.pack_sequences(b_all, b_off)
+    costs, pool, off, ln, st = engine.align_batch_packed(ap, al, bp, bl, preset, True)
+    assert st["upload_mode"] == 7 and st["upload_chunks"] >= 3, st
+    _check_against(apa, costs, pool, off, ln, want_costs, want_digests, "packed input, streamed")
+    engine.free_pool(pool)
