@@ -21,6 +21,7 @@
 // carrying apa_last_error(). There is no CPU fallback: without a usable B200 the constructor throws.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -288,6 +289,70 @@ inline std::vector<Cost> search(Seq pattern, Seq text, float unmatched_cost = 0.
     apa_engine_destroy(e);
     if (rc != APA_OK) throw Error(rc, msg);
     return out;
+}
+
+// SearchResult of pa_bitpacking::search with its trace() (pa-bitpacking/src/search.rs:5-16,135-230): `out` as above; trace(idx)
+// is the alignment of the pattern that ends at out[idx] - CIGAR plus the position where the walk stopped and where it ended
+// (i = text column, j = pattern row).
+struct SearchTrace {
+    Cigar cigar;
+    std::pair<int32_t, int32_t> start, end;
+    Cost cost;
+};
+class SearchResult {
+  public:
+    std::vector<Cost> out;
+    SearchResult(Seq pattern, Seq text, float unmatched_cost = 0.0f, int device = 0)
+        : pattern_(pattern), text_(text), unmatched_cost_(unmatched_cost), device_(device) {
+        out = search(pattern, text, unmatched_cost, device);
+    }
+    SearchTrace trace(size_t idx) const {
+        apa_engine* e = nullptr;
+        int rc = apa_engine_create(device_, &e);
+        if (rc != APA_OK) throw Error(rc, std::string("apa_engine_create: ") + apa_last_error());
+        std::string text(2 * (pattern_.size() + text_.size()) + 16, '\0');
+        int32_t pos[5] = {0, 0, 0, 0, 0};
+        rc = apa_search_trace(e, (const uint8_t*)pattern_.data(), pattern_.size(), (const uint8_t*)text_.data(), text_.size(), unmatched_cost_,
+                              idx, text.data(), text.size(), pos);
+        std::string msg = rc == APA_OK ? "" : std::string("apa_search_trace: ") + apa_last_error();
+        apa_engine_destroy(e);
+        if (rc != APA_OK) throw Error(rc, msg);
+        text.resize(strlen(text.c_str()));
+        return SearchTrace{Cigar::parse(text), {pos[0], pos[1]}, {pos[2], pos[3]}, (Cost)pos[4]};
+    }
+
+  private:
+    std::string pattern_, text_;
+    float unmatched_cost_;
+    int device_;
+};
+
+// One call over several GPUs of the box (apa_align_batch_multi): contiguous shards of the batch, one per device, results in
+// input order. The engines are the process-wide ones of the library.
+inline BatchResult align_batch_multi(const std::vector<int>& devices, AstarPa2::Preset preset, bool trace,
+                                     const std::vector<std::pair<Seq, Seq>>& pairs) {
+    const size_t n = pairs.size();
+    std::string a_all, b_all;
+    std::vector<int64_t> a_off(n + 1, 0), b_off(n + 1, 0);
+    for (size_t p = 0; p < n; p++) {
+        a_all.append(pairs[p].first);
+        b_all.append(pairs[p].second);
+        a_off[p + 1] = (int64_t)a_all.size();
+        b_off[p + 1] = (int64_t)b_all.size();
+    }
+    BatchResult r;
+    std::vector<int64_t> costs(n ? n : 1), off(n ? n : 1), len(n ? n : 1);
+    char* pool = nullptr;
+    int rc = apa_align_batch_multi(devices.data(), (int)devices.size(), (int)preset, trace ? 1 : 0, n, (const uint8_t*)a_all.data(), a_off.data(),
+                                   (const uint8_t*)b_all.data(), b_off.data(), costs.data(), &pool, off.data(), len.data(), nullptr);
+    if (rc != APA_OK) throw Error(rc, std::string("apa_align_batch_multi: ") + apa_last_error());
+    r.costs.assign(costs.begin(), costs.begin() + n);
+    if (trace && pool) {
+        r.cigars.resize(n);
+        for (size_t p = 0; p < n; p++) r.cigars[p].assign(pool + off[p], (size_t)len[p]);
+    }
+    apa_free(pool);
+    return r;
 }
 
 // astarpa2::astarpa2_simple / astarpa2_full (astarpa2/src/lib.rs:44-53): a fresh aligner per call, with trace.

@@ -71,6 +71,17 @@ int main(int argc, char** argv) {
         auto [c1, g1] = astarpa2_simple(a, b);
         auto [c2, g2] = astarpa2_full(a, b);
         CHECK(c1 == 2 && c2 == 2 && g1.verify(a, b) == 2 && g2.verify(a, b) == 2);
+        // one call over the GPUs of the box (apa_align_batch_multi), and SearchResult::trace (search.rs:135-230)
+        {
+            std::vector<std::pair<Seq, Seq>> pairs = {{a, b}, {a, a}, {"", b}, {b, a}};
+            BatchResult r = align_batch_multi({0}, AstarPa2::Full, true, pairs);
+            CHECK(r.costs.size() == 4 && r.costs[0] == 2 && r.costs[1] == 0 && r.costs[2] == 8 && r.costs[3] == 2);
+            for (size_t p = 0; p < pairs.size(); p++) CHECK(Cigar::parse(r.cigars[p]).verify(pairs[p].first, pairs[p].second) == r.costs[p]);
+            SearchResult sr("AC", "CTTACTTA", 0.0f);  // the reference's doc-test, search.rs:29-32
+            CHECK((sr.out == std::vector<Cost>{0, 0, 1, 2, 1, 0, 1, 2, 1, 0, 0}));
+            SearchTrace tr = sr.trace(5);
+            CHECK(tr.cigar.to_string() == "2=" && tr.start == std::make_pair(3, 0) && tr.end == std::make_pair(5, 2) && tr.cost == 0);
+        }
         // explicit parameters (general kernel) and the stats surface (align_with_stats, lib.rs:200-208)
         {
             AstarPa2Params q = AstarPa2Params::nw();  // params.rs:46-68: the full n*m rectangle in one pass
