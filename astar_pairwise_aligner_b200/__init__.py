@@ -85,6 +85,18 @@ class AstarPa2Params(C.Structure):
         q.domain, q.heuristic, q.doubling, q.dt_trace, q.sparse_h, q.prune = 0, 0, 0, 0, 0, 0
         return q
 
+    @classmethod
+    def from_json(cls, text):
+        """AstarPa2Params from the reference's serde JSON (apa_params_from_json); raises AstarPaError naming an unsupported field."""
+        L = load_library()
+        L.apa_params_from_json.argtypes = [C.c_char_p, C.POINTER(cls), C.c_char_p, C.c_uint64]
+        q = cls()
+        err = C.create_string_buffer(512)
+        rc = L.apa_params_from_json(text.encode() if isinstance(text, str) else text, C.byref(q), err, 512)
+        if rc != 0:
+            raise AstarPaError(err.value.decode())
+        return q
+
     def replace(self, **kw):
         """Copy with fields replaced; domain / heuristic / doubling / doubling_start also accept their names."""
         q = type(self).from_buffer_copy(self)

@@ -28,7 +28,7 @@
 namespace {
 
 struct Args {
-    std::string input, output, aligner = "astarpa2-full", error_model = "uniform";
+    std::string input, output, aligner = "astarpa2-full", error_model = "uniform", params_file;
     bool have_length = false, have_seed = false, cost_only = false, dry_run = false;
     uint64_t length = 1000, cnt = 1, seed = 0, batch_bases = 2000000000ull;
     double error_rate = 0.05;
@@ -44,6 +44,7 @@ struct Args {
             "  -o, --output <OUTPUT>    Write a .csv of `{cost},{cigar}` lines\n"
             "      --aligner <ALIGNER>  The aligner to use [default: astarpa2-full] [possible values: astarpa,\n"
             "                           astarpa2-simple, astarpa2-full]\n"
+            "      --params <FILE>      AstarPa2Params as the reference's serde JSON (a pa-bench job's `params`); overrides --aligner\n"
             "      --device <D>         CUDA device index [default: 0]\n"
             "      --batch-bases <B>    Bases (a + b) per GPU batch [default: 2000000000]\n"
             "      --cost-only          Compute costs only (no traceback); the csv then holds `{cost},`\n"
@@ -81,6 +82,7 @@ Args parse(int argc, char** argv) {
         else if (s == "-i" || s == "--input") a.input = value();
         else if (s == "-o" || s == "--output") a.output = value();
         else if (s == "--aligner") a.aligner = value();
+        else if (s == "--params") a.params_file = value();
         else if (s == "-n" || s == "--length") a.length = strtoull(value().c_str(), nullptr, 10), a.have_length = true;
         else if (s == "-e" || s == "--error-rate") a.error_rate = atof(value().c_str());
         else if (s == "--seed") a.seed = strtoull(value().c_str(), nullptr, 10), a.have_seed = true;
@@ -171,7 +173,21 @@ int main(int argc, char** argv) {
         std::unique_ptr<astarpa2::AstarPa2> al;
         if (!args.dry_run) {
             auto preset = args.aligner == "astarpa2-simple" ? astarpa2::AstarPa2::Simple : astarpa2::AstarPa2::Full;
-            al.reset(new astarpa2::AstarPa2(preset, !args.cost_only, args.device));  // AlignerType::build, lib.rs:25-33
+            if (!args.params_file.empty()) {  // AstarPa2Params::make_aligner (params.rs:132-226) from the serde JSON form
+                FILE* pf = fopen(args.params_file.c_str(), "r");
+                if (!pf) {
+                    fprintf(stderr, "error: cannot read %s\n", args.params_file.c_str());
+                    return 1;
+                }
+                std::string json;
+                char buf[4096];
+                size_t got;
+                while ((got = fread(buf, 1, sizeof buf, pf)) > 0) json.append(buf, got);
+                fclose(pf);
+                al.reset(new astarpa2::AstarPa2(astarpa2::AstarPa2Params::from_json(json), !args.cost_only, args.device));
+            } else {
+                al.reset(new astarpa2::AstarPa2(preset, !args.cost_only, args.device));  // AlignerType::build, lib.rs:25-33
+            }
             run.aligner = al.get();
             if (!args.output.empty()) {
                 run.out = fopen(args.output.c_str(), "w");

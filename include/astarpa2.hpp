@@ -139,6 +139,14 @@ struct AstarPa2Params : apa_params {
         q.dt_trace = q.sparse_h = q.prune = 0;
         return q;
     }
+    // The serde JSON form of the reference / pa-bench (params.rs:7-42); throws Error naming a field this engine does not serve.
+    static AstarPa2Params from_json(const std::string& json) {
+        AstarPa2Params q;
+        char err[512] = {0};
+        int rc = apa_params_from_json(json.c_str(), &q, err, sizeof err);
+        if (rc != APA_OK) throw Error(rc, err);
+        return q;
+    }
     inline AstarPa2 make_aligner(bool trace, int device = 0) const;
 };
 

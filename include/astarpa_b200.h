@@ -173,6 +173,10 @@ typedef struct apa_params {
 } apa_params;
 /* Fills *out with AstarPa2Params::simple() / ::full() (params.rs:70-128). */
 int apa_params_preset(int preset, apa_params* out);
+/* AstarPa2Params from the serde JSON the reference and pa-bench exchange (params.rs:7-42; missing fields take serde's defaults,
+ * unknown fields are an error like #[serde(deny_unknown_fields)]). Values this engine does not serve are refused with
+ * APA_ERR_BAD_INPUT and a message naming the field in err (err_cap bytes, may be NULL). */
+int apa_params_from_json(const char* json, apa_params* out, char* err, uint64_t err_cap);
 /* apa_batch_run / apa_align_batch / apa_debug_band_log with explicit parameters (always the general kernel). */
 int apa_batch_run_params(apa_engine* e, apa_batch* b, const apa_params* params, int trace);
 int apa_align_batch_params(apa_engine* e, const apa_params* params, int trace, uint64_t n_pairs, const uint8_t* a_all,

@@ -94,3 +94,43 @@ def test_params_presets_and_struct_layout(apa):
     assert (nw.domain, nw.doubling, nw.dt_trace) == (0, 0, 0)  # params.rs:46-68
     g = f.replace(domain="gap_gap", block_width=64, doubling_start="gap")
     assert (g.domain, g.block_width, g.doubling_start, g.k) == (2, 64, 1, 12) and f.domain == 3  # replace() copies
+
+
+FULL_JSON = ('{"name":"full","domain":{"Astar":null},"heuristic":{"type":"GCSH","r":1,"k":12,"p":14,"prune":"Start","kmin":null,'
+             '"kmax":null,"max_matches":null,"skip_prune":null},"doubling":{"BandDoubling":{"start":"H0","factor":2.0}},"block_width":256,'
+             '"front":{"sparse":true,"simd":true,"no_ilp":false,"incremental_doubling":true,"dt_trace":true,"max_g":40,"fr_drop":10},'
+             '"sparse_h":true,"prune":true,"viz":false}')
+SIMPLE_JSON = ('{"name":"simple","domain":{"Astar":null},"heuristic":{"type":"Gap","r":2,"k":15,"p":0,"prune":"Start","kmin":null,'
+               '"kmax":null,"max_matches":null,"skip_prune":null},"doubling":{"BandDoubling":{"start":"H0","factor":2.0}},"block_width":256,'
+               '"front":{"sparse":true,"simd":true,"no_ilp":false,"incremental_doubling":false,"dt_trace":true,"max_g":40,"fr_drop":10},'
+               '"sparse_h":true,"prune":false,"viz":false}')
+
+
+def test_params_from_json(apa):
+    """apa_params_from_json: the serde form of AstarPa2Params (astarpa2/src/params.rs:7-42, what pa-bench job files hold). The two
+    documents above are serde_json of AstarPa2Params::full() / ::simple() (params.rs:70-128) written out field by field."""
+    P = apa.AstarPa2Params
+
+    def fields(q):
+        return {k: getattr(q, k) for k, _ in q._fields_}
+
+    assert fields(P.from_json(FULL_JSON)) == fields(P.full())
+    want = fields(P.simple())
+    got = fields(P.from_json(SIMPLE_JSON))
+    assert got == want, {k: (got[k], want[k]) for k in got if got[k] != want[k]}
+    # serde defaults for absent fields; the other domains / doubling types
+    q = P.from_json('{"domain":"GapGap","heuristic":{"type":"None"},"doubling":{"LinearSearch":{"start":"Gap","delta":48.0}},'
+                    '"block_width":64,"front":{"sparse":true}}')
+    assert (q.domain, q.heuristic, q.doubling, q.doubling_start, q.delta, q.block_width, q.dt_trace, q.sparse_h, q.prune) == \
+           (2, 0, 2, 1, 48, 64, 0, 0, 0)
+    q = P.from_json('{"domain":"Full","heuristic":{"type":"Zero"},"doubling":"None","block_width":1,"front":{"sparse":true,"dt_trace":false}}')
+    assert (q.domain, q.doubling, q.block_width) == (0, 0, 1)
+    # Prune::None inside the heuristic switches pruning off
+    assert P.from_json(FULL_JSON.replace('"prune":"Start"', '"prune":"None"')).prune == 0
+    # refused, never ignored: inexact matches, other heuristics, Prune::Both, LocalDoubling, viz, unknown fields, malformed text
+    for bad in (FULL_JSON.replace('"r":1', '"r":2'), FULL_JSON.replace('"GCSH"', '"SH"'), FULL_JSON.replace('"prune":"Start"', '"prune":"Both"'),
+                FULL_JSON.replace('{"BandDoubling":{"start":"H0","factor":2.0}}', '"LocalDoubling"'), FULL_JSON.replace('"viz":false', '"viz":true'),
+                FULL_JSON.replace('"sparse_h":true', '"sparse_hh":true'), FULL_JSON.replace('"kmin":null', '"kmin":10'), FULL_JSON[:-1],
+                '{"domain":"Full"}', FULL_JSON.replace('"delta"', '"x"').replace('2.0}}', '2.0,"start_increment":3}}')):
+        with pytest.raises(apa.AstarPaError):
+            P.from_json(bad)

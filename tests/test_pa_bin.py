@@ -148,3 +148,25 @@ def test_pa_bin_end_to_end_gpu(pa_bin, apa, oracle, tmp_path, aligner, preset):
     r = subprocess.run([pa_bin, "-i", str(seq), "--aligner", aligner, "-o", str(out3), "--cost-only"], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0 and out3.read_text().split() == [w.split(",")[0] + "," for w in want]
+
+
+@pytest.mark.gpu
+def test_pa_bin_params_json_gpu(pa_bin, apa, oracle, tmp_path):
+    # --params: AstarPa2Params in the reference's serde JSON form (a pa-bench job's `params`, astarpa2/src/params.rs:7-42).
+    # The reference's test configuration `dt_trace` (astarpa2/src/tests.rs:91-104: GCSH k = 15 exact, BandDoubling from Gap,
+    # BlockParams::default() with dt_trace) = oracle configuration 3; unsupported values are refused before any alignment.
+    pairs = [apa.generate_pair(1500, 0.08, m, 500 + m) for m in range(4)]
+    seq = tmp_path / "in.seq"
+    seq.write_bytes(b"".join(b">" + a + b"\n<" + b + b"\n" for a, b in pairs))
+    js = tmp_path / "params.json"
+    js.write_text('{"name":"dt_trace","domain":{"Astar":null},"heuristic":{"type":"GCSH","r":1,"k":15,"p":0,"prune":"Start"},'
+                  '"doubling":{"BandDoubling":{"start":"Gap","factor":2.0}},"block_width":256,'
+                  '"front":{"sparse":true,"simd":true,"no_ilp":false,"incremental_doubling":true,"dt_trace":true,"max_g":40,"fr_drop":20},'
+                  '"sparse_h":true,"prune":true}')
+    out = tmp_path / "out.csv"
+    r = subprocess.run([pa_bin, "-i", str(seq), "--params", str(js), "-o", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text().split() == ["%d,%s" % oracle.align(a, b, 3, True)[:2] for a, b in pairs]
+    js.write_text(js.read_text().replace('"r":1', '"r":2'))
+    r = subprocess.run([pa_bin, "-i", str(seq), "--params", str(js), "-o", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "r must be 1" in r.stderr
