@@ -35,7 +35,7 @@ class BatchStats(C.Structure):
                 ("dp_word_steps", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("retries", C.c_uint64), ("fill_blocks", C.c_uint64), ("dt_blocks", C.c_uint64),
                 ("phase_cycles", C.c_uint64 * 8), ("phase_ms", C.c_double * 3), ("score_calls", C.c_uint64), ("score_probes", C.c_uint64),
-                ("pass_warps_per_pair", C.c_uint32), ("upload_mode", C.c_uint32), ("upload_chunks", C.c_uint32), ("waves", C.c_uint32), ("dp_issue_steps", C.c_uint64), ("upload_chunks_raw", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("pass_warps_per_pair", C.c_uint32), ("upload_mode", C.c_uint32), ("upload_chunks", C.c_uint32), ("waves", C.c_uint32), ("dp_issue_steps", C.c_uint64), ("upload_chunks_raw", C.c_uint32), ("overlapped", C.c_uint32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

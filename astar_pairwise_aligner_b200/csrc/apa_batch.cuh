@@ -38,6 +38,11 @@ struct BatchDev {
     // them into aprof / bprof first (dev_pack_planes). Null: the planes were packed before the launch.
     const uint8_t* raw_a;
     const uint8_t* raw_b;
+    // Overlapped phase kernels (one warp per pair, whole batch in one wave): the build, pass and trace kernels are launched
+    // together on three streams; phase_flag[q] (work-order position) is 1 once pair q is built and 2 once its passes are done,
+    // and the kernel of the next phase waits for it before it opens the pair - so its CTAs fill the SM slots the previous
+    // kernel's tail leaves empty. nullptr = the kernels run back to back.
+    volatile uint8_t* phase_flag;
     int32_t* dbg;  // band log of the (single) pair, or nullptr
     uint32_t dbg_cap;
     uint32_t* dbg_n;

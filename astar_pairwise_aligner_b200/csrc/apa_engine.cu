@@ -226,6 +226,29 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
         if (q >= bd.n_order) break;
         int landed = 1;
         if (PHASE == 0) landed = wait_ready(bd, q);  // later phases run after the build kernel, which saw every pair land
+        if (PHASE >= 1 && bd.phase_flag) {  // overlapped kernels: the previous phase of this pair is done (bounded wait, as above)
+            int okf = 1;
+            if (lane == 0) {
+                unsigned long long spins = 0;
+                while (bd.phase_flag[q] < (uint8_t)PHASE) {
+                    __nanosleep(1000);
+                    if (++spins > 20000000ull) {
+                        okf = 0;
+                        break;
+                    }
+                }
+                __threadfence();
+            }
+            okf = __shfl_sync(FULL, okf, 0);
+            if (!okf) {  // never came: report, and let the next phase pass through
+                if (lane == 0) {
+                    bd.status[bd.order[q]] = ST_ASSERT;
+                    __threadfence();
+                    bd.phase_flag[q] = 2;
+                }
+                continue;
+            }
+        }
         const uint32_t p = bd.order[q];
         uint8_t* arena = bd.arena + (size_t)(q - bd.q0) * bd.arena_size;
         PairState* ps = (PairState*)arena;
@@ -265,6 +288,11 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
                 ps->cost = -1;
             }
             __syncwarp();
+            if (bd.phase_flag) {  // everything this warp wrote for the pair is visible before the flag is
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) bd.phase_flag[q] = 1;
+            }
             continue;
         }
         cx = ps->cx;
@@ -295,6 +323,11 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
                 ps->cost = cost;
             }
             __syncwarp();
+            if (bd.phase_flag && bd.trace) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) bd.phase_flag[q] = 2;
+            }
             if (bd.trace) continue;
         }
         // PHASE 2, or PHASE 1 of a cost-only run: finish the pair
@@ -604,6 +637,10 @@ struct apa_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // streaming uploads overlap the persistent kernel: raw bases (DMA only)
     cudaStream_t copy_stream2 = nullptr;  // ... and host-packed planes, issued by the packing threads
+    cudaStream_t st_pass = nullptr, st_trace = nullptr;  // overlapped phase kernels (lower priority than `stream`)
+    cudaEvent_t ev_ov[3] = {};                           // start of the overlapped launch | pass kernel done | trace kernel done
+    uint8_t* d_phase_flag = nullptr;
+    size_t phase_flag_cap = 0;
     cudaEvent_t ev_ring[4] = {};          // pacing of the raw copies (two chunks in flight)
     uint32_t* d_ready = nullptr;  // [0, 256): per-chunk upload state (BatchDev::chunk_state), [300]: bad-input flag of apa_pack_kernel
     uint32_t* h_ready = nullptr;  // pinned constants the state flags are copied from: h_ready[1] = 1, h_ready[2] = 2
@@ -757,7 +794,12 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
     apa_engine* eng = guard.e;
     eng->device = device;
     eng->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // (numerically lower = higher priority)
+    CUDA_TRY(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, prio_hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&eng->st_pass, cudaStreamNonBlocking, std::min(prio_lo, prio_hi + 1)));
+    CUDA_TRY(cudaStreamCreateWithPriority(&eng->st_trace, cudaStreamNonBlocking, std::min(prio_lo, prio_hi + 2)));
+    for (auto& ev : eng->ev_ov) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream2, cudaStreamNonBlocking));
     for (auto& ev : eng->ev_ring) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
@@ -798,6 +840,11 @@ extern "C" void apa_engine_destroy(apa_engine* e) {
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->copy_stream2) cudaStreamDestroy(e->copy_stream2);
+    if (e->st_pass) cudaStreamDestroy(e->st_pass);
+    if (e->st_trace) cudaStreamDestroy(e->st_trace);
+    for (auto& ev : e->ev_ov)
+        if (ev) cudaEventDestroy(ev);
+    if (e->d_phase_flag) cudaFree(e->d_phase_flag);
     for (auto& ev : e->ev_ring)
         if (ev) cudaEventDestroy(ev);
     if (e->d_ready) cudaFree(e->d_ready);
@@ -1598,8 +1645,40 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         bd.q0 = 0;
         const unsigned grid = (unsigned)(slots / WARPS_PER_CTA);
         // pass + trace kernels of the phase-split path, with the per-phase events (stats.phase_ms)
+        // One warp per pair, the whole batch in one wave: the three phase kernels are launched together (see BatchDev::phase_flag).
+        // APA_OVERLAP=0 runs them back to back (per-kernel timings: bench.py measures its roofline numbers that way).
+        const bool overlap = split && coop_w == 1 && wave_n == n_work && attempt == 0 && trace &&
+                             !(getenv("APA_OVERLAP") && atoi(getenv("APA_OVERLAP")) == 0);
+        bd.phase_flag = nullptr;
+        if (overlap) {
+            if (e->phase_flag_cap < n_work) {
+                if (e->d_phase_flag) CUDA_TRY(cudaFree(e->d_phase_flag));
+                e->d_phase_flag = nullptr;
+                e->phase_flag_cap = 0;
+                CUDA_TRY(cudaMalloc(&e->d_phase_flag, n_work + 256));
+                e->phase_flag_cap = n_work;
+            }
+            CUDA_TRY(cudaMemsetAsync(e->d_phase_flag, 0, n_work, st));
+            bd.phase_flag = e->d_phase_flag;
+        }
+        b->stats.overlapped = overlap ? 1u : 0u;
         auto launch_pass_trace = [&]() -> cudaError_t {
             const unsigned wave_pairs = (unsigned)(bd.n_order - bd.q0);
+            if (overlap) {  // pass and trace kernels on their own streams, behind the setup of this launch only
+                cudaError_t ce = cudaStreamWaitEvent(e->st_pass, e->ev_ov[0], 0);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->st_trace, e->ev_ov[0], 0);
+                if (ce != cudaSuccess) return ce;
+                phase_kernel(1, phase_regs(1))<<<grid, WARPS_PER_CTA * 32, 0, e->st_pass>>>(bd);
+                phase_kernel(2, phase_regs(2))<<<grid, WARPS_PER_CTA * 32, 0, e->st_trace>>>(bd);
+                b->stats.kernel_launches += 2;
+                ce = cudaEventRecord(e->ev_ov[1], e->st_pass);
+                if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_ov[2], e->st_trace);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, e->ev_ov[1], 0);  // the engine's stream continues when all three are done
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, e->ev_ov[2], 0);
+                if (ce == cudaSuccess) ce = cudaEventRecord(e->evp[2], st);
+                if (ce == cudaSuccess) ce = cudaEventRecord(e->evp[3], st);
+                return ce != cudaSuccess ? ce : cudaGetLastError();
+            }
             if (coop_w == 8)
                 apa_phase_pass_coop_kernel<8><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 4), 256, 0, st>>>(bd);
             else if (coop_w == 4)
@@ -1631,13 +1710,15 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 bd.n_order = (uint32_t)std::min<uint64_t>(w0 + wave_n, n_work);
                 CUDA_TRY(cudaMemsetAsync(e->d_queue + 24, 0, 3 * sizeof(unsigned long long), st));
                 CUDA_TRY(cudaEventRecord(e->evp[0], st));
+                if (overlap) CUDA_TRY(cudaEventRecord(e->ev_ov[0], st));
                 phase_kernel(0, phase_regs(0))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
                 b->stats.kernel_launches++;
                 CUDA_TRY(cudaEventRecord(e->evp[1], st));
                 // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
                 // the device (first-use module loading of another kernel, allocations) may be issued before the upload is
-                // done, so the pass / trace kernels are launched after upload_planes() below.
-                if (!host_streaming) CUDA_TRY(launch_pass_trace());
+                // done, so the pass / trace kernels of a back-to-back run are launched after stream_upload() below. Overlapped
+                // kernels go out at once: they wait for their pairs on the device, and every kernel was loaded at engine creation.
+                if (!host_streaming || overlap) CUDA_TRY(launch_pass_trace());
                 if (w0 + wave_n < n_work) {  // more waves follow: the arenas are reused
                     CUDA_TRY(cudaStreamSynchronize(st));
                     CUDA_TRY(add_phase_ms());
@@ -1666,7 +1747,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 cudaStreamSynchronize(st);
                 return rc;
             }
-            if (split) CUDA_TRY(launch_pass_trace());
+            if (split && !overlap) CUDA_TRY(launch_pass_trace());
         }
         CUDA_TRY(cudaMemcpyAsync(b->h_status.data(), b->d_status, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));

@@ -58,7 +58,9 @@ typedef struct apa_batch_stats {
     uint32_t pass_warps_per_pair, upload_mode, upload_chunks, waves;
     uint64_t dp_issue_steps; /* 32-row lane-steps ISSUED by the block DP: 32 lanes x anti-diagonals swept by every chunk (ramps, idle lanes
                                 and the feeder lane included); dp_word_steps / dp_issue_steps = lane utilisation */
-    uint32_t upload_chunks_raw, reserved0;
+    uint32_t upload_chunks_raw;
+    uint32_t overlapped; /* 1: the three phase kernels of the last run were launched together and overlapped at their tails
+                            (phase_ms then holds overlapping intervals: build = its own run, pass / trace = 0) */
 } apa_batch_stats;
 
 const char* apa_last_error(void);
