@@ -1011,6 +1011,14 @@ struct BatchGuard {
 // Page-locked host memory can be read by the copy engines directly: such inputs go to HBM as raw bytes and are packed
 // there (device-side K0). Pageable inputs are packed by host threads into a pinned staging buffer (4x fewer bytes through
 // the driver's pageable-copy path). APA_RAW=0 / 1 overrides the detection (1 is only safe for pinned buffers when streaming).
+// Nsight Compute / Systems inject into the process and may serialise kernel launches: a kernel that waits for data the host sends
+// after the launch (streamed upload) or for another kernel (overlapped phases) would then sit in its bounded wait. Under a
+// profiler the engine therefore uploads first and runs the kernels back to back (the same as APA_STREAM=0 APA_OVERLAP=0).
+static bool profiler_attached() {
+    static const bool on = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE");
+    return on;
+}
+
 static bool host_pinned(const void* p) {
     if (!p) return true;
     cudaPointerAttributes at{};
@@ -1080,7 +1088,7 @@ static int batch_prepare(apa_engine* e, uint64_t n_pairs, const uint8_t* a_all, 
     };
     if (n_pairs) {
         const uint64_t total = b->total_a + b->total_b;
-        const bool want_stream = defer_data && !(getenv("APA_STREAM") && atoi(getenv("APA_STREAM")) == 0);
+        const bool want_stream = defer_data && !(getenv("APA_STREAM") && atoi(getenv("APA_STREAM")) == 0) && !profiler_attached();
         const uint64_t n_chunks = want_stream ? std::min<uint64_t>(200, std::max<uint64_t>(1, total / (32ull << 20))) : 1;
         const uint64_t per = (total + n_chunks - 1) / n_chunks;
         uint64_t acc = 0, start = 0;
@@ -1648,7 +1656,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
         // One warp per pair, the whole batch in one wave: the three phase kernels are launched together (see BatchDev::phase_flag).
         // APA_OVERLAP=0 runs them back to back (per-kernel timings: bench.py measures its roofline numbers that way).
         const bool overlap = split && coop_w == 1 && wave_n == n_work && attempt == 0 && trace &&
-                             !(getenv("APA_OVERLAP") && atoi(getenv("APA_OVERLAP")) == 0);
+                             !(getenv("APA_OVERLAP") && atoi(getenv("APA_OVERLAP")) == 0) && !profiler_attached();
         bd.phase_flag = nullptr;
         if (overlap) {
             if (e->phase_flag_cap < n_work) {
@@ -1711,7 +1719,15 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 CUDA_TRY(cudaMemsetAsync(e->d_queue + 24, 0, 3 * sizeof(unsigned long long), st));
                 CUDA_TRY(cudaEventRecord(e->evp[0], st));
                 if (overlap) CUDA_TRY(cudaEventRecord(e->ev_ov[0], st));
-                phase_kernel(0, phase_regs(0))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+                // Overlapped under a streamed upload: the build kernel waits for data for the first ~20 ms anyway, so it leaves
+                // SM slots to the pass kernel from the start (APA_BUILD_CTAS per SM; the default was measured, profiles/README.md).
+                unsigned build_grid = grid;
+                if (overlap && streaming) {
+                    int per_sm = 9;
+                    if (const char* ev = getenv("APA_BUILD_CTAS")) per_sm = std::max(1, atoi(ev));
+                    build_grid = std::min<unsigned>(grid, (unsigned)(e->sm_count * per_sm));
+                }
+                phase_kernel(0, phase_regs(0))<<<build_grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
                 b->stats.kernel_launches++;
                 CUDA_TRY(cudaEventRecord(e->evp[1], st));
                 // With a streaming upload the build kernel spins until the bases arrive: nothing that may synchronise with
