@@ -384,11 +384,12 @@ class Engine:
                                         buf, cap, pos.ctypes.data))
         return buf.value.decode(), (int(pos[0]), int(pos[1])), (int(pos[2]), int(pos[3])), int(pos[4])
 
-    def block_compute(self, a: bytes, b: bytes, v=None):
-        """pa_bitpacking::simd::compute on the GPU with +1 top deltas. Returns (bottom_sum, h_out, v_out)."""
+    def block_compute(self, a: bytes, b: bytes, v=None, h=None):
+        """pa_bitpacking::simd::compute on the GPU. h: top-edge deltas, one byte per column (0, 1 = +1, 2 = -1; default all +1);
+        v: left-edge (p, m) u64 pairs per 64-row word (default all +1). Returns (bottom_sum, h_out, v_out)."""
         na, mb = len(a), len(b)
         nwords = (mb + 63) // 64
-        h = np.ones(max(na, 1), dtype=np.uint8)
+        h = np.ones(max(na, 1), dtype=np.uint8) if h is None else np.ascontiguousarray(h, dtype=np.uint8).copy()
         vv = np.zeros(2 * max(nwords, 1), dtype=np.uint64)
         if v is None:
             vv[0::2] = np.uint64(0xFFFFFFFFFFFFFFFF)

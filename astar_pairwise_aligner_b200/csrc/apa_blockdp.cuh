@@ -264,21 +264,28 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
 //   njs, nje  : rounded-out row range of the new block (multiples of 64)
 //   vout/cum  : nhw (p,m) words and nhw+1 running values of the new column
 //   fillvals  : if FILL, every column's V is also stored: fillvals[col * nhw + hw]   (simd::fill)
-// Horizontal deltas along the top edge are +1 (HMode::None, blocks.rs:728-734).
+// Horizontal deltas along the top edge: +1 when h_in is null (HMode::None / Output, blocks.rs:728-734), else h_in[col] (one byte per
+// column: bit0 = +1, bit1 = -1; HMode::Input / Update). When h_out is not null the deltas along the bottom edge are written there in
+// the same form (HMode::Output / Update); h_in and h_out may be the same array.
 // Returns the value at the bottom of the rounded range (bot_val); top_val is supplied by the caller.
 template <bool FILL>
 __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const BlkView& prev, int ncols, I njs, I nje,
                          uint2* __restrict__ vout, int32_t* __restrict__ cumout, Cost top_val_new, uint2* __restrict__ fillvals,
-                         DpCounters& dpc) {
+                         DpCounters& dpc, const uint8_t* h_in = nullptr, uint8_t* h_out = nullptr) {
     const int lane = threadIdx.x & 31;
     const int nhw = (nje - njs) >> 5;
+    if (h_in) {  // the first chunk takes its incoming deltas from shared memory like every later chunk does
+        for (int k = lane; k < ncols; k += 32) sm.hrow[k] = h_in[k];
+        __syncwarp();
+    }
     // chunks of at most 31 rows (the first chunk gives lane 0 to the feeder), evenly sized
     const int nchunks = (nhw + 30) / 31;
     const int per = nchunks ? (nhw + nchunks - 1) / nchunks : 0;
     Cost running = top_val_new;
     for (int c = 0; c < nchunks; c++) {
         const int nrow = min(per, nhw - per * c);
-        const int rl = c == 0 ? lane - 1 : lane;  // row of this lane inside the chunk
+        const bool feeder = c == 0 && !h_in;       // lane 0 of the first chunk feeds the +1 top edge
+        const int rl = feeder ? lane - 1 : lane;  // row of this lane inside the chunk
         const bool is_row = rl >= 0 && rl < nrow;
         const int hw = per * c + (is_row ? rl : 0);
         const I j0 = njs + 32 * hw;
@@ -296,9 +303,9 @@ __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const Bl
             b0 = bb.x;
             b1 = bb.y;
         }
-        const bool hand_off = (c + 1 < nchunks);
+        const bool hand_off = (c + 1 < nchunks) || h_out;
         uint2* fillcol = FILL ? fillvals + hw : nullptr;
-        if (c == 0) {
+        if (feeder) {
             if (hand_off)
                 dp_chunk<FILL, true, true>(sm, ncols, nrow + 1, b0, b1, vp, vm, fillcol, nhw);
             else
@@ -327,6 +334,10 @@ __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const Bl
     if (nchunks) dpc.issue_steps += 32ull * (unsigned long long)(nchunks * (ncols - 1) + nhw + 1);
     if (lane == 0) cumout[nhw] = running;
     __syncwarp();
+    if (h_out) {  // what the last chunk left in shared memory is the bottom edge (an empty range passes its top edge through)
+        for (int k = lane; k < ncols; k += 32) h_out[k] = nchunks ? sm.hrow[k] : (h_in ? h_in[k] : (uint8_t)1);
+        __syncwarp();
+    }
     return running;
 }
 

@@ -438,9 +438,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 12) apa_align_kernel_r40(B
     apa_align_body(bd, smem);
 }
 
-// Stand-alone block-DP rectangle (apa_block_compute): one warp, arbitrary top deltas are not needed by the hot
-// path (HMode::None only), so h_in must be all +1; h_out is reconstructed column by column for the KAT.
-__global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof, int nhw, uint2* v, int32_t* cum, uint2* fillvals) {
+// Stand-alone block-DP rectangle (apa_block_compute = pa_bitpacking::simd::compute with HMode::Update): one warp; h holds the
+// top-edge deltas on entry and the bottom-edge deltas on return (one byte per column: bit0 = +1, bit1 = -1).
+__global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof, int nhw, uint2* v, int32_t* cum, uint8_t* h) {
     __shared__ WarpSmem sm;
     tma_stage_reset(sm);
     const int lane = threadIdx.x & 31;
@@ -457,7 +457,7 @@ __global__ void apa_block_kernel(const uint2* aprof, int na, const uint2* bprof,
     for (int c0 = 0; c0 < na; c0 += BLOCK_W) {
         int nc = min(BLOCK_W, na - c0);
         stage_amask(sm, aprof, c0, nc, lane);
-        block_dp<true>(sm, bprof, prev, nc, 0, nhw * 32, v, cum, 0, fillvals + (size_t)c0 * nhw, ws);
+        block_dp<false>(sm, bprof, prev, nc, 0, nhw * 32, v, cum, 0, nullptr, ws, h + c0, h + c0);
         __syncwarp();
     }
 }
@@ -2416,10 +2416,12 @@ extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, c
     if (!e) return set_err(APA_ERR_NO_DEVICE, "null engine");
     CUDA_TRY(cudaSetDevice(e->device));
     for (uint64_t i = 0; i < na; i++)
-        if (h[i] != 1) return set_err(APA_ERR_BAD_INPUT, "apa_block_compute: top deltas must all be +1 (HMode::None)");
+        if (h[i] > 2) return set_err(APA_ERR_BAD_INPUT, "apa_block_compute: h holds 0 (0), 1 (+1) or 2 (-1) per column");
     const uint64_t nwords = (mb + 63) / 64, nhw = nwords * 2;
-    if (na == 0 || nhw == 0) {
-        *bottom_sum = (int64_t)na;
+    if (na == 0 || nhw == 0) {  // nothing to sweep: the top edge is the bottom edge
+        int64_t s = 0;
+        for (uint64_t i = 0; i < na; i++) s += h[i] == 1 ? 1 : (h[i] == 2 ? -1 : 0);
+        *bottom_sum = s;
         return APA_OK;
     }
     // host-side planes of a and b in the device layout (+2 padding half-words)
@@ -2433,47 +2435,36 @@ extern "C" int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, c
         vv[2 * w] = make_uint2((uint32_t)v[2 * w], (uint32_t)v[2 * w + 1]);
         vv[2 * w + 1] = make_uint2((uint32_t)(v[2 * w] >> 32), (uint32_t)(v[2 * w + 1] >> 32));
     }
-    uint2 *d_a = nullptr, *d_bp = nullptr, *d_v = nullptr, *d_fill = nullptr;
+    uint2 *d_a = nullptr, *d_bp = nullptr, *d_v = nullptr;
+    uint8_t* d_h = nullptr;
     int32_t* d_cum = nullptr;
     struct Free {  // the CUDA_TRYs below may return early
         void** p[5];
         ~Free() {
             for (void** q : p) cudaFree(*q);
         }
-    } free_all{{(void**)&d_a, (void**)&d_bp, (void**)&d_v, (void**)&d_fill, (void**)&d_cum}};
+    } free_all{{(void**)&d_a, (void**)&d_bp, (void**)&d_v, (void**)&d_h, (void**)&d_cum}};
+    cudaStream_t st = e->stream;
     CUDA_TRY(cudaMalloc(&d_a, (nhw_a + 2) * 8));
     CUDA_TRY(cudaMalloc(&d_bp, (nhw + 2) * 8));
     CUDA_TRY(cudaMalloc(&d_v, nhw * 8));
     CUDA_TRY(cudaMalloc(&d_cum, (nhw + 1) * 4));
-    CUDA_TRY(cudaMalloc(&d_fill, na * nhw * 8));
-    CUDA_TRY(cudaMemcpy(d_a, apl.data(), (nhw_a + 2) * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d_bp, bp.data(), (nhw + 2) * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d_v, vv.data(), nhw * 8, cudaMemcpyHostToDevice));
-    apa_block_kernel<<<1, 32, 0, e->stream>>>(d_a, (int)na, d_bp, (int)nhw, d_v, d_cum, d_fill);
+    CUDA_TRY(cudaMalloc(&d_h, na));
+    CUDA_TRY(cudaMemcpyAsync(d_a, apl.data(), (nhw_a + 2) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_bp, bp.data(), (nhw + 2) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_v, vv.data(), nhw * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_h, h, na, cudaMemcpyHostToDevice, st));
+    apa_block_kernel<<<1, 32, 0, st>>>(d_a, (int)na, d_bp, (int)nhw, d_v, d_cum, d_h);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
-    std::vector<uint2> fill(na * nhw);
-    std::vector<uint2> vin = vv;
-    CUDA_TRY(cudaMemcpy(vv.data(), d_v, nhw * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(fill.data(), d_fill, na * nhw * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(vv.data(), d_v, nhw * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h, d_h, na, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     for (uint64_t w = 0; w < nwords; w++) {
         v[2 * w] = (uint64_t)vv[2 * w].x | ((uint64_t)vv[2 * w + 1].x << 32);
         v[2 * w + 1] = (uint64_t)vv[2 * w].y | ((uint64_t)vv[2 * w + 1].y << 32);
     }
-    // bottom deltas: D[i][bot] - D[i-1][bot] = 1 + sum_col(i) - sum_col(i-1), with top-row deltas +1.
-    auto colsum = [&](const uint2* col) {
-        int64_t s = 0;
-        for (uint64_t hw = 0; hw < nhw; hw++) s += __builtin_popcount(col[hw].x) - __builtin_popcount(col[hw].y);
-        return s;
-    };
-    int64_t prev = colsum(vin.data()), total = 0;
-    for (uint64_t i = 0; i < na; i++) {
-        int64_t cur = colsum(&fill[i * nhw]);
-        int64_t d = 1 + cur - prev;
-        h[i] = d == 1 ? 1 : (d == -1 ? 2 : 0);
-        total += d;
-        prev = cur;
-    }
+    int64_t total = 0;
+    for (uint64_t i = 0; i < na; i++) total += h[i] == 1 ? 1 : (h[i] == 2 ? -1 : 0);
     *bottom_sum = total;
     return APA_OK;
 }

@@ -216,9 +216,10 @@ int apa_search_trace(apa_engine* e, const uint8_t* pattern, uint64_t pattern_len
  * 4 IMAD per step running next to them on the FMA pipe, out[6] = those IMADs per second; out[5] = the device clock attribute in Hz. */
 int apa_int32_peak(apa_engine* e, double* out /* 7 doubles */);
 
-/* Block-DP kernel on its own (pa_bitpacking::simd::compute semantics, pa-bitpacking/src/simd.rs:98-226):
- * rectangle a[na] x b[mb]; h one byte per column (bit0 = +1, bit1 = -1), in/out; v interleaved (p,m) u64 pairs
- * per 64-row word, in/out. Returns the sum of the bottom-row deltas via *bottom_sum. */
+/* Block-DP kernel on its own (pa_bitpacking::simd::compute semantics, pa-bitpacking/src/simd.rs:98-226, HMode::Update of
+ * astarpa2/src/blocks.rs:665-748): rectangle a[na] x b[mb]; h one byte per column (0, 1 = +1, 2 = -1): the deltas along the top
+ * edge on entry, along the bottom edge on return; v interleaved (p,m) u64 pairs per 64-row word, in/out. *bottom_sum = sum of
+ * the returned bottom deltas. */
 int apa_block_compute(apa_engine* e, const uint8_t* a, uint64_t na, const uint8_t* b, uint64_t mb, uint8_t* h, uint64_t* v,
                       int64_t* bottom_sum);
 

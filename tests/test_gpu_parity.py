@@ -60,6 +60,25 @@ def test_block_kernel_kat_gpu(apa, oracle, engine, h):
         assert (v == vout).all()
 
 
+def test_block_kernel_hmode_update_gpu(apa, oracle, engine):
+    # HMode::Update (astarpa2/src/blocks.rs:665-748): arbitrary deltas along the top edge in, the bottom edge out, arbitrary left
+    # column - what incremental doubling feeds the kernel. Random +1 / 0 / -1 top deltas and random consistent left columns
+    # against the oracle's bp_compute, single- and multi-chunk heights, partial last slab.
+    rng = np.random.default_rng(3)
+    for na, h in [(1, 64), (37, 64), (256, 128), (300, 1024), (700, 2112), (256, 4096)]:
+        a, _ = apa.generate_pair(na, 0.0, 0, 11 + na)
+        b, _ = apa.generate_pair(h, 0.0, 0, 13 + h)
+        hin = rng.integers(0, 3, size=na).astype(np.uint8)
+        p = rng.integers(0, 1 << 62, size=h // 64, dtype=np.uint64) * np.uint64(3)
+        m = rng.integers(0, 1 << 62, size=h // 64, dtype=np.uint64) & ~p
+        v = np.zeros(2 * (h // 64), dtype=np.uint64)
+        v[0::2], v[1::2] = p, m
+        s, hout, vout = engine.block_compute(a, b, v=v.copy(), h=hin)
+        hb, vo = hin.copy(), v.copy()
+        so = oracle.lib().oracle_bp_compute(a, len(a), b, len(b), hb.ctypes.data, vo.ctypes.data)
+        assert (hb == hout).all() and (vo == vout).all() and so == s, (na, h)
+
+
 @pytest.mark.parametrize("preset", PRESETS)
 def test_golden_pairs_gpu(apa, oracle, preset):
     pairs = [(p["a"].encode(), p["b"].encode()) for p in GOLD["pairs"]]
