@@ -24,8 +24,12 @@ struct PairCtx {
     int nblk_alloc;      // blocks.len() of the reference: entries [0, nblk_alloc) hold ranges of an earlier pass
     int last_idx;        // Blocks.last_block_idx: survives from one pass to the next (see dev_pass, column 0)
     uint32_t v_base;     // start of the V region in the arena (bytes)
-    uint32_t v_top;      // bump pointer
-    uint32_t hi_bot;     // lowest byte used by the downward-growing region at the arena end (CIGAR elements)
+    uint32_t v_top;      // bump pointer of block store A (odd passes), growing up from v_base; later the traceback scratch
+    uint32_t hi_bot;     // lowest byte used from the arena end: block store B (even passes, incremental doubling only), growing
+                         // down; later the CIGAR elements
+    uint32_t cig_top;    // where the CIGAR elements grow down from: the arena end, or the bottom of store B when the final pass lives there
+    uint32_t hrow_off;   // incremental doubling: the pair's row of horizontal deltas, one byte per column of a (Blocks.h, blocks.rs:106)
+    int incremental;     // BlockParams.incremental_doubling (astarpa2_full: true, astarpa2_simple: false; params.rs:88,119)
     int status;          // ST_PENDING while healthy
     // stats
     DpCounters dpc;  // block-DP lane-steps: useful / issued
@@ -90,6 +94,20 @@ __device__ __forceinline__ uint32_t arena_alloc(PairCtx& cx, uint32_t bytes) {
     uint32_t off = cx.v_top;
     cx.v_top += bytes;
     return off;
+}
+
+// Block store of the current pass: A grows up from v_base (odd passes, and every pass without incremental doubling), B grows
+// down from the arena end (even passes with incremental doubling) - the store of the previous pass stays readable meanwhile.
+__device__ __forceinline__ bool store_is_b(const PairCtx& cx) { return cx.incremental && (cx.passes & 1) == 0; }
+__device__ __forceinline__ uint32_t store_alloc(PairCtx& cx, uint32_t bytes) {
+    if (!store_is_b(cx)) return arena_alloc(cx, bytes);
+    bytes = (bytes + 15u) & ~15u;
+    if ((uint64_t)cx.v_top + bytes > (uint64_t)cx.hi_bot) {
+        cx.status = ST_OVERFLOW;
+        return 0xffffffffu;
+    }
+    cx.hi_bot -= bytes;
+    return cx.hi_bot;
 }
 
 __device__ __forceinline__ BlkView view_of(const PairCtx& cx, const BlkMeta& mt) {
@@ -239,9 +257,10 @@ constexpr Cost PASS_NONE = -1;
 // Right-edge column of the next block on one warp: stage the bases of the block's columns, then sweep (see run_block_dp in
 // apa_coop.cuh for the variant where the warps of a CTA share the chunks of a tall band).
 __device__ __forceinline__ Cost run_block_dp(WarpSmem& sm, PairCtx& cx, const BlkView& prev, I is, int ncols, I njs, I nje,
-                                             uint2* vout, int32_t* cumout, Cost top_val) {
+                                             uint2* vout, int32_t* cumout, Cost top_val, const uint8_t* h_in = nullptr,
+                                             uint8_t* h_out = nullptr) {
     stage_amask(sm, cx.aprof, is, ncols, threadIdx.x & 31);
-    return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc);
+    return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc, h_in, h_out);
 }
 
 template <class Hh, class SM>
@@ -253,7 +272,14 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
         hh.update_contours();
         APA_TOC(cx.tphase[7], t_u0);
     }
-    cx.v_top = cx.v_base;  // blocks are recomputed in every pass
+    // The block store of this pass starts empty; with incremental doubling the other store still holds the previous pass.
+    if (!cx.incremental) {
+        cx.v_top = cx.v_base;
+    } else if (store_is_b(cx)) {
+        cx.hi_bot = cx.arena_size;
+    } else {
+        cx.v_top = cx.v_base;
+    }
 
     // Column 0 (domain.rs:395-413, blocks.rs:146-179).
     BlkMeta* meta = cx.meta;
@@ -284,6 +310,9 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
         nm.v_off = 0;
         nm.col_s = -1;
         nm.col_e = 0;
+        nm.j_h = J_H_NONE;
+        nm.store_pass = cx.passes;
+        nm.pad_[0] = nm.pad_[1] = 0;
         __syncwarp();
         if (lane == 0) meta[0] = nm;
         __syncwarp();
@@ -305,18 +334,87 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
         bool reuse = existed && old.js == jr.s && old.je == jr.e && all_reused;
         all_reused = all_reused && reuse;
 
-        // Blocks::compute_next_block (blocks.rs:205-545), always from scratch.
+        // Blocks::compute_next_block (blocks.rs:205-545). Without incremental doubling the block is computed from scratch. With
+        // it (blocks.rs:342-469): rows the previous pass had fixed are kept and only the rest is computed, in up to three
+        // ranges around the old and the new j_h - the row along which the pair's h row carries the horizontal deltas from one
+        // pass to the next. A reused block (domain.rs:449-455, blocks.rs:190-197) is not computed at all: its column, fixed range
+        // and j_h carry over (the column is copied into this pass's store).
         JRange rounded = jr_round_out(jr);
         int nhw = (rounded.e - rounded.s) >> 5;
-        uint32_t off = arena_alloc(cx, (uint32_t)nhw * 8u + (uint32_t)(nhw + 1) * 4u);
+        if (cx.incremental && reuse && old.store_pass == cx.passes - 1) {
+            rounded = JRange{old.js, old.je};
+            nhw = (rounded.e - rounded.s) >> 5;
+        }
+        uint32_t off = store_alloc(cx, (uint32_t)nhw * 8u + (uint32_t)(nhw + 1) * 4u);
         if (cx.status != ST_PENDING) return PASS_NONE;
         Cost top_val = blk_index(prev, rounded.s) + (ie - is);
         uint2* vout = (uint2*)(cx.arena + off);
         int32_t* cumout = (int32_t*)(cx.arena + off + (size_t)nhw * 8);
         long long t_dp0 = APA_TIC();
-        Cost bot_val = run_block_dp(sm, cx, prev, is, ie - is, rounded.s, rounded.e, vout, cumout, top_val);
+        Cost bot_val;
+        I new_j_h = J_H_NONE;
+        const bool old_v = existed && old.store_pass == cx.passes - 1;  // the old column is still in the other store
+        if (cx.incremental && reuse && old_v) {
+            const uint2* ov = (const uint2*)(cx.arena + old.v_off);
+            const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)nhw * 8);
+            for (int k = lane; k < nhw; k += 32) vout[k] = ov[k];
+            for (int k = lane; k <= nhw; k += 32) cumout[k] = oc[k];
+            __syncwarp();
+            top_val = old.top_val;
+            bot_val = old.bot_val;
+            new_j_h = old.j_h;
+        } else if (!cx.incremental || !pm.has_fixed) {
+            bot_val = run_block_dp(sm, cx, prev, is, ie - is, rounded.s, rounded.e, vout, cumout, top_val);
+            cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
+        } else {
+            const JRange pfix = jr_round_in(JRange{pm.fs, pm.fe});
+            new_j_h = pfix.e;
+            uint8_t* hrow = cx.arena + cx.hrow_off + is;
+            // the reference asserts these orders (blocks.rs:388-397,427-430); a violation is a panic there
+            if (new_j_h < rounded.s || new_j_h > rounded.e) {
+                cx.status = ST_ASSERT;
+                return PASS_NONE;
+            }
+            const int ncols = ie - is;
+            auto region = [&](I rs, I re, Cost start_val, const uint8_t* h_in, uint8_t* h_out) -> Cost {
+                const int o = (rs - rounded.s) >> 5;
+                cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(re - rs);
+                return run_block_dp(sm, cx, prev, is, ncols, rs, re, vout + o, cumout + o, start_val, h_in, h_out);
+            };
+            const bool three = old_v && old.j_h != J_H_NONE && old.has_fixed && next_mult64(old.fs - 1) < old.j_h;
+            if (three) {
+                const I ps = next_mult64(old.fs - 1), pe = old.j_h;  // preserved rows [ps, pe): round_in(old_fixed.0 - 1 .. old_j_h)
+                if (pe > new_j_h || ps < rounded.s || rounded.s > old.js || pe > old.je) {  // "j_h may only increase!" and friends
+                    cx.status = ST_ASSERT;
+                    return PASS_NONE;
+                }
+                // range 0: everything above the preserved part, from the +1 top edge, h row untouched
+                if (ps > rounded.s) region(rounded.s, ps, top_val, nullptr, nullptr);
+                // preserved part: the old column's words and running values
+                {
+                    const int old_nhw = (old.je - old.js) >> 5;
+                    const uint2* ov = (const uint2*)(cx.arena + old.v_off);
+                    const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)old_nhw * 8);
+                    const int o_new = (ps - rounded.s) >> 5, o_old = (ps - old.js) >> 5, cnt = (pe - ps) >> 5;
+                    for (int k = lane; k < cnt; k += 32) {
+                        vout[o_new + k] = ov[o_old + k];
+                        cumout[o_new + k] = oc[o_old + k];
+                    }
+                    __syncwarp();
+                    const Cost at_pe = oc[(pe - old.js) >> 5];  // value at (ie, old_j_h): exact, the row was fixed
+                    // range 1: old j_h .. new j_h, h row in and out (an empty range leaves the h row as it is)
+                    Cost run = at_pe;
+                    if (new_j_h > pe) run = region(pe, new_j_h, at_pe, hrow, hrow);
+                    // range 2: below the new j_h, h row in
+                    bot_val = region(new_j_h, rounded.e, run, hrow, nullptr);
+                }
+            } else {
+                // range 01: everything above the new j_h from the +1 top edge, its bottom edge becomes the h row
+                const Cost run = region(rounded.s, new_j_h, top_val, nullptr, hrow);
+                bot_val = region(new_j_h, rounded.e, run, hrow, nullptr);
+            }
+        }
         APA_TOC(cx.tphase[1], t_dp0);
-        cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
 
         BlkMeta nm;
         nm.orig_s = reuse ? old.orig_s : jr.s;
@@ -329,6 +427,9 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
         nm.ones = 0;
         nm.col_s = is;
         nm.col_e = ie;
+        nm.j_h = new_j_h;
+        nm.store_pass = cx.passes;
+        nm.pad_[0] = nm.pad_[1] = 0;
         BlkView cur;
         cur.js = rounded.s;
         cur.je = rounded.e;
@@ -384,6 +485,19 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
 // band::exponential_search / linear_search driven by cost_or_align (band.rs:100-190, lib.rs:122-175). The presets use
 // BandDoubling{start: H0, factor: 2}: offset = h0, s0 = max(1, block_width) = 256. Returns the cost; the blocks of the
 // final pass stay in the arena.
+// After the last pass only its own block store matters: the traceback scratch grows up from behind store A (or from v_base when
+// the final columns live in store B), the CIGAR elements grow down from the arena end (or from the bottom of store B).
+__device__ __forceinline__ void arena_after_passes(PairCtx& cx) {
+    cx.cig_top = cx.arena_size;
+    if (!cx.incremental) return;
+    if (store_is_b(cx)) {
+        cx.v_top = cx.v_base;
+        cx.cig_top = cx.hi_bot;
+    } else {
+        cx.hi_bot = cx.arena_size;
+    }
+}
+
 template <class Hh, class SM>
 __device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
     Cost offset = h0;
@@ -395,6 +509,7 @@ __device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
     if (cx.par.doubling == 0) {  // DoublingType::None: one pass without a bound (lib.rs:126-130)
         Cost cost = dev_pass(cx, sm, hh, F_MAX_NONE);
         if (cx.status == ST_PENDING && cost == PASS_NONE) cx.status = ST_ASSERT;  // .unwrap()
+        arena_after_passes(cx);
         return cost;
     }
     {
@@ -424,6 +539,7 @@ __device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
                     cx.status = ST_ASSERT;
                     return -1;
                 }
+                arena_after_passes(cx);
                 return cost;
             }
             maxs = min(maxs, cost);

@@ -62,5 +62,6 @@ struct RunParams {
     int block_width;   // 1 ..= 256
     int dt_trace, max_g, fr_drop;  // BlockParams (blocks.rs:31-74); sparse = true always
     int sparse_h, prune;
+    int incremental;   // BlockParams.incremental_doubling
 };
 cudaError_t apa_general_launch(const BatchDev& bd, const RunParams& par, unsigned grid, cudaStream_t st);

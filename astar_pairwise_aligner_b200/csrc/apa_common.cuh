@@ -83,8 +83,12 @@ struct BlkMeta {
     uint16_t has_fixed;
     uint16_t ones;      // column 0: all vertical deltas +1, nothing stored
     I col_s, col_e;     // i_range (left-exclusive)
+    I j_h;              // Block.j_h (block.rs:30): row along which the pair's h row holds this block's horizontal deltas; J_H_NONE = None
+    int32_t store_pass; // pass that wrote the V column at v_off: the column is still there during the NEXT pass only (two block stores)
+    int32_t pad_[2];
 };
-static_assert(sizeof(BlkMeta) == 48, "BlkMeta layout");
+static_assert(sizeof(BlkMeta) == 64, "BlkMeta layout");
+constexpr I J_H_NONE = INT32_MIN;
 
 // A read-only view of a stored right-edge column: V as (p,m) per 32-row half-word + running values.
 struct BlkView {

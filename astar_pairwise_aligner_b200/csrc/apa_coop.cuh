@@ -22,6 +22,8 @@ struct CoopSmem {
     WarpSmem lead;  // the leader's own scratch; lead.achar (bases of the block's columns) is read by every warp
     // job descriptor, written by the leader before the START barrier
     int quit;
+    int h_first;  // 1: the top edge of the range is +1 (chunk 0 has the feeder lane); 0: chunk 0 takes its deltas from ring slot W
+    int h_keep;   // 1: the last chunk publishes its bottom deltas too (they become the pair's h row)
     int ncols, nhw, nchunks, per;
     I njs;
     Cost top_val;
@@ -135,7 +137,8 @@ __device__ __forceinline__ Cost coop_work(CoopSmem<W>& cs, int wid) {
     int32_t* cumout = cs.cumout;
     for (int c = wid; c < nchunks; c += W) {
         const int nrow = min(per, nhw - per * c);
-        const int rl = c == 0 ? lane - 1 : lane;
+        const bool feeder = c == 0 && cs.h_first;
+        const int rl = feeder ? lane - 1 : lane;
         const bool is_row = rl >= 0 && rl < nrow;
         const int hw = per * c + (is_row ? rl : 0);
         const I j0 = njs + 32 * hw;
@@ -152,7 +155,7 @@ __device__ __forceinline__ Cost coop_work(CoopSmem<W>& cs, int wid) {
             b0 = bb.x;
             b1 = bb.y;
         }
-        coop_chunk<W>(cs, wid, c, ncols, c == 0 ? nrow + 1 : nrow, c == 0, c + 1 < nchunks, b0, b1, vp, vm);
+        coop_chunk<W>(cs, wid, c, ncols, feeder ? nrow + 1 : nrow, feeder, c + 1 < nchunks || cs.h_keep, b0, b1, vp, vm);
         __syncwarp();
         if (is_row) vout[hw] = make_uint2(vp, vm);
         const int val = is_row ? (__popc(vp) - __popc(vm)) : 0;
@@ -184,7 +187,7 @@ __device__ __forceinline__ Cost coop_work(CoopSmem<W>& cs, int wid) {
         }
         base += cs.top_val;
         const int nrow = min(per, nhw - per * c);
-        const int rl = c == 0 ? lane - 1 : lane;
+        const int rl = (c == 0 && cs.h_first) ? lane - 1 : lane;
         if (rl >= 0 && rl < nrow) cumout[per * c + rl] += base;
     }
     if (wid == 0 && lane == 0) cumout[nhw] = cs.top_val + total;
@@ -195,15 +198,21 @@ __device__ __forceinline__ Cost coop_work(CoopSmem<W>& cs, int wid) {
 // Leader side of a block (the dev_pass hook): blocks with a single chunk, or too many, run on the leader alone.
 template <int W>
 __device__ __forceinline__ Cost run_block_dp(CoopSmem<W>& cs, PairCtx& cx, const BlkView& prev, I is, int ncols, I njs, I nje,
-                                             uint2* vout, int32_t* cumout, Cost top_val) {
+                                             uint2* vout, int32_t* cumout, Cost top_val, const uint8_t* h_in = nullptr,
+                                             uint8_t* h_out = nullptr) {
     const int lane = threadIdx.x & 31;
     const int nhw = (nje - njs) >> 5;
     const int nchunks = (nhw + 30) / 31;
     stage_amask(cs.lead, cx.aprof, is, ncols, lane);
     if (nchunks < 2 || nchunks > COOP_MAX_CHUNKS)
-        return block_dp<false>(cs.lead, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc);
+        return block_dp<false>(cs.lead, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc, h_in, h_out);
+    if (h_in)  // the top-edge deltas of the range: ring slot W is what chunk 0 reads as "the chunk above" (its progress word
+               // starts at -1, which is past everything chunk 0 asks for); the slot is next written by chunk W, on this warp
+        for (int k = lane; k < ncols; k += 32) cs.hrow[W][k] = h_in[k];
     if (lane == 0) {
         cs.quit = 0;
+        cs.h_first = h_in ? 0 : 1;
+        cs.h_keep = h_out ? 1 : 0;
         cs.ncols = ncols;
         cs.nhw = nhw;
         cs.nchunks = nchunks;
@@ -223,7 +232,13 @@ __device__ __forceinline__ Cost run_block_dp(CoopSmem<W>& cs, PairCtx& cx, const
     coop_bar<W>(COOP_BAR_START);
     cx.dpc.word_steps += (unsigned long long)ncols * (unsigned long long)nhw;
     cx.dpc.issue_steps += 32ull * (unsigned long long)(((nhw + 30) / 31) * (ncols - 1) + nhw + 1);  // chunks of 31 half-words, as block_dp counts
-    return coop_work<W>(cs, 0);
+    const Cost bot = coop_work<W>(cs, 0);
+    if (h_out) {  // (after the END barrier) the bottom deltas of the last chunk are the new h row of these columns
+        const uint8_t* last = cs.hrow[(nchunks - 1) % (W + 1)];
+        for (int k = lane; k < ncols; k += 32) h_out[k] = last[k];
+        __syncwarp();
+    }
+    return bot;
 }
 
 // Warps 1 .. W-1 of a cooperative CTA: serve blocks until the leader says quit.

@@ -106,8 +106,12 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.meta = (BlkMeta*)arena;
         uint32_t meta_bytes = ((uint32_t)(cx.nblk + 1) * (uint32_t)sizeof(BlkMeta) + 15u) & ~15u;
         cx.v_base = meta_bytes;
-        cx.v_top = meta_bytes;
+        cx.incremental = bd.preset == APA_PRESET_FULL;  // params.rs:88,119
+        cx.hrow_off = cx.v_base;
+        if (cx.incremental) cx.v_base += ((uint32_t)cx.n + 31u) & ~15u;
+        cx.v_top = cx.v_base;
         cx.hi_bot = bd.arena_size;
+        cx.cig_top = bd.arena_size;
         cx.status = ST_PENDING;
         cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
         cx.passes = 0;
@@ -116,7 +120,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.dbg = bd.dbg;
         cx.dbg_cap = bd.dbg_cap;
         cx.dbg_n = 0;
-        if (meta_bytes + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
+        if ((uint64_t)cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
         if (!landed) cx.status = ST_ASSERT;
         else if (pack_pair(bd, p, cx.n, cx.m, landed, sm)) cx.status = ST_BAD_INPUT;
 
@@ -153,7 +157,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         if (cx.status == ST_PENDING && bd.trace) {
             CigarWriter cw;
             cw.arena = arena;
-            cw.arena_size = bd.arena_size;
+            cw.arena_size = cx.cig_top;
             cw.count = 0;
             cw.pend_cnt = 0;
             cw.pend_op = 0;
@@ -266,8 +270,12 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             cx.meta = (BlkMeta*)(arena + ARENA_HEADER);
             uint32_t meta_bytes = ((uint32_t)(cx.nblk + 1) * (uint32_t)sizeof(BlkMeta) + 15u) & ~15u;
             cx.v_base = ARENA_HEADER + meta_bytes;
+            cx.incremental = bd.preset == APA_PRESET_FULL;  // params.rs:88,119
+            cx.hrow_off = cx.v_base;
+            if (cx.incremental) cx.v_base += ((uint32_t)cx.n + 31u) & ~15u;
             cx.v_top = cx.v_base;
             cx.hi_bot = bd.arena_size;
+            cx.cig_top = bd.arena_size;
             cx.status = ST_PENDING;
             cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
             cx.passes = 0;
@@ -276,7 +284,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             cx.dbg = bd.dbg;
             cx.dbg_cap = bd.dbg_cap;
             cx.dbg_n = 0;
-            if (cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
+            if ((uint64_t)cx.v_base + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
             if (!landed) cx.status = ST_ASSERT;
             else if (pack_pair(bd, p, cx.n, cx.m, landed, sm)) cx.status = ST_BAD_INPUT;
             GcshH hh;
@@ -335,7 +343,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
         if constexpr (PHASE == 2) if (cx.status == ST_PENDING && bd.trace) {
             CigarWriter cw;
             cw.arena = arena;
-            cw.arena_size = bd.arena_size;
+            cw.arena_size = cx.cig_top;
             cw.count = 0;
             cw.pend_cnt = 0;
             cw.pend_op = 0;
@@ -1416,6 +1424,8 @@ static uint32_t estimate_arena(const apa_batch* b, int preset, int trace, const 
                                : std::min<uint64_t>((uint64_t)b->max_m + 64, 2048);
     if (gp && gp->domain == APA_DOMAIN_FULL) band_rows = (uint64_t)b->max_m + 64;
     uint64_t vcols = nblk * (band_rows / 32 * 12 + 16);
+    const bool incremental = gp ? gp->incremental != 0 : preset == APA_PRESET_FULL;
+    if (incremental) vcols = 2 * vcols + (uint64_t)b->max_n + 64;  // two block stores (this pass and the previous one) + the h row
     uint64_t tr = trace ? (DT_CACHE_ELEMS * 8 + 256 * (band_rows / 32) * 8 / 4 + (uint64_t)(b->max_n + b->max_m) / 4 * 4 + 65536) : 0;
     uint64_t heur = gcsh ? 24ull * (uint64_t)b->max_n + 65536 : 0;  // k-mer table, matches, contours
     uint64_t s = ARENA_HEADER + meta + vcols + tr + heur + 16384;
@@ -1457,6 +1467,7 @@ static int validate_params(const apa_params* q, RunParams* out) {
     out->max_g = q->max_g;
     out->fr_drop = q->fr_drop;
     out->sparse_h = q->sparse_h != 0;
+    out->incremental = q->incremental_doubling != 0;
     out->prune = q->prune != 0;
     return APA_OK;
 }

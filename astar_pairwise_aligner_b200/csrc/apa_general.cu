@@ -43,8 +43,12 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
         const uint64_t meta_bytes64 = ((uint64_t)(cx.nblk + 1) * sizeof(BlkMeta) + 15u) & ~15ull;
         const uint32_t meta_bytes = (uint32_t)min(meta_bytes64, (uint64_t)0xffffffffu);
         cx.v_base = meta_bytes;
-        cx.v_top = meta_bytes;
+        cx.incremental = par.incremental != 0;
+        cx.hrow_off = cx.v_base;
+        if (cx.incremental) cx.v_base += ((uint32_t)cx.n + 31u) & ~15u;
+        cx.v_top = cx.v_base;
         cx.hi_bot = bd.arena_size;
+        cx.cig_top = bd.arena_size;
         cx.status = ST_PENDING;
         cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
         cx.passes = 0;
@@ -53,7 +57,7 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
         cx.dbg = bd.dbg;
         cx.dbg_cap = bd.dbg_cap;
         cx.dbg_n = 0;
-        if (meta_bytes64 + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
+        if (meta_bytes64 + (uint64_t)cx.n + 4096u > bd.arena_size) cx.status = ST_OVERFLOW;
 
         Cost cost = -1;
         long long cig_off = -1, cig_len = 0;
@@ -90,7 +94,7 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
         if (cx.status == ST_PENDING && bd.trace) {
             CigarWriter cw;
             cw.arena = arena;
-            cw.arena_size = bd.arena_size;
+            cw.arena_size = cx.cig_top;
             cw.count = 0;
             cw.pend_cnt = 0;
             cw.pend_op = 0;

@@ -25,7 +25,7 @@ __device__ __forceinline__ void sts_i32(uint32_t addr, int v) { asm volatile("st
 
 struct CigarWriter {  // elements are pushed newest-first (the path is walked from the end); see emit_cigar_text.
     uint8_t* arena;
-    uint32_t arena_size;
+    uint32_t arena_size; // the elements grow down from here: PairCtx::cig_top (the arena end, or the bottom of block store B)
     uint32_t count;      // elements already stored in the arena
     uint32_t pend_op;    // pending (mergeable) element
     uint32_t pend_cnt;   // 0 = none
@@ -38,16 +38,16 @@ __device__ __forceinline__ void cig_drain(PairCtx& cx, CigarWriter& cw) {
     if (cw.nbuf == 0) return;
     const uint64_t need64 = ((uint64_t)cw.count + cw.nbuf) * 4u;  // 64-bit: must not wrap past the arena size
     const uint32_t need = (uint32_t)need64;
-    if (need64 > cx.arena_size || cx.arena_size - need < cx.v_top) {
+    if (need64 > cw.arena_size || cw.arena_size - need < cx.v_top) {
         cx.status = ST_OVERFLOW;
         cw.nbuf = 0;
         return;
     }
     const uint32_t lane = threadIdx.x & 31;
-    if (lane < cw.nbuf) *(uint32_t*)(cw.arena + cx.arena_size - 4u * (cw.count + lane + 1u)) = cw.buf;
+    if (lane < cw.nbuf) *(uint32_t*)(cw.arena + cw.arena_size - 4u * (cw.count + lane + 1u)) = cw.buf;
     cw.count += cw.nbuf;
     cw.nbuf = 0;
-    cx.hi_bot = cx.arena_size - need;
+    cx.hi_bot = cw.arena_size - need;
 }
 __device__ __forceinline__ void cig_store(PairCtx& cx, CigarWriter& cw, uint32_t op, uint32_t cnt) {
     // cig_pack keeps 30 bits of count: pend_cnt is capped below 2^30 by cig_push, which starts a new element instead
