@@ -504,12 +504,15 @@ def test_incremental_doubling_cells_gpu(apa, oracle):
     # Incremental doubling and block reuse as WORK SAVERS (astarpa2/src/blocks.rs:190-197,342-469): on multi-pass pairs the cells
     # the GPU evaluates (64 * lanes * cols of every computed range) stay within 10 % of the reference's BlockStats count, one
     # warp per pair and with a whole CTA per pair; results are those of the oracle as everywhere else.
-    pairs = [apa.generate_pair(n, e, m, 70 + n) for n, e, m in [(20000, 0.15, 0), (30000, 0.25, 1), (50000, 0.1, 2), (100000, 0.15, 0)]]
+    pairs = [apa.generate_pair(n, e, m, 70 + n) for n, e, m in [(20000, 0.15, 0), (100000, 0.15, 0), (20000, 0.3, 0), (40000, 0.3, 3),
+                                                                (60000, 0.2, 0), (10000, 0.4, 0)]]
     for preset in (1, 2, 3):
-        aligner = apa.AstarPa2(1, True) if preset == 1 else apa.AstarPa2(params_for(apa, preset), True)
-        costs, cigars, stats = aligner.align_batch_with_stats(pairs)
-        for (a, b), c, cg, st in zip(pairs, costs, cigars, stats):
-            oc, ocg, ost = oracle.align(a, b, preset, True)
-            assert (int(c), cg) == (oc, ocg)
-            assert st["f_max_tries"] == ost["f_max_tries"] >= 2
-            assert ost["computed_cells"] <= st["computed_cells"] <= 1.1 * ost["computed_cells"], (preset, len(a), st["computed_cells"], ost["computed_cells"])
+        aligners = [apa.AstarPa2(params_for(apa, preset), True)] + ([apa.AstarPa2(1, True)] if preset == 1 else [])
+        for aligner in aligners:
+            costs, cigars, stats = aligner.align_batch_with_stats(pairs)
+            for (a, b), c, cg, st in zip(pairs, costs, cigars, stats):
+                oc, ocg, ost = oracle.align(a, b, preset, True)
+                assert (int(c), cg) == (oc, ocg)
+                assert st["f_max_tries"] == ost["f_max_tries"] >= 3  # 3 .. 7 passes each (the oracle says)
+                assert ost["computed_cells"] <= st["computed_cells"] <= 1.1 * ost["computed_cells"], \
+                    (preset, len(a), st["computed_cells"], ost["computed_cells"])
