@@ -258,9 +258,9 @@ constexpr Cost PASS_NONE = -1;
 // apa_coop.cuh for the variant where the warps of a CTA share the chunks of a tall band).
 __device__ __forceinline__ Cost run_block_dp(WarpSmem& sm, PairCtx& cx, const BlkView& prev, I is, int ncols, I njs, I nje,
                                              uint2* vout, int32_t* cumout, Cost top_val, const uint8_t* h_in = nullptr,
-                                             uint8_t* h_out = nullptr) {
+                                             uint8_t* h_out = nullptr, int tap_hw = -1, uint8_t* h_tap = nullptr) {
     stage_amask(sm, cx.aprof, is, ncols, threadIdx.x & 31);
-    return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc, h_in, h_out);
+    return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc, h_in, h_out, tap_hw, h_tap);
 }
 
 template <class Hh, class SM>
@@ -363,7 +363,9 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
             top_val = old.top_val;
             bot_val = old.bot_val;
             new_j_h = old.j_h;
-        } else if (!cx.incremental || !pm.has_fixed) {
+        } else if (!cx.incremental || !pm.has_fixed || cx.passes == 1) {
+            // (The first pass of a pair writes no h row: most pairs need one pass only - the headline averages 1.0 - and pay
+            // nothing; the second pass then recomputes the rows the first had fixed, which the reference would have kept.)
             bot_val = run_block_dp(sm, cx, prev, is, ie - is, rounded.s, rounded.e, vout, cumout, top_val);
             cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
         } else {
@@ -376,11 +378,9 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
                 return PASS_NONE;
             }
             const int ncols = ie - is;
-            auto region = [&](I rs, I re, Cost start_val, const uint8_t* h_in, uint8_t* h_out) -> Cost {
-                const int o = (rs - rounded.s) >> 5;
-                cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(re - rs);
-                return run_block_dp(sm, cx, prev, is, ncols, rs, re, vout + o, cumout + o, start_val, h_in, h_out);
-            };
+            I start = rounded.s;        // first row of the sweep that carries the new h row
+            Cost start_val = top_val;
+            const uint8_t* h_in = nullptr;
             const bool three = old_v && old.j_h != J_H_NONE && old.has_fixed && next_mult64(old.fs - 1) < old.j_h;
             if (three) {
                 const I ps = next_mult64(old.fs - 1), pe = old.j_h;  // preserved rows [ps, pe): round_in(old_fixed.0 - 1 .. old_j_h)
@@ -389,29 +389,40 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
                     return PASS_NONE;
                 }
                 // range 0: everything above the preserved part, from the +1 top edge, h row untouched
-                if (ps > rounded.s) region(rounded.s, ps, top_val, nullptr, nullptr);
-                // preserved part: the old column's words and running values
-                {
-                    const int old_nhw = (old.je - old.js) >> 5;
-                    const uint2* ov = (const uint2*)(cx.arena + old.v_off);
-                    const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)old_nhw * 8);
-                    const int o_new = (ps - rounded.s) >> 5, o_old = (ps - old.js) >> 5, cnt = (pe - ps) >> 5;
-                    for (int k = lane; k < cnt; k += 32) {
-                        vout[o_new + k] = ov[o_old + k];
-                        cumout[o_new + k] = oc[o_old + k];
-                    }
-                    __syncwarp();
-                    const Cost at_pe = oc[(pe - old.js) >> 5];  // value at (ie, old_j_h): exact, the row was fixed
-                    // range 1: old j_h .. new j_h, h row in and out (an empty range leaves the h row as it is)
-                    Cost run = at_pe;
-                    if (new_j_h > pe) run = region(pe, new_j_h, at_pe, hrow, hrow);
-                    // range 2: below the new j_h, h row in
-                    bot_val = region(new_j_h, rounded.e, run, hrow, nullptr);
+                if (ps > rounded.s) {
+                    run_block_dp(sm, cx, prev, is, ncols, rounded.s, ps, vout, cumout, top_val);
+                    cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(ps - rounded.s);
                 }
+                // preserved part: the old column's words and running values
+                const int old_nhw = (old.je - old.js) >> 5;
+                const uint2* ov = (const uint2*)(cx.arena + old.v_off);
+                const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)old_nhw * 8);
+                const int o_new = (ps - rounded.s) >> 5, o_old = (ps - old.js) >> 5, cnt = (pe - ps) >> 5;
+                for (int k = lane; k < cnt; k += 32) {
+                    vout[o_new + k] = ov[o_old + k];
+                    cumout[o_new + k] = oc[o_old + k];
+                }
+                __syncwarp();
+                start = pe;
+                start_val = oc[(pe - old.js) >> 5];  // value at (ie, old_j_h): exact, the row was fixed
+                h_in = hrow;                         // the deltas along row old_j_h, left there by the previous pass
+            }
+            // Ranges 1 and 2 (or 01 and 2) of the reference are ONE sweep here, from `start` to the bottom of the band: what
+            // range 1 (01) would write to the h row and range 2 read back are the deltas along row new_j_h inside the sweep,
+            // recorded by the lane below that row (dp_chunk TAP). Cutting the sweep in two would halve the lanes at work.
+            const int o = (start - rounded.s) >> 5;
+            cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(rounded.e - start);
+            if (new_j_h == start) {  // an empty range 1 leaves the h row as it is; an empty range 01 leaves +1 deltas
+                if (!three) {
+                    for (int k = lane; k < ncols; k += 32) hrow[k] = 1;
+                    __syncwarp();
+                }
+                bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in);
+            } else if (new_j_h == rounded.e) {
+                bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in, hrow);
             } else {
-                // range 01: everything above the new j_h from the +1 top edge, its bottom edge becomes the h row
-                const Cost run = region(rounded.s, new_j_h, top_val, nullptr, hrow);
-                bot_val = region(new_j_h, rounded.e, run, hrow, nullptr);
+                bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in, nullptr,
+                                       (new_j_h - start) >> 5, hrow);
             }
         }
         APA_TOC(cx.tphase[1], t_dp0);

@@ -52,6 +52,7 @@ struct alignas(16) WarpSmem {  // (also the 1 040-byte landing zone of dev_pack_
     uint2 amask[BLOCK_W];   // per column of the current block: (0 - rank bit0, 0 - rank bit1) of a[i]  (profile.rs:117-121)
 #endif
     uint8_t hrow[BLOCK_W];  // bottom horizontal deltas of the previous chunk: bit0 = +1, bit1 = -1
+    uint8_t htap[BLOCK_W];  // horizontal deltas along an interior row of the sweep (the new h row of incremental doubling)
 #if APA_TMA_STAGE
     alignas(16) uint2 astage[8];      // landing zone of the bulk copy of a block's planes of a (8 half-words = 256 columns)
     alignas(8) unsigned long long mbar;  // its completion barrier
@@ -182,9 +183,11 @@ __device__ __forceinline__ void stage_amask(WarpSmem& sm, const uint2* __restric
 // the last lane of the previous chunk left them. HAND_OFF: the last lane publishes its bottom deltas for the next chunk.
 // The sweep is split into ramp-up / steady / ramp-down so the steady state (all lanes busy) runs without guards.
 // CUSTOM_ETAB: the caller has filled sm.etab itself (match masks that are not plain base equality: apa_search).
-template <bool FILL, bool FIRST, bool HAND_OFF, bool CUSTOM_ETAB = false>
+// TAP: lane `tap_lane` also records the deltas ENTERING its top row, per column, in sm.htap: the horizontal deltas along the row
+// boundary above it (HMode::Output / Update of an interior row without cutting the sweep in two, see dev_pass).
+template <bool FILL, bool FIRST, bool HAND_OFF, bool CUSTOM_ETAB = false, bool TAP = false>
 __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint32_t b0, uint32_t b1, uint32_t& vp, uint32_t& vm,
-                                         uint2* __restrict__ fillcol /* fillvals + hw of this lane */, int nhw) {
+                                         uint2* __restrict__ fillcol /* fillvals + hw of this lane */, int nhw, int tap_lane = -1) {
     const int lane = threadIdx.x & 31;
     const bool act_lane = lane < nact;
     const bool is_row = FIRST ? (act_lane && lane > 0) : act_lane;
@@ -218,6 +221,9 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
         }
     };
     auto step_core = [&](int col, uint32_t eq, uint32_t cpi, uint32_t cmi) {
+        if (TAP) {
+            if (lane == tap_lane) sm.htap[col] = (uint8_t)(cpi | (cmi << 1));
+        }
         myers_step_eq(eq, vp, vm, cpi, cmi, cp_o, cm_o);
         if (HAND_OFF) {
             if (is_bot) sm.hrow[col] = (uint8_t)(cp_o | (cm_o << 1));
@@ -271,7 +277,8 @@ __device__ __forceinline__ void dp_chunk(WarpSmem& sm, int ncols, int nact, uint
 template <bool FILL>
 __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const BlkView& prev, int ncols, I njs, I nje,
                          uint2* __restrict__ vout, int32_t* __restrict__ cumout, Cost top_val_new, uint2* __restrict__ fillvals,
-                         DpCounters& dpc, const uint8_t* h_in = nullptr, uint8_t* h_out = nullptr) {
+                         DpCounters& dpc, const uint8_t* h_in = nullptr, uint8_t* h_out = nullptr, int tap_hw = -1, uint8_t* h_tap = nullptr) {
+    // tap_hw in [0, nhw): the deltas along the top edge of half-word tap_hw (row njs + 32 tap_hw) go to h_tap as well
     const int lane = threadIdx.x & 31;
     const int nhw = (nje - njs) >> 5;
     if (h_in) {  // the first chunk takes its incoming deltas from shared memory like every later chunk does
@@ -305,7 +312,21 @@ __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const Bl
         }
         const bool hand_off = (c + 1 < nchunks) || h_out;
         uint2* fillcol = FILL ? fillvals + hw : nullptr;
-        if (feeder) {
+        const int tl = tap_hw - per * c;  // the tapped half-word as a row of this chunk
+        if (!FILL && tap_hw >= 0 && tl >= 0 && tl < nrow) {
+            const int tap_lane = feeder ? tl + 1 : tl;
+            if (feeder) {
+                if (hand_off)
+                    dp_chunk<false, true, true, false, true>(sm, ncols, nrow + 1, b0, b1, vp, vm, nullptr, nhw, tap_lane);
+                else
+                    dp_chunk<false, true, false, false, true>(sm, ncols, nrow + 1, b0, b1, vp, vm, nullptr, nhw, tap_lane);
+            } else {
+                if (hand_off)
+                    dp_chunk<false, false, true, false, true>(sm, ncols, nrow, b0, b1, vp, vm, nullptr, nhw, tap_lane);
+                else
+                    dp_chunk<false, false, false, false, true>(sm, ncols, nrow, b0, b1, vp, vm, nullptr, nhw, tap_lane);
+            }
+        } else if (feeder) {
             if (hand_off)
                 dp_chunk<FILL, true, true>(sm, ncols, nrow + 1, b0, b1, vp, vm, fillcol, nhw);
             else
@@ -334,6 +355,10 @@ __device__ Cost block_dp(WarpSmem& sm, const uint2* __restrict__ bprof, const Bl
     if (nchunks) dpc.issue_steps += 32ull * (unsigned long long)(nchunks * (ncols - 1) + nhw + 1);
     if (lane == 0) cumout[nhw] = running;
     __syncwarp();
+    if (h_tap && tap_hw >= 0) {
+        for (int k = lane; k < ncols; k += 32) h_tap[k] = sm.htap[k];
+        __syncwarp();
+    }
     if (h_out) {  // what the last chunk left in shared memory is the bottom edge (an empty range passes its top edge through)
         for (int k = lane; k < ncols; k += 32) h_out[k] = nchunks ? sm.hrow[k] : (h_in ? h_in[k] : (uint8_t)1);
         __syncwarp();

@@ -24,6 +24,8 @@ struct CoopSmem {
     int quit;
     int h_first;  // 1: the top edge of the range is +1 (chunk 0 has the feeder lane); 0: chunk 0 takes its deltas from ring slot W
     int h_keep;   // 1: the last chunk publishes its bottom deltas too (they become the pair's h row)
+    int tap_c, tap_lane;  // chunk and lane whose incoming deltas are recorded in htap (-1: none), see dp_chunk TAP
+    uint8_t htap[BLOCK_W];
     int ncols, nhw, nchunks, per;
     I njs;
     Cost top_val;
@@ -67,6 +69,7 @@ __device__ __forceinline__ void coop_chunk(CoopSmem<W>& cs, int wid, int c, int 
     volatile int* pin = &cs.progress[(c + W) % (W + 1)];
     volatile int* pout = &cs.progress[c % (W + 1)];
     const int T = ncols + nact - 1;
+    const bool is_tap = c == cs.tap_c && lane == cs.tap_lane;
     const uint32_t etab_lane = (uint32_t)__cvta_generic_to_shared(&etab[lane]);
     auto load_eq = [&](int col) -> uint32_t {  // etab[achar[col] * 32 + lane], the address is one IMAD (see dp_chunk)
         uint32_t eaddr;
@@ -98,6 +101,7 @@ __device__ __forceinline__ void coop_chunk(CoopSmem<W>& cs, int wid, int c, int 
                     cpi = is_top ? (x & 1u) : cpi;
                     cmi = is_top ? (x >> 1) : cmi;
                 }
+                if (is_tap) cs.htap[t0 + k - r] = (uint8_t)(cpi | (cmi << 1));
                 myers_step_eq(eqs[k], vp, vm, cpi, cmi, cp_o, cm_o);
                 if (hand_off && is_bot) hout[t0 + k - r] = (uint8_t)(cp_o | (cm_o << 1));
             }
@@ -112,6 +116,7 @@ __device__ __forceinline__ void coop_chunk(CoopSmem<W>& cs, int wid, int c, int 
                 }
                 const int col = t - r;
                 if ((unsigned)col < (unsigned)ncols) {
+                    if (is_tap) cs.htap[col] = (uint8_t)(cpi | (cmi << 1));
                     myers_step_eq(load_eq(col), vp, vm, cpi, cmi, cp_o, cm_o);
                     if (hand_off && is_bot) hout[col] = (uint8_t)(cp_o | (cm_o << 1));
                 }
@@ -199,13 +204,13 @@ __device__ __forceinline__ Cost coop_work(CoopSmem<W>& cs, int wid) {
 template <int W>
 __device__ __forceinline__ Cost run_block_dp(CoopSmem<W>& cs, PairCtx& cx, const BlkView& prev, I is, int ncols, I njs, I nje,
                                              uint2* vout, int32_t* cumout, Cost top_val, const uint8_t* h_in = nullptr,
-                                             uint8_t* h_out = nullptr) {
+                                             uint8_t* h_out = nullptr, int tap_hw = -1, uint8_t* h_tap = nullptr) {
     const int lane = threadIdx.x & 31;
     const int nhw = (nje - njs) >> 5;
     const int nchunks = (nhw + 30) / 31;
     stage_amask(cs.lead, cx.aprof, is, ncols, lane);
     if (nchunks < 2 || nchunks > COOP_MAX_CHUNKS)
-        return block_dp<false>(cs.lead, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc, h_in, h_out);
+        return block_dp<false>(cs.lead, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc, h_in, h_out, tap_hw, h_tap);
     if (h_in)  // the top-edge deltas of the range: ring slot W is what chunk 0 reads as "the chunk above" (its progress word
                // starts at -1, which is past everything chunk 0 asks for); the slot is next written by chunk W, on this warp
         for (int k = lane; k < ncols; k += 32) cs.hrow[W][k] = h_in[k];
@@ -213,6 +218,13 @@ __device__ __forceinline__ Cost run_block_dp(CoopSmem<W>& cs, PairCtx& cx, const
         cs.quit = 0;
         cs.h_first = h_in ? 0 : 1;
         cs.h_keep = h_out ? 1 : 0;
+        cs.tap_c = -1;
+        cs.tap_lane = -1;
+        if (tap_hw >= 0) {  // chunks of `per` half-words; chunk 0 gives lane 0 to the feeder when the top edge is +1
+            const int per = (nhw + nchunks - 1) / nchunks;
+            cs.tap_c = tap_hw / per;
+            cs.tap_lane = tap_hw - cs.tap_c * per + ((cs.tap_c == 0 && !h_in) ? 1 : 0);
+        }
         cs.ncols = ncols;
         cs.nhw = nhw;
         cs.nchunks = nchunks;
@@ -233,6 +245,10 @@ __device__ __forceinline__ Cost run_block_dp(CoopSmem<W>& cs, PairCtx& cx, const
     cx.dpc.word_steps += (unsigned long long)ncols * (unsigned long long)nhw;
     cx.dpc.issue_steps += 32ull * (unsigned long long)(((nhw + 30) / 31) * (ncols - 1) + nhw + 1);  // chunks of 31 half-words, as block_dp counts
     const Cost bot = coop_work<W>(cs, 0);
+    if (h_tap && tap_hw >= 0) {  // (after the END barrier)
+        for (int k = lane; k < ncols; k += 32) h_tap[k] = cs.htap[k];
+        __syncwarp();
+    }
     if (h_out) {  // (after the END barrier) the bottom deltas of the last chunk are the new h row of these columns
         const uint8_t* last = cs.hrow[(nchunks - 1) % (W + 1)];
         for (int k = lane; k < ncols; k += 32) h_out[k] = last[k];
