@@ -30,6 +30,9 @@ struct PairCtx {
     uint32_t cig_top;    // where the CIGAR elements grow down from: the arena end, or the bottom of store B when the final pass lives there
     uint32_t hrow_off;   // incremental doubling: the pair's row of horizontal deltas, one byte per column of a (Blocks.h, blocks.rs:106)
     int incremental;     // BlockParams.incremental_doubling (astarpa2_full: true, astarpa2_simple: false; params.rs:88,119)
+    // exponential_search between the first-pass kernel and the continuation kernel (band.rs:100-141): last_s, s, maxs
+    Cost bd_last_s, bd_s, bd_maxs;
+    int more;            // 1: the first pass did not find the cost; the continuation kernel takes the pair over
     int status;          // ST_PENDING while healthy
     // stats
     DpCounters dpc;  // block-DP lane-steps: useful / issued
@@ -263,7 +266,10 @@ __device__ __forceinline__ Cost run_block_dp(WarpSmem& sm, PairCtx& cx, const Bl
     return block_dp<false>(sm, cx.bprof, prev, ncols, njs, nje, vout, cumout, top_val, nullptr, cx.dpc, h_in, h_out, tap_hw, h_tap);
 }
 
-template <class Hh, class SM>
+// INC: compiled with the code of incremental doubling and block reuse (second and later passes of a pair). The first-pass
+// kernel is compiled without it: the single-pass path - the headline - keeps its instruction footprint (the pass kernel is
+// sensitive to it: 45.7 -> 47.5 ms per 10 000 pairs with that code inlined, 48.2 ms with it out of line).
+template <bool INC, class Hh, class SM>
 __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
     const int lane = threadIdx.x & 31;
     cx.passes++;
@@ -341,7 +347,7 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
         // and j_h carry over (the column is copied into this pass's store).
         JRange rounded = jr_round_out(jr);
         int nhw = (rounded.e - rounded.s) >> 5;
-        if (cx.incremental && reuse && old.store_pass == cx.passes - 1) {
+        if (INC && cx.incremental && reuse && old.store_pass == cx.passes - 1) {
             rounded = JRange{old.js, old.je};
             nhw = (rounded.e - rounded.s) >> 5;
         }
@@ -351,79 +357,89 @@ __device__ Cost dev_pass(PairCtx& cx, SM& sm, Hh& hh, Cost f_max) {
         uint2* vout = (uint2*)(cx.arena + off);
         int32_t* cumout = (int32_t*)(cx.arena + off + (size_t)nhw * 8);
         long long t_dp0 = APA_TIC();
-        Cost bot_val;
+        Cost bot_val = 0;
         I new_j_h = J_H_NONE;
         const bool old_v = existed && old.store_pass == cx.passes - 1;  // the old column is still in the other store
-        if (cx.incremental && reuse && old_v) {
-            const uint2* ov = (const uint2*)(cx.arena + old.v_off);
-            const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)nhw * 8);
-            for (int k = lane; k < nhw; k += 32) vout[k] = ov[k];
-            for (int k = lane; k <= nhw; k += 32) cumout[k] = oc[k];
-            __syncwarp();
-            top_val = old.top_val;
-            bot_val = old.bot_val;
-            new_j_h = old.j_h;
-        } else if (!cx.incremental || !pm.has_fixed || cx.passes == 1) {
-            // (The first pass of a pair writes no h row: most pairs need one pass only - the headline averages 1.0 - and pay
-            // nothing; the second pass then recomputes the rows the first had fixed, which the reference would have kept.)
-            bot_val = run_block_dp(sm, cx, prev, is, ie - is, rounded.s, rounded.e, vout, cumout, top_val);
-            cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
-        } else {
-            const JRange pfix = jr_round_in(JRange{pm.fs, pm.fe});
-            new_j_h = pfix.e;
-            uint8_t* hrow = cx.arena + cx.hrow_off + is;
-            // the reference asserts these orders (blocks.rs:388-397,427-430); a violation is a panic there
-            if (new_j_h < rounded.s || new_j_h > rounded.e) {
-                cx.status = ST_ASSERT;
-                return PASS_NONE;
-            }
-            const int ncols = ie - is;
-            I start = rounded.s;        // first row of the sweep that carries the new h row
-            Cost start_val = top_val;
-            const uint8_t* h_in = nullptr;
-            const bool three = old_v && old.j_h != J_H_NONE && old.has_fixed && next_mult64(old.fs - 1) < old.j_h;
-            if (three) {
-                const I ps = next_mult64(old.fs - 1), pe = old.j_h;  // preserved rows [ps, pe): round_in(old_fixed.0 - 1 .. old_j_h)
-                if (pe > new_j_h || ps < rounded.s || rounded.s > old.js || pe > old.je) {  // "j_h may only increase!" and friends
+        bool computed = false;
+        if constexpr (INC) {
+            if (cx.incremental && reuse && old_v) {
+
+                const uint2* ov = (const uint2*)(cx.arena + old.v_off);
+                const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)nhw * 8);
+                for (int k = lane; k < nhw; k += 32) vout[k] = ov[k];
+                for (int k = lane; k <= nhw; k += 32) cumout[k] = oc[k];
+                __syncwarp();
+                top_val = old.top_val;
+                bot_val = old.bot_val;
+                new_j_h = old.j_h;
+                computed = true;
+            } else if (cx.incremental && pm.has_fixed && cx.passes > 1) {
+
+                const JRange pfix = jr_round_in(JRange{pm.fs, pm.fe});
+                new_j_h = pfix.e;
+                uint8_t* hrow = cx.arena + cx.hrow_off + is;
+                // the reference asserts these orders (blocks.rs:388-397,427-430); a violation is a panic there
+                if (new_j_h < rounded.s || new_j_h > rounded.e) {
                     cx.status = ST_ASSERT;
                     return PASS_NONE;
                 }
-                // range 0: everything above the preserved part, from the +1 top edge, h row untouched
-                if (ps > rounded.s) {
-                    run_block_dp(sm, cx, prev, is, ncols, rounded.s, ps, vout, cumout, top_val);
-                    cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(ps - rounded.s);
-                }
-                // preserved part: the old column's words and running values
-                const int old_nhw = (old.je - old.js) >> 5;
-                const uint2* ov = (const uint2*)(cx.arena + old.v_off);
-                const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)old_nhw * 8);
-                const int o_new = (ps - rounded.s) >> 5, o_old = (ps - old.js) >> 5, cnt = (pe - ps) >> 5;
-                for (int k = lane; k < cnt; k += 32) {
-                    vout[o_new + k] = ov[o_old + k];
-                    cumout[o_new + k] = oc[o_old + k];
-                }
-                __syncwarp();
-                start = pe;
-                start_val = oc[(pe - old.js) >> 5];  // value at (ie, old_j_h): exact, the row was fixed
-                h_in = hrow;                         // the deltas along row old_j_h, left there by the previous pass
-            }
-            // Ranges 1 and 2 (or 01 and 2) of the reference are ONE sweep here, from `start` to the bottom of the band: what
-            // range 1 (01) would write to the h row and range 2 read back are the deltas along row new_j_h inside the sweep,
-            // recorded by the lane below that row (dp_chunk TAP). Cutting the sweep in two would halve the lanes at work.
-            const int o = (start - rounded.s) >> 5;
-            cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(rounded.e - start);
-            if (new_j_h == start) {  // an empty range 1 leaves the h row as it is; an empty range 01 leaves +1 deltas
-                if (!three) {
-                    for (int k = lane; k < ncols; k += 32) hrow[k] = 1;
+                const int ncols = ie - is;
+                I start = rounded.s;        // first row of the sweep that carries the new h row
+                Cost start_val = top_val;
+                const uint8_t* h_in = nullptr;
+                const bool three = old_v && old.j_h != J_H_NONE && old.has_fixed && next_mult64(old.fs - 1) < old.j_h;
+                if (three) {
+                    const I ps = next_mult64(old.fs - 1), pe = old.j_h;  // preserved rows [ps, pe): round_in(old_fixed.0 - 1 .. old_j_h)
+                    if (pe > new_j_h || ps < rounded.s || rounded.s > old.js || pe > old.je) {  // "j_h may only increase!" and friends
+                        cx.status = ST_ASSERT;
+                        return PASS_NONE;
+                    }
+                    // range 0: everything above the preserved part, from the +1 top edge, h row untouched
+                    if (ps > rounded.s) {
+                        run_block_dp(sm, cx, prev, is, ncols, rounded.s, ps, vout, cumout, top_val);
+                        cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(ps - rounded.s);
+                    }
+                    // preserved part: the old column's words and running values
+                    const int old_nhw = (old.je - old.js) >> 5;
+                    const uint2* ov = (const uint2*)(cx.arena + old.v_off);
+                    const int32_t* oc = (const int32_t*)(cx.arena + old.v_off + (size_t)old_nhw * 8);
+                    const int o_new = (ps - rounded.s) >> 5, o_old = (ps - old.js) >> 5, cnt = (pe - ps) >> 5;
+                    for (int k = lane; k < cnt; k += 32) {
+                        vout[o_new + k] = ov[o_old + k];
+                        cumout[o_new + k] = oc[o_old + k];
+                    }
                     __syncwarp();
+                    start = pe;
+                    start_val = oc[(pe - old.js) >> 5];  // value at (ie, old_j_h): exact, the row was fixed
+                    h_in = hrow;                         // the deltas along row old_j_h, left there by the previous pass
                 }
-                bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in);
-            } else if (new_j_h == rounded.e) {
-                bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in, hrow);
-            } else {
-                bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in, nullptr,
-                                       (new_j_h - start) >> 5, hrow);
+                // Ranges 1 and 2 (or 01 and 2) of the reference are ONE sweep here, from `start` to the bottom of the band: what
+                // range 1 (01) would write to the h row and range 2 read back are the deltas along row new_j_h inside the sweep,
+                // recorded by the lane below that row (dp_chunk TAP). Cutting the sweep in two would halve the lanes at work.
+                const int o = (start - rounded.s) >> 5;
+                cx.computed_cells += (unsigned long long)ncols * (unsigned long long)(rounded.e - start);
+                if (new_j_h == start) {  // an empty range 1 leaves the h row as it is; an empty range 01 leaves +1 deltas
+                    if (!three) {
+                        for (int k = lane; k < ncols; k += 32) hrow[k] = 1;
+                        __syncwarp();
+                    }
+                    bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in);
+                } else if (new_j_h == rounded.e) {
+                    bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in, hrow);
+                } else {
+                    bot_val = run_block_dp(sm, cx, prev, is, ncols, start, rounded.e, vout + o, cumout + o, start_val, h_in, nullptr,
+                                           (new_j_h - start) >> 5, hrow);
+                }
+        
+                computed = true;
             }
+        }
+        if (!computed) {
+            // From scratch: no incremental doubling, no fixed range to the left, or the FIRST pass of a pair - which writes no h
+            // row (most pairs need one pass only - the headline averages 1.0 - and pay nothing; the second pass then recomputes
+            // the rows the first had fixed, which the reference would have kept).
+            bot_val = run_block_dp(sm, cx, prev, is, ie - is, rounded.s, rounded.e, vout, cumout, top_val);
+            cx.computed_cells += (unsigned long long)(ie - is) * (unsigned long long)(rounded.e - rounded.s);
         }
         APA_TOC(cx.tphase[1], t_dp0);
 
@@ -509,7 +525,12 @@ __device__ __forceinline__ void arena_after_passes(PairCtx& cx) {
     }
 }
 
-template <class Hh, class SM>
+constexpr Cost BD_MORE = -2;  // dev_band_doubling<BD_FIRST>: the first pass did not settle the pair
+enum : int { BD_WHOLE = 0, BD_FIRST = 1, BD_CONTINUE = 2 };
+// MODE BD_WHOLE: the whole search in one call (fused and general kernels). BD_FIRST: the first pass only - compiled without the
+// incremental-doubling code; returns BD_MORE with the state of the search in cx.bd_* when another pass is needed. BD_CONTINUE:
+// takes such a pair over from its second pass on (the continuation kernel).
+template <int MODE, class Hh, class SM>
 __device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
     Cost offset = h0;
     Cost s0 = BLOCK_W;
@@ -518,7 +539,7 @@ __device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
     Cost delta = 0;
 #if APA_GENERAL
     if (cx.par.doubling == 0) {  // DoublingType::None: one pass without a bound (lib.rs:126-130)
-        Cost cost = dev_pass(cx, sm, hh, F_MAX_NONE);
+        Cost cost = dev_pass<true>(cx, sm, hh, F_MAX_NONE);
         if (cx.status == ST_PENDING && cost == PASS_NONE) cx.status = ST_ASSERT;  // .unwrap()
         arena_after_passes(cx);
         return cost;
@@ -537,8 +558,9 @@ __device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
     Cost last_s = -1;
     Cost s = linear ? offset : offset + s0;
     Cost maxs = INT32_MAX;
+    if (MODE == BD_CONTINUE) last_s = cx.bd_last_s, s = cx.bd_s, maxs = cx.bd_maxs;
     for (;;) {
-        Cost cost = dev_pass(cx, sm, hh, s);
+        Cost cost = MODE == BD_FIRST ? dev_pass<false>(cx, sm, hh, s) : dev_pass<true>(cx, sm, hh, s);
         if (cx.status != ST_PENDING) return -1;
         if (cost != PASS_NONE) {
             if (cost > maxs) {
@@ -565,6 +587,10 @@ __device__ Cost dev_band_doubling(PairCtx& cx, SM& sm, Hh& hh, Cost h0) {
             float grown = ceilf(factor * (float)(s - offset));
             s = max((Cost)grown, 1) + offset;
             s = min(s, maxs);
+        }
+        if (MODE == BD_FIRST) {
+            cx.bd_last_s = last_s, cx.bd_s = s, cx.bd_maxs = maxs;
+            return BD_MORE;
         }
     }
 }

@@ -112,6 +112,8 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
         cx.v_top = cx.v_base;
         cx.hi_bot = bd.arena_size;
         cx.cig_top = bd.arena_size;
+        cx.more = 0;
+        cx.bd_last_s = cx.bd_s = cx.bd_maxs = 0;
         cx.status = ST_PENDING;
         cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
         cx.passes = 0;
@@ -133,7 +135,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
                 Cost h0 = hh.h(0, 0);
                 st_h0 = h0;
                 long long t0 = APA_TIC();
-                cost = dev_band_doubling(cx, sm, hh, h0);
+                cost = dev_band_doubling<BD_WHOLE>(cx, sm, hh, h0);
                 APA_TOC(cx.tphase[2], t0);
                 if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
             } else {
@@ -144,7 +146,7 @@ __device__ __forceinline__ void apa_align_body(const BatchDev& bd, WarpSmem* sme
                 if (built) {
                     Cost h0 = hh.h(0, 0);
                     t0 = APA_TIC();
-                    cost = dev_band_doubling(cx, sm, hh, h0);
+                    cost = dev_band_doubling<BD_WHOLE>(cx, sm, hh, h0);
                     APA_TOC(cx.tphase[2], t0);
                     cx.tphase[6] += hh.t_h;
                     st_h0 = h0;
@@ -230,7 +232,8 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
         if (q >= bd.n_order) break;
         int landed = 1;
         if (PHASE == 0) landed = wait_ready(bd, q);  // later phases run after the build kernel, which saw every pair land
-        if (PHASE >= 1 && bd.phase_flag) {  // overlapped kernels: the previous phase of this pair is done (bounded wait, as above)
+        if ((PHASE == 1 || PHASE == 2) && bd.phase_flag) {  // overlapped kernels: the previous phase of this pair is done (bounded wait, as
+                                                            // above); the continuation kernel follows the pass kernel on its stream
             int okf = 1;
             if (lane == 0) {
                 unsigned long long spins = 0;
@@ -276,6 +279,8 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             cx.v_top = cx.v_base;
             cx.hi_bot = bd.arena_size;
             cx.cig_top = bd.arena_size;
+            cx.more = 0;
+            cx.bd_last_s = cx.bd_s = cx.bd_maxs = 0;
             cx.status = ST_PENDING;
             cx.dpc.word_steps = cx.dpc.issue_steps = cx.computed_cells = 0;
             cx.passes = 0;
@@ -305,32 +310,44 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
         }
         cx = ps->cx;
         Cost cost = ps->cost;
-        if constexpr (PHASE == 1) {
+        // PHASE 1: the first pass of every pair (compiled without the incremental-doubling code). PHASE 3: the continuation
+        // kernel - second and later passes of the pairs the first pass did not settle (cx.more), from the saved search state.
+        if constexpr (PHASE == 1 || PHASE == 3) {
+            if (PHASE == 3 && !cx.more) continue;
             if (cx.status == ST_PENDING) {
                 long long* pst = bd.pair_stats + 8ull * p;
+                constexpr int MODE = PHASE == 1 ? BD_FIRST : BD_CONTINUE;
                 if (bd.preset == APA_PRESET_SIMPLE) {
                     GapH hh{cx.n, cx.m};
                     Cost h0 = hh.h(0, 0);
-                    cost = dev_band_doubling(cx, sm, hh, h0);
-                    if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
+                    cost = dev_band_doubling<MODE>(cx, sm, hh, h0);
+                    if (cx.status == ST_PENDING && cost != BD_MORE && h0 > cost) cx.status = ST_ASSERT;  // lib.rs:173
                     if (lane == 0) pst[1] = h0, pst[2] = 0, pst[3] = 0;
                 } else {
                     GcshH hh = ps->hh;
-                    hh.h_calls = hh.probes = 0;
-                    Cost h0 = hh.h(0, 0);
-                    cost = dev_band_doubling(cx, sm, hh, h0);
-                    if (cx.status == ST_PENDING && h0 > cost) cx.status = ST_ASSERT;
-                    acc_h += hh.h_calls;
-                    acc_probe += hh.probes;
-                    if (lane == 0) pst[1] = h0, pst[2] = hh.M, pst[3] = (long long)hh.h_calls + 1;  // + CSHI::new's own h(0,0) (csh.rs:296)
+                    if (PHASE == 1) hh.h_calls = hh.probes = 0;
+                    Cost h0 = ps->h0;
+                    if (PHASE == 1) h0 = hh.h(0, 0);
+                    cost = dev_band_doubling<MODE>(cx, sm, hh, h0);
+                    if (cx.status == ST_PENDING && cost != BD_MORE && h0 > cost) cx.status = ST_ASSERT;
+                    if (cost == BD_MORE) {  // the heuristic (pruned matches, search hints, counters) goes on in the continuation kernel
+                        __syncwarp();
+                        if (lane == 0) ps->hh = hh, ps->h0 = h0;
+                    } else {
+                        acc_h += hh.h_calls;
+                        acc_probe += hh.probes;
+                        if (lane == 0) pst[1] = h0, pst[2] = hh.M, pst[3] = (long long)hh.h_calls + 1;  // + CSHI::new's own h(0,0) (csh.rs:296)
+                    }
                 }
             }
+            cx.more = (cx.status == ST_PENDING && cost == BD_MORE) ? 1 : 0;
             __syncwarp();
             if (lane == 0) {
                 ps->cx = cx;
                 ps->cost = cost;
             }
             __syncwarp();
+            if (cx.more) continue;  // (PHASE 1 only) the pair's passes are not done yet
             if (bd.phase_flag && bd.trace) {
                 __threadfence();
                 __syncwarp();
@@ -338,7 +355,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
             }
             if (bd.trace) continue;
         }
-        // PHASE 2, or PHASE 1 of a cost-only run: finish the pair
+        // PHASE 2, or PHASE 1 / 3 of a cost-only run: finish the pair
         long long cig_off = -1, cig_len = 0;
         if constexpr (PHASE == 2) if (cx.status == ST_PENDING && bd.trace) {
             CigarWriter cw;
@@ -370,7 +387,7 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
         acc_fill += cx.fill_blocks;
         acc_dt += cx.dt_blocks;
     }
-    if (PHASE == 1 && lane == 0) {
+    if ((PHASE == 1 || PHASE == 3) && lane == 0) {
         atomicAdd(&bd.stats[13], acc_h);
         atomicAdd(&bd.stats[14], acc_probe);
     }
@@ -397,17 +414,18 @@ APA_PHASE_KERNEL(apa_phase_build_kernel_r64, 0, 8)
 APA_PHASE_KERNEL(apa_phase_pass_kernel, 1, 10)
 APA_PHASE_KERNEL(apa_phase_pass_kernel_r56, 1, 9)
 APA_PHASE_KERNEL(apa_phase_pass_kernel_r64, 1, 8)
+APA_PHASE_KERNEL(apa_phase_cont_kernel, 3, 8)
 APA_PHASE_KERNEL(apa_phase_trace_kernel, 2, 10)
 APA_PHASE_KERNEL(apa_phase_trace_kernel_r56, 2, 9)
 APA_PHASE_KERNEL(apa_phase_trace_kernel_r64, 2, 8)
 // Pass kernel with the W warps of a CTA on one pair (apa_coop.cuh): warp 0 runs the pair, the others serve its tall blocks.
-template <int W>
+template <int W, int PHASE>
 __global__ void __launch_bounds__(W * 32, 32 / W) apa_phase_pass_coop_kernel(BatchDev bd) {
     __shared__ CoopSmem<W> cs;
     const int wid = threadIdx.x >> 5;
     if (wid == 0) {
         tma_stage_reset(cs.lead);
-        apa_phase_body<1>(bd, cs);
+        apa_phase_body<PHASE>(bd, cs);
         coop_release_workers<W>(cs);
     } else {
         coop_worker_loop<W>(cs, wid);
@@ -826,8 +844,11 @@ extern "C" int apa_engine_create(int device, apa_engine** out) {
             for (int regs = 48; regs <= 64; regs += 8) CUDA_TRY(cudaFuncGetAttributes(&fa, phase_kernel(ph, regs)));
         CUDA_TRY(cudaFuncGetAttributes(&fa, apa_block_kernel));
         CUDA_TRY(cudaFuncGetAttributes(&fa, apa_pack_kernel));
-        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<4>));
-        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<8>));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<4, 1>));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<8, 1>));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<4, 3>));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_pass_coop_kernel<8, 3>));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, apa_phase_cont_kernel));
     }
     guard.e = nullptr;
     *out = eng;
@@ -1688,8 +1709,9 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->st_trace, e->ev_ov[0], 0);
                 if (ce != cudaSuccess) return ce;
                 phase_kernel(1, phase_regs(1))<<<grid, WARPS_PER_CTA * 32, 0, e->st_pass>>>(bd);
+                apa_phase_cont_kernel<<<grid, WARPS_PER_CTA * 32, 0, e->st_pass>>>(bd);  // pairs that need a second pass (none on the headline)
                 phase_kernel(2, phase_regs(2))<<<grid, WARPS_PER_CTA * 32, 0, e->st_trace>>>(bd);
-                b->stats.kernel_launches += 2;
+                b->stats.kernel_launches += 3;
                 ce = cudaEventRecord(e->ev_ov[1], e->st_pass);
                 if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_ov[2], e->st_trace);
                 if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, e->ev_ov[1], 0);  // the engine's stream continues when all three are done
@@ -1698,13 +1720,17 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
                 if (ce == cudaSuccess) ce = cudaEventRecord(e->evp[3], st);
                 return ce != cudaSuccess ? ce : cudaGetLastError();
             }
-            if (coop_w == 8)
-                apa_phase_pass_coop_kernel<8><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 4), 256, 0, st>>>(bd);
-            else if (coop_w == 4)
-                apa_phase_pass_coop_kernel<4><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 8), 128, 0, st>>>(bd);
-            else
+            if (coop_w == 8) {
+                apa_phase_pass_coop_kernel<8, 1><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 4), 256, 0, st>>>(bd);
+                apa_phase_pass_coop_kernel<8, 3><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 4), 256, 0, st>>>(bd);
+            } else if (coop_w == 4) {
+                apa_phase_pass_coop_kernel<4, 1><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 8), 128, 0, st>>>(bd);
+                apa_phase_pass_coop_kernel<4, 3><<<std::min<unsigned>(wave_pairs, (unsigned)e->sm_count * 8), 128, 0, st>>>(bd);
+            } else {
                 phase_kernel(1, phase_regs(1))<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
-            b->stats.kernel_launches++;
+                apa_phase_cont_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(bd);
+            }
+            b->stats.kernel_launches += 2;
             cudaError_t ce = cudaEventRecord(e->evp[2], st);
             if (ce != cudaSuccess) return ce;
             if (trace) {
@@ -1727,7 +1753,7 @@ static int batch_run(apa_engine* e, apa_batch* b, int preset, int trace, bool st
             for (uint64_t w0 = 0; w0 < n_work; w0 += wave_n) {
                 bd.q0 = (uint32_t)w0;
                 bd.n_order = (uint32_t)std::min<uint64_t>(w0 + wave_n, n_work);
-                CUDA_TRY(cudaMemsetAsync(e->d_queue + 24, 0, 3 * sizeof(unsigned long long), st));
+                CUDA_TRY(cudaMemsetAsync(e->d_queue + 24, 0, 4 * sizeof(unsigned long long), st));
                 CUDA_TRY(cudaEventRecord(e->evp[0], st));
                 if (overlap) CUDA_TRY(cudaEventRecord(e->ev_ov[0], st));
                 // Overlapped under a streamed upload: the build kernel waits for data for the first ~20 ms anyway, so it leaves

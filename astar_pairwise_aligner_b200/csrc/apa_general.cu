@@ -67,18 +67,18 @@ __device__ __forceinline__ void general_body(const BatchDev& bd, const RunParams
             long long st_matches = 0, st_hcalls = 0;
             if (par.domain != DOM_ASTAR || par.heuristic == 0) {
                 NoneH hh;
-                cost = dev_band_doubling(cx, sm, hh, 0);
+                cost = dev_band_doubling<BD_WHOLE>(cx, sm, hh, 0);
             } else if (par.heuristic == 1) {
                 GapH hh{cx.n, cx.m};
                 h0 = hh.h(0, 0);
-                cost = dev_band_doubling(cx, sm, hh, h0);
+                cost = dev_band_doubling<BD_WHOLE>(cx, sm, hh, h0);
             } else {
                 GcshH hh;
                 hh.k_ = par.k;
                 hh.p_ = par.p;
                 if (gcsh_build(cx, sm, hh)) {
                     h0 = hh.h(0, 0);
-                    cost = dev_band_doubling(cx, sm, hh, h0);
+                    cost = dev_band_doubling<BD_WHOLE>(cx, sm, hh, h0);
                     acc_h += hh.h_calls;
                     acc_probe += hh.probes;
                     st_matches = hh.M;
