@@ -224,6 +224,7 @@ static_assert(sizeof(PairState) <= ARENA_HEADER, "PairState must fit the arena h
 template <int PHASE, class SM>
 __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
     const int lane = threadIdx.x & 31;
+    if (PHASE == 3 && *(volatile unsigned long long*)&bd.stats[16] == 0ull) return;  // no pair asked for a second pass
     unsigned long long acc_steps = 0, acc_issue = 0, acc_cells = 0, acc_pass = 0, acc_fill = 0, acc_dt = 0, acc_h = 0, acc_probe = 0;
     for (;;) {
         unsigned long long q = 0;
@@ -347,7 +348,10 @@ __device__ __forceinline__ void apa_phase_body(const BatchDev& bd, SM& sm) {
                 ps->cost = cost;
             }
             __syncwarp();
-            if (cx.more) continue;  // (PHASE 1 only) the pair's passes are not done yet
+            if (cx.more) {  // (PHASE 1 only) the pair's passes are not done yet: the continuation kernel has work
+                if (lane == 0) atomicAdd(&bd.stats[16], 1ull);
+                continue;
+            }
             if (bd.phase_flag && bd.trace) {
                 __threadfence();
                 __syncwarp();
