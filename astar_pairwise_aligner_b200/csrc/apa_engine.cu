@@ -736,8 +736,16 @@ static cudaError_t eng_alloc(apa_engine* e, void** out, size_t bytes) {
     }
     cudaError_t ce = cudaMalloc(out, bytes);
     if (ce != cudaSuccess) {  // drop the cache and retry once
+        cudaGetLastError();
         for (auto& fb : e->free_blocks) cudaFree(fb.first);
         e->free_blocks.clear();
+        ce = cudaMalloc(out, bytes);
+    }
+    if (ce != cudaSuccess && e->d_arena) {  // the scratch arena of an earlier batch may hold nearly all of HBM (wave-sized work lists):
+        cudaGetLastError();                   // give it back; batch_run sizes a new one from what is free then
+        cudaFree(e->d_arena);
+        e->d_arena = nullptr;
+        e->arena_total = 0;
         ce = cudaMalloc(out, bytes);
     }
     if (ce == cudaSuccess) e->live[*out] = bytes;
