@@ -290,10 +290,24 @@ class Engine:
         _check(L.apa_engine_create(device, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def shared(cls, device=0):
+        """The process-wide engine of `device` (apa_shared_engine): the one align_batch_multi and the drop-in symbols use."""
+        L = load_library()
+        L.apa_shared_engine.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        self = cls.__new__(cls)
+        self._L = L
+        self._h = None
+        self._owned = False
+        h = C.c_void_p()
+        _check(L.apa_shared_engine(device, C.byref(h)))
+        self._h = h
+        return self
+
     def close(self):
-        if self._h:
+        if self._h and getattr(self, "_owned", True):
             self._L.apa_engine_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:

@@ -2541,6 +2541,16 @@ static EngineSlot* engine_slot(int device) {  // nullptr on failure (apa_last_er
     return sl;
 }
 
+// The process-wide engine of a device (the one apa_align_batch_multi and the single-pair symbols use), for callers that want
+// their resident batches on the same engine - and so on the same scratch arena - as those calls. Not to be destroyed.
+extern "C" int apa_shared_engine(int device, apa_engine** out) {
+    *out = nullptr;
+    EngineSlot* sl = engine_slot(device);
+    if (!sl) return APA_ERR_NO_DEVICE;
+    *out = sl->eng;
+    return APA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ multi-GPU batch call
 // Pairs are independent (astarpa2/src/lib.rs:50-53 builds a fresh aligner per call): the batch is cut into contiguous shards
 // balanced by bases, one per device, each aligned by that device's engine on its own host thread - no data-path collective

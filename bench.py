@@ -253,7 +253,7 @@ def main():
     # one process per GPU: this rank's threads and page-locked buffers stay on the GPU's NUMA node (APA_BENCH_NUMA=0 turns it off)
     cpus_before = os.sched_getaffinity(0)
     numa_cpus = A.bind_to_device_numa(local_rank) if os.environ.get("APA_BENCH_NUMA", "1") != "0" else 0
-    eng = A.Engine(local_rank)
+    eng = A.Engine.shared(local_rank)  # the engine apa_align_batch_multi runs on: resident and end-to-end steps share one scratch arena
     eff_cells = float(np.sum((a_off[1:] - a_off[:-1]).astype(np.float64) * (b_off[1:] - b_off[:-1])))
     total_bp = float(a_off[-1])
     a_pin, b_pin = A.pinned_copy(a_all), A.pinned_copy(b_all)
@@ -296,6 +296,7 @@ def main():
     digests = A.cigar_digests(pool, off, ln) if trace else None
     d2h_bytes = batch.stats()["d2h_bytes"]
     batch.free_pool(pool)
+    batch.free()  # the end-to-end steps bring their own copy of the batch
     ms_step = kernel_ms / args.steps
 
     # ---- end-to-end through the public multi-GPU batch call with host (page-locked) buffers (e2e): H2D of this step's bases,

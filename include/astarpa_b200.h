@@ -67,6 +67,10 @@ const char* apa_last_error(void);
 int apa_device_count(void);
 
 int apa_engine_create(int device, apa_engine** out);
+/* The process-wide engine of a device - the one apa_align_batch_multi and the single-pair symbols run on - for callers that keep
+ * resident batches next to those calls (one scratch arena instead of two). Owned by the library: do not destroy it, and do
+ * not use it from two threads at once. */
+int apa_shared_engine(int device, apa_engine** out);
 /* One process (or thread) per GPU: bind the calling thread - and with it the packing threads the engine spawns from it and the
  * page-locked buffers it touches first - to the CPUs of the GPU's NUMA node (sysfs local_cpulist of the device, intersected
  * with the caller's current affinity mask). Returns the number of CPUs bound to, 0 if nothing was changed, < 0 on error. */
