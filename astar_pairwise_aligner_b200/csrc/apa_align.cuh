@@ -3,9 +3,10 @@
 //   AstarPa2Instance::{j_range, fixed_j_range, align_for_bounded_dist}   astarpa2/src/domain.rs:77-541
 //   Blocks::{init, compute_next_block, set_last_block_fixed_j_range}     astarpa2/src/blocks.rs:146-569
 //   band::exponential_search + AstarPa2::cost_or_align                   astarpa2/src/band.rs:100-141, lib.rs:122-175
-// Blocks are always recomputed (no reuse_next_block / incremental doubling): the reference itself asserts that
-// both give the same V column (blocks.rs:471-543), and the oracle's differential check confirms it. The
-// reuse *decision* is still tracked because it keeps the old original_j_range (domain.rs:451-455, blocks.rs:190-197).
+// Incremental doubling and block reuse (blocks.rs:190-197,342-469) are built for the second and later passes of a pair
+// (dev_pass<INC = true>): two block stores, the pair's h row, rows the previous pass had fixed are kept. The reference
+// asserts that this gives the same V column as a fresh computation (blocks.rs:471-543); here the parity tests check it
+// (cost, CIGAR and band log equal to the oracle's, which recomputes) together with the count of cells saved.
 #pragma once
 #include "apa_batch.cuh"
 #include "apa_blockdp.cuh"

@@ -112,8 +112,8 @@ KERNELS = ["apa_phase_build_kernel", "apa_phase_pass_kernel", "apa_phase_trace_k
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from the `ncu --set full` captures of the headline
 # shape (astarpa2_full, n=100k, e=5 %, cost+CIGAR), in MB PER PAIR; scaled by the pairs of a launch. Source files are
 # named next to each figure. None for shapes that were not captured.
-NCU_TRAFFIC_MB_PER_PAIR = {  # profiles/r2b_launches_dram.csv (10 000 pairs per launch; round 1: 5.447 / 0.784 / 0.271)
-    "apa_phase_build_kernel": 4.860, "apa_phase_pass_kernel": 0.861, "apa_phase_trace_kernel": 0.272}
+NCU_TRAFFIC_MB_PER_PAIR = {  # profiles/r2c_launches.csv (10 000 pairs per launch; round 1: 5.447 / 0.784 / 0.271)
+    "apa_phase_build_kernel": 4.831, "apa_phase_pass_kernel": 0.863, "apa_phase_trace_kernel": 0.279}
 
 
 def traffic_per_launch(args, kernel):

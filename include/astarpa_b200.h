@@ -90,8 +90,8 @@ int apa_batch_download(apa_engine* e, apa_batch* b, int64_t* costs, char** cigar
 int apa_batch_get_stats(apa_batch* b, apa_batch_stats* out);
 /* Per-pair counters of the last run (the stats surface of AstarPa2StatsAligner::align_with_stats, astarpa2/src/lib.rs:200-208):
  * AstarPa2Stats.f_max_tries (domain.rs:36), h0 = h(0,0) (lib.rs:124), pa_heuristic's num_matches and h_calls (GCSH only, 0
- * otherwise), BlockStats-style computed cells (64 * lanes * cols actually evaluated here: blocks are always recomputed, so
- * this is >= the reference's incremental count), TraceStats.dt_trace_success and fill_tries (trace.rs:3-14). Timers are
+ * otherwise), BlockStats-style computed cells (64 * lanes * cols actually evaluated here; with incremental doubling the kept
+ * rows and reused blocks of later passes are not counted, as in the reference), TraceStats.dt_trace_success and fill_tries (trace.rs:3-14). Timers are
  * per batch (apa_batch_stats), not per pair. */
 typedef struct apa_pair_stats {
     int64_t f_max_tries, h0, num_matches, h_calls, computed_cells, dt_trace_success, fill_tries, reserved;
@@ -170,7 +170,7 @@ typedef struct apa_params {
     int32_t delta;        /* LinearSearch */
     int32_t block_width;  /* 1..256 */
     int32_t sparse;       /* BlockParams.sparse: must be 1 */
-    int32_t incremental_doubling; /* accepted; blocks are always recomputed, which the reference asserts is identical (blocks.rs:471-543) */
+    int32_t incremental_doubling; /* blocks.rs:342-469: later passes keep the rows the previous pass had fixed and reuse unchanged blocks */
     int32_t dt_trace;
     int32_t max_g;        /* 1..40 */
     int32_t fr_drop;      /* 0 disables the x-drop */
