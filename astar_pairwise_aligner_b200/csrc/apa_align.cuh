@@ -5,8 +5,8 @@
 //   band::exponential_search + AstarPa2::cost_or_align                   astarpa2/src/band.rs:100-141, lib.rs:122-175
 // Incremental doubling and block reuse (blocks.rs:190-197,342-469) are built for the second and later passes of a pair
 // (dev_pass<INC = true>): two block stores, the pair's h row, rows the previous pass had fixed are kept. The reference
-// asserts that this gives the same V column as a fresh computation (blocks.rs:471-543); here the parity tests check it
-// (cost, CIGAR and band log equal to the oracle's, which recomputes) together with the count of cells saved.
+// asserts that this gives the same V column as a fresh computation (blocks.rs:471-543); here the parity tests check cost,
+// CIGAR and band log against the oracle and bound the count of computed cells by the oracle's BlockStats count.
 #pragma once
 #include "apa_batch.cuh"
 #include "apa_blockdp.cuh"
