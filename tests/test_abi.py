@@ -32,6 +32,36 @@ def test_no_cpu_fallback(apa):
         A.Engine(0)
 
 
+def test_no_cpu_fallback_shared_engine_and_multi(apa):
+    """The process-wide engine and the multi-GPU entry fail the same way without a device."""
+    import numpy as np
+    import astar_pairwise_aligner_b200 as A
+    if A.load_library().apa_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(A.AstarPaError):
+        A.Engine.shared(0)
+    with pytest.raises(A.AstarPaError):
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)
+        off = np.array([0, 4], dtype=np.int64)
+        A.align_batch_multi([0], seq, off, seq, off)
+
+
+def test_library_holds_sm100a_kernels(apa):
+    """The shipped library carries sm_100a machine code for every kernel DESIGN.md names (static check, no GPU)."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([tool, "-lelf", apa.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in elfs and not re.search(r"sm_(?!100a)\d+", elfs), elfs
+    res = subprocess.run([tool, "-res-usage", apa.lib_path()], capture_output=True, text=True).stdout
+    for k in ("apa_phase_build_kernel", "apa_phase_pass_kernel", "apa_phase_cont_kernel", "apa_phase_trace_kernel",
+              "apa_phase_pass_coop_kernel", "apa_align_kernel_r64", "apa_general_kernel", "apa_pack_kernel", "apa_block_kernel",
+              "apa_search_kernel", "apa_search_trace_kernel", "apa_peak_kernel"):
+        assert k in res, k
+
+
 def test_product_does_not_reference_oracle():
     pkg = os.path.join(ROOT, "astar_pairwise_aligner_b200")
     for dirpath, _, files in os.walk(pkg):
